@@ -1,0 +1,297 @@
+// C ABI of liberd_b200.so (include/erd_b200.h): argument checking, workspace carving and
+// kernel sequencing.  No torch types; every call is asynchronous on the caller's stream.
+#include <stdio.h>
+#include <string.h>
+
+#include "erd_common.cuh"
+
+using namespace erd;
+
+static thread_local char g_err[256] = "";
+
+static int fail(ErdStatus s, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s", what);
+  return (int)s;
+}
+static int fail_cuda(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return (int)ERD_ERR_CUDA;
+}
+
+static int make_geo(const ErdShape* s, Geo* g) {
+  if (!s) return fail(ERD_ERR_NULL, "shape is NULL");
+  if (s->num_levels != kLevels) return fail(ERD_ERR_BAD_SHAPE, "num_levels must be 5");
+  if (s->reg_max != kBins - 1) return fail(ERD_ERR_BAD_SHAPE, "only reg_max=16 is compiled");
+  if (s->num_imgs < 1 || s->num_classes < 2 || s->ori_classes < 1 || s->ori_classes >= s->num_classes)
+    return fail(ERD_ERR_BAD_SHAPE, "need num_imgs>=1 and 1 <= ori_classes < num_classes");
+  if (s->total_gt < 0) return fail(ERD_ERR_BAD_SHAPE, "total_gt < 0");
+  memset(g, 0, sizeof(*g));
+  g->n_img = s->num_imgs;
+  g->C = s->num_classes;
+  g->ori = s->ori_classes;
+  g->cn = s->num_classes - s->ori_classes;
+  g->total_gt = s->total_gt;
+  g->w_cls = s->loss_weight_cls;
+  g->w_bbox = s->loss_weight_bbox;
+  g->w_dfl = s->loss_weight_dfl;
+  g->w_ld = s->loss_weight_ld;
+  g->T = s->kd_temperature;
+  if (!(g->T > 0.f)) return fail(ERD_ERR_BAD_SHAPE, "kd_temperature must be > 0");
+  int a = 0, t = 0;
+  for (int l = 0; l < kLevels; ++l) {
+    if (s->level_h[l] < 1 || s->level_w[l] < 1 || s->stride[l] < 1) return fail(ERD_ERR_BAD_SHAPE, "bad level size");
+    g->h[l] = s->level_h[l];
+    g->w[l] = s->level_w[l];
+    g->hw[l] = s->level_h[l] * s->level_w[l];
+    g->stride[l] = s->stride[l];
+    g->start[l] = a;
+    g->tile_start[l] = t;
+    g->half[l] = 0.5f * (float)s->stride[l] * (s->anchor_scale > 0.f ? s->anchor_scale : 8.0f);
+    g->vec[l] = (g->hw[l] % 4 == 0) ? 1 : 0;
+    a += g->hw[l];
+    t += (g->hw[l] + kTile - 1) / kTile;
+  }
+  g->tile_start[kLevels] = t;
+  g->A = a;
+  g->sel_cap = a / 5 + 1;
+  return ERD_OK;
+}
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void carve(const Geo& g, void* base, Workspace* ws) {
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(bytes);
+    return r;
+  };
+  const size_t NA = (size_t)g.n_img * g.A, NS = (size_t)g.n_img * g.sel_cap;
+  ws->t_m = (float*)take(NA * 4);
+  ws->t_arg = (int*)take(NA * 4);
+  ws->t_u = (float*)take(NA * 4);
+  ws->t_dist = (float4*)take(NA * 16);
+  ws->ers_part = (double*)take((size_t)g.n_img * g.tile_start[kLevels] * 4 * 8);
+  ws->atss_key = (unsigned long long*)take(NA * 8);
+  ws->pos_list = (int*)take(NA * 4);
+  ws->avg_part = (double*)take((size_t)g.n_img * 8);
+  ws->counters = (unsigned int*)take(8 * 4);
+  ws->nms_raw = (float4*)take(NS * 16);
+  ws->nms_cls = (int*)take(NS * 4);
+  ws->nms_box = (float4*)take(NS * 16);
+  ws->nms_order = (int*)take(NS * 4);
+  ws->nms_mask = (unsigned long long*)take(NS * nms_words(g.sel_cap) * 8);
+  ws->loss_acc = (double*)take((size_t)(3 * kLevels + 2 * g.n_img) * 8);
+  ws->bytes = off;
+}
+
+static void set_vec(Geo* g, const float* const* a, const float* const* b = nullptr, float* const* c = nullptr,
+                    float* const* d = nullptr) {
+  for (int l = 0; l < kLevels; ++l) {
+    uintptr_t bits = 0;
+    if (a) bits |= (uintptr_t)a[l];
+    if (b) bits |= (uintptr_t)b[l];
+    if (c) bits |= (uintptr_t)c[l];
+    if (d) bits |= (uintptr_t)d[l];
+    if (bits & 15) g->vec[l] = 0;
+  }
+}
+
+static bool any_null(const void* const* p) {
+  if (!p) return true;
+  for (int l = 0; l < kLevels; ++l)
+    if (!p[l]) return true;
+  return false;
+}
+#define NULLS(x) any_null((const void* const*)(x))
+
+static Ptr5 ptr5(const float* const* p) {
+  Ptr5 r;
+  for (int l = 0; l < kLevels; ++l) r.p[l] = p[l];
+  return r;
+}
+static MPtr5 mptr5(float* const* p) {
+  MPtr5 r;
+  for (int l = 0; l < kLevels; ++l) r.p[l] = p[l];
+  return r;
+}
+
+struct ErdContext {
+  cudaStream_t side[2];
+  cudaEvent_t fork, join[2];
+};
+
+extern "C" {
+
+int erd_abi_version(void) { return ERD_ABI_VERSION; }
+const char* erd_last_error(void) { return g_err; }
+
+int erd_sizes(const ErdShape* shape, ErdSizes* out) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (!out) return fail(ERD_ERR_NULL, "out is NULL");
+  Workspace ws;
+  carve(g, nullptr, &ws);
+  out->anchors_per_img = g.A;
+  out->sel_cap = g.sel_cap;
+  out->num_losses = 3 * kLevels + 2 * g.n_img;
+  out->workspace_bytes = ws.bytes;
+  return ERD_OK;
+}
+
+int erd_create(ErdContext** ctx) {
+  if (!ctx) return fail(ERD_ERR_NULL, "ctx is NULL");
+  ErdContext* c = new ErdContext();
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail_cuda(e, "erd_create");
+  }
+  *ctx = c;
+  return ERD_OK;
+}
+
+int erd_destroy(ErdContext* c) {
+  if (!c) return ERD_OK;
+  for (int i = 0; i < 2; ++i) {
+    cudaStreamDestroy(c->side[i]);
+    cudaEventDestroy(c->join[i]);
+  }
+  cudaEventDestroy(c->fork);
+  delete c;
+  return ERD_OK;
+}
+
+int erd_ers_select(const ErdShape* shape, const float* const* t_cls, const float* const* t_box, int32_t* cls_inds,
+                   int32_t* cls_count, int32_t* box_inds, int32_t* box_count, float* thr, uint8_t* sel_flags,
+                   void* wsp, void* stream) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (NULLS(t_cls) || NULLS(t_box) || !cls_inds || !cls_count || !box_inds || !box_count || !thr || !sel_flags || !wsp)
+    return fail(ERD_ERR_NULL, "erd_ers_select: NULL argument");
+  set_vec(&g, t_cls, t_box);
+  Workspace ws;
+  carve(g, wsp, &ws);
+  cudaError_t e = launch_ers(g, ws, ptr5(t_cls), ptr5(t_box), cls_inds, cls_count, box_inds, box_count, thr,
+                             sel_flags, (cudaStream_t)stream);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_ers_select");
+}
+
+int erd_atss_assign(const ErdShape* shape, const float* gt_boxes, const int64_t* gt_labels,
+                    const int32_t* gt_offsets, const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos, void* wsp,
+                    void* stream) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (!gt_offsets || !pad_hw || !gt_inds || !num_pos || !wsp || (g.total_gt > 0 && (!gt_boxes || !gt_labels)))
+    return fail(ERD_ERR_NULL, "erd_atss_assign: NULL argument");
+  Workspace ws;
+  carve(g, wsp, &ws);
+  cudaError_t e = launch_atss(g, ws, gt_boxes, gt_labels, gt_offsets, pad_hw, gt_inds, num_pos, (cudaStream_t)stream);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_atss_assign");
+}
+
+int erd_avg_factors(const ErdShape* shape, const float* const* s_cls, const int64_t* gt_labels,
+                    const int32_t* gt_offsets, const int32_t* gt_inds, const int32_t* num_pos, float* avg, void* wsp,
+                    void* stream) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (NULLS(s_cls) || !gt_offsets || !gt_inds || !num_pos || !avg || !wsp || (g.total_gt > 0 && !gt_labels))
+    return fail(ERD_ERR_NULL, "erd_avg_factors: NULL argument");
+  Workspace ws;
+  carve(g, wsp, &ws);
+  cudaError_t e = cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned int), (cudaStream_t)stream);
+  if (e == cudaSuccess)
+    e = launch_avg(g, ws, ptr5(s_cls), gt_labels, gt_offsets, gt_inds, num_pos, avg, (cudaStream_t)stream);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_avg_factors");
+}
+
+int erd_teacher_nms(const ErdShape* shape, const int32_t* box_inds, const int32_t* box_count, const int32_t* pad_hw,
+                    float iou_thr, int32_t* keep, int32_t* keep_count, void* wsp, void* stream) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (!box_inds || !box_count || !pad_hw || !keep || !keep_count || !wsp)
+    return fail(ERD_ERR_NULL, "erd_teacher_nms: NULL argument");
+  Workspace ws;
+  carve(g, wsp, &ws);
+  cudaError_t e = launch_nms(g, ws, box_inds, box_count, pad_hw, iou_thr, keep, keep_count, (cudaStream_t)stream);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_teacher_nms");
+}
+
+int erd_loss_fwd_bwd(const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
+                     const float* const* t_cls, const float* const* t_box, const float* gt_boxes,
+                     const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
+                     const int32_t* gt_inds, const int32_t* cls_count, const uint8_t* sel_flags, const int32_t* box_inds,
+                     const int32_t* keep, const int32_t* keep_count, const float* avg, float dist_loss_weight,
+                     const float* upstream, int32_t skip_if_unit_upstream, float* losses, float* const* g_cls,
+                     float* const* g_box, void* wsp, void* stream) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (NULLS(s_cls) || NULLS(s_box) || NULLS(t_cls) || NULLS(t_box) || NULLS(g_cls) || NULLS(g_box) || !gt_offsets ||
+      !pad_hw || !gt_inds || !cls_count || !sel_flags || !box_inds || !keep || !keep_count || !avg || !losses || !wsp ||
+      (g.total_gt > 0 && (!gt_boxes || !gt_labels)))
+    return fail(ERD_ERR_NULL, "erd_loss_fwd_bwd: NULL argument");
+  set_vec(&g, s_cls, s_box, g_cls, g_box);
+  if (g.total_gt > 0 && ((uintptr_t)gt_boxes & 15)) return fail(ERD_ERR_BAD_SHAPE, "gt_boxes must be 16 B aligned");
+  Workspace ws;
+  carve(g, wsp, &ws);
+  LossArgs a;
+  a.s_cls = ptr5(s_cls);
+  a.s_box = ptr5(s_box);
+  a.t_cls = ptr5(t_cls);
+  a.t_box = ptr5(t_box);
+  a.g_cls = mptr5(g_cls);
+  a.g_box = mptr5(g_box);
+  a.gt_boxes = gt_boxes;
+  a.gt_labels = gt_labels;
+  a.gt_offsets = gt_offsets;
+  a.pad_hw = pad_hw;
+  a.gt_inds = gt_inds;
+  a.cls_count = cls_count;
+  a.sel_flags = sel_flags;
+  a.box_inds = box_inds;
+  a.keep = keep;
+  a.keep_count = keep_count;
+  a.avg = avg;
+  a.upstream = upstream;
+  a.skip_flag = (upstream && skip_if_unit_upstream) ? ws.counters + 1 : nullptr;
+  a.losses = losses;
+  a.dlw = dist_loss_weight;
+  cudaError_t e = launch_loss(g, ws, a, (cudaStream_t)stream);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_loss_fwd_bwd");
+}
+
+int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const* t_cls, const float* const* t_box,
+                     const float* const* s_cls, const float* gt_boxes, const int64_t* gt_labels,
+                     const int32_t* gt_offsets, const int32_t* pad_hw, float iou_thr, const ErdStepBuffers* b,
+                     void* wsp, void* stream) {
+  if (!ctx || !b) return fail(ERD_ERR_NULL, "erd_step_prepare: NULL ctx/buffers");
+  cudaStream_t main = (cudaStream_t)stream;
+  // fork: ATSS + avg factors run beside the teacher pass; join before returning
+  cudaError_t e = cudaEventRecord(ctx->fork, main);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[0], ctx->fork, 0);
+  if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork");
+  int rc = erd_atss_assign(shape, gt_boxes, gt_labels, gt_offsets, pad_hw, b->gt_inds, b->num_pos, wsp, ctx->side[0]);
+  if (!rc) rc = erd_avg_factors(shape, s_cls, gt_labels, gt_offsets, b->gt_inds, b->num_pos, b->avg, wsp, ctx->side[0]);
+  if (!rc)
+    rc = erd_ers_select(shape, t_cls, t_box, b->cls_inds, b->cls_count, b->box_inds, b->box_count, b->thr,
+                        b->sel_flags, wsp, main);
+  if (!rc) rc = erd_teacher_nms(shape, b->box_inds, b->box_count, pad_hw, iou_thr, b->keep, b->keep_count, wsp, main);
+  e = cudaEventRecord(ctx->join[0], ctx->side[0]);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ctx->join[0], 0);
+  if (rc) return rc;
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_step_prepare join");
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// Shared device/host definitions for the erd_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/erd_b200.h"
+
+namespace erd {
+
+constexpr int kLevels = 5;
+constexpr int kBins = 17;             // reg_max + 1
+constexpr int kBoxCh = 4 * kBins;     // 68 box-distribution channels
+constexpr int kTile = 512;            // anchors per CTA in the streaming kernels
+constexpr int kTileThreads = 128;     // 4 anchors per thread
+constexpr int kTopK = 9;              // ATSSAssigner topk (config train_cfg.assigner)
+constexpr float kEps32 = 1.1920928955078125e-07f;  // torch.finfo(float32).eps
+
+struct Ptr5 {
+  const float* p[kLevels];
+};
+struct MPtr5 {
+  float* p[kLevels];
+};
+
+// Static geometry of a batch, passed by value to every kernel.
+struct Geo {
+  int n_img, C, ori, cn, A;
+  int h[kLevels], w[kLevels], hw[kLevels], stride[kLevels], start[kLevels];
+  int tile_start[kLevels + 1];  // prefix sum of ceil(hw/kTile): CTA index -> level
+  int vec[kLevels];             // 1 when hw % 4 == 0 and all level pointers are 16 B aligned
+  float half[kLevels];          // anchor half size = 0.5 * stride * scale
+  int sel_cap;                  // A/5 + 1
+  int total_gt;
+  float w_cls, w_bbox, w_dfl, w_ld, T;   // loss weights and KD temperature
+};
+
+// Device workspace carved from the caller's buffer (see workspace.cu).
+struct Workspace {
+  float* t_m;                     // [N][A] teacher max_c sigmoid(cls)
+  int* t_arg;                     // [N][A] teacher argmax class
+  float* t_u;                     // [N][A] teacher max raw box logit
+  float4* t_dist;                 // [N][A] teacher softmax-integral distances (l,t,r,b), bin units
+  double* ers_part;               // [N][tiles][4] per-CTA sums: m, m^2, u, u^2
+  unsigned long long* atss_key;   // [N][A] packed (iou bits << 32 | ~gt) argmax table
+  int* pos_list;                  // [N][A] anchors with an assigned GT (unordered)
+  double* avg_part;               // [N] per-image sum of positive weights
+  unsigned int* counters;         // [8] last-block tickets
+  float4* nms_raw;                // [N][sel_cap] decoded teacher boxes in list order
+  int* nms_cls;                   // [N][sel_cap] class ids in list order
+  float4* nms_box;                // [N][sel_cap] offset boxes in score order
+  int* nms_order;                 // [N][sel_cap] list position of each score-ordered box
+  unsigned long long* nms_mask;   // [N][sel_cap][W] suppression bit matrix, W = ceil(sel_cap/64)
+  double* loss_acc;               // [3L + 2N]
+  size_t bytes;
+};
+
+inline __host__ __device__ int nms_words(int sel_cap) { return (sel_cap + 63) / 64; }
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ int level_of_tile(const Geo& g, int tile) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < kLevels; ++i) l += (tile >= g.tile_start[i]) ? 1 : 0;
+  return l;
+}
+
+__device__ __forceinline__ int level_of_anchor(const Geo& g, int a) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < kLevels; ++i) l += (a >= g.start[i]) ? 1 : 0;
+  return l;
+}
+
+// torch.sigmoid on fp32 is 1/(1+exp(-x)) evaluated in fp32 (ATen UnaryOpsKernel); the
+// index-critical statistics (ERS, weights) use the same formula with IEEE ops.
+__device__ __forceinline__ float sigmoid_ref(float x) {
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Four anchors per thread.  VEC: four consecutive hw positions (one 16 B access per
+// channel); otherwise positions tid, tid+128, tid+256, tid+384 of the tile (coalesced 4 B).
+template <bool VEC>
+struct Quad {
+  int hw[4];
+  bool ok[4];
+  __device__ __forceinline__ Quad(int hw0, int limit) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      hw[k] = VEC ? hw0 + (int)threadIdx.x * 4 + k : hw0 + (int)threadIdx.x + kTileThreads * k;
+      ok[k] = hw[k] < limit;
+    }
+  }
+  // plane points at hw = 0 of one (image, channel) plane
+  __device__ __forceinline__ void load(const float* __restrict__ plane, float (&v)[4], float fill) const {
+    if (VEC) {
+      if (ok[0]) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(plane + hw[0]));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+        v[0] = v[1] = v[2] = v[3] = fill;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = ok[k] ? __ldg(plane + hw[k]) : fill;
+    }
+  }
+  __device__ __forceinline__ void store(float* __restrict__ plane, const float (&v)[4]) const {
+    if (VEC) {
+      if (ok[0]) __stcs(reinterpret_cast<float4*>(plane + hw[0]), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ok[k]) __stcs(plane + hw[k], v[k]);
+    }
+  }
+  __device__ __forceinline__ void store_zero(float* __restrict__ plane) const {
+    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+    store(plane, z);
+  }
+};
+
+// ---------------------------------------------------------------- host launchers (one per .cu)
+struct StepIO;  // api.cu
+
+cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box,
+                       int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds, int32_t* box_count,
+                       float* thr, uint8_t* sel_flags, cudaStream_t st);
+cudaError_t launch_atss(const Geo& g, const Workspace& ws, const float* gt_boxes, const int64_t* gt_labels,
+                        const int32_t* gt_offsets, const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos,
+                        cudaStream_t st);
+cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const int64_t* gt_labels,
+                       const int32_t* gt_offsets, const int32_t* gt_inds, const int32_t* num_pos, float* avg,
+                       cudaStream_t st);
+cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_inds, const int32_t* box_count,
+                       const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count, cudaStream_t st);
+
+struct LossArgs {
+  Ptr5 s_cls, s_box, t_cls, t_box;
+  MPtr5 g_cls, g_box;
+  const float* gt_boxes;
+  const int64_t* gt_labels;
+  const int32_t* gt_offsets;
+  const int32_t* pad_hw;
+  const int32_t* gt_inds;
+  const int32_t* cls_count;
+  const uint8_t* sel_flags;
+  const int32_t* box_inds;
+  const int32_t* keep;
+  const int32_t* keep_count;
+  const float* avg;
+  const float* upstream;
+  const unsigned int* skip_flag;   // non-NULL: kernels return at once when *skip_flag == 0
+  float* losses;
+  float dlw;
+};
+cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st);
+
+}  // namespace erd

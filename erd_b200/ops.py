@@ -1,0 +1,226 @@
+"""Torch-facing wrappers over the C ABI: device memory, streams and the all-reduce.
+
+PyTorch is plumbing here (allocation, current stream, ``torch.distributed``); all
+arithmetic happens in liberd_b200.so.  There is no CPU path: tensors must be CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+
+STRIDES = (8, 16, 32, 64, 128)
+
+
+def _ptrs(ts: Sequence[torch.Tensor]):
+    return N.PtrArray(*[t.data_ptr() for t in ts])
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_level_tensors(name: str, ts: Sequence[torch.Tensor], n: int, ch: int, shapes):
+    if len(ts) != len(shapes):
+        raise AssertionError(f'{name}: expected {len(shapes)} levels, got {len(ts)}')
+    for t, (h, w) in zip(ts, shapes):
+        if not t.is_cuda:
+            raise RuntimeError(f'{name} must be CUDA tensors (erd_b200 has no CPU path)')
+        if t.dtype != torch.float32 or tuple(t.shape) != (n, ch, h, w):
+            raise AssertionError(f'{name}: expected float32 {(n, ch, h, w)}, got {t.dtype} {tuple(t.shape)}')
+
+
+class Plan:
+    """Buffers for one static batch geometry on one device (reused across steps)."""
+
+    def __init__(self, key, device):
+        n, shapes, num_classes, ori, reg_max, strides, scale, weights = key
+        self.key, self.device = key, device
+        self.n, self.shapes, self.C, self.ori, self.reg_max = n, shapes, num_classes, ori, reg_max
+        self.shape = N.ErdShape()
+        self.shape.num_imgs, self.shape.num_levels = n, len(shapes)
+        self.shape.num_classes, self.shape.ori_classes, self.shape.reg_max = num_classes, ori, reg_max
+        for l in range(min(len(shapes), N.MAX_LEVELS)):
+            self.shape.level_h[l], self.shape.level_w[l] = shapes[l]
+            self.shape.stride[l] = strides[l]
+        self.shape.total_gt = 0
+        self.shape.anchor_scale = scale
+        (self.shape.loss_weight_cls, self.shape.loss_weight_bbox, self.shape.loss_weight_dfl,
+         self.shape.loss_weight_ld, self.shape.kd_temperature) = weights
+        sizes = N.ErdSizes()
+        N.check(N.load().erd_sizes(C.byref(self.shape), C.byref(sizes)), 'erd_sizes')
+        self.A, self.sel_cap = int(sizes.anchors_per_img), int(sizes.sel_cap)
+        self.num_losses = int(sizes.num_losses)
+        i32 = dict(dtype=torch.int32, device=device)
+        self.ws = torch.empty(int(sizes.workspace_bytes), dtype=torch.uint8, device=device)
+        self.cls_inds = torch.empty(n, self.sel_cap, **i32)
+        self.box_inds = torch.empty(n, self.sel_cap, **i32)
+        self.keep = torch.empty(n, self.sel_cap, **i32)
+        self.cls_count = torch.zeros(n, **i32)
+        self.box_count = torch.zeros(n, **i32)
+        self.keep_count = torch.zeros(n, **i32)
+        self.num_pos = torch.zeros(n, **i32)
+        self.gt_inds = torch.empty(n, self.A, **i32)
+        self.thr = torch.empty(n, 2, dtype=torch.float32, device=device)
+        self.sel_flags = torch.zeros(n, self.A, dtype=torch.uint8, device=device)
+        self.avg = torch.zeros(2, dtype=torch.float32, device=device)
+        self.meta = torch.zeros(3 * n + 1, **i32)            # gt_offsets (n+1) | pad_hw (2n)
+        self.meta_host = torch.zeros(3 * n + 1, dtype=torch.int32).pin_memory()
+        self.gt_boxes = torch.zeros(1, 4, dtype=torch.float32, device=device)
+        self.gt_labels = torch.zeros(1, dtype=torch.int64, device=device)
+        self.bufs = N.ErdStepBuffers(
+            self.cls_inds.data_ptr(), self.cls_count.data_ptr(), self.box_inds.data_ptr(),
+            self.box_count.data_ptr(), self.thr.data_ptr(), self.sel_flags.data_ptr(), self.gt_inds.data_ptr(),
+            self.num_pos.data_ptr(),
+            self.keep.data_ptr(), self.keep_count.data_ptr(), self.avg.data_ptr())
+
+    @property
+    def gt_offsets(self):
+        return self.meta[:self.n + 1]
+
+    @property
+    def pad_hw(self):
+        return self.meta[self.n + 1:]
+
+    def set_targets(self, gt_bboxes: Sequence[torch.Tensor], gt_labels: Sequence[torch.Tensor],
+                    pad_shapes: Sequence[Tuple[int, int]]):
+        """Pack per-image GT into CSR form and upload offsets + pad shapes in one copy."""
+        n = self.n
+        if not (len(gt_bboxes) == len(gt_labels) == len(pad_shapes) == n):
+            raise AssertionError('gt / meta list lengths must equal the batch size')   # gfl_head.py:518
+        off = 0
+        for i in range(n):
+            self.meta_host[i] = off
+            off += int(gt_bboxes[i].shape[0])
+            ph, pw = int(pad_shapes[i][0]), int(pad_shapes[i][1])
+            if ph < 1 or pw < 1:
+                # reference: ValueError when an image has no valid anchor (gfl_head.py:613-617)
+                raise ValueError('There is no valid anchor inside the image boundary.')
+            self.meta_host[n + 1 + 2 * i] = ph
+            self.meta_host[n + 2 + 2 * i] = pw
+        self.meta_host[n] = off
+        self.meta.copy_(self.meta_host, non_blocking=True)
+        self.shape.total_gt = off
+        if off > 0:
+            self.gt_boxes = torch.cat([b.reshape(-1, 4) for b in gt_bboxes]).to(
+                device=self.device, dtype=torch.float32).contiguous()
+            self.gt_labels = torch.cat([l.reshape(-1) for l in gt_labels]).to(
+                device=self.device, dtype=torch.int64).contiguous()
+
+
+class ErdPath:
+    """The hot path behind the reference's ``sel_pos`` / ``loss_by_feat`` (one per process)."""
+
+    def __init__(self, strides: Sequence[int] = STRIDES, anchor_scale: float = 8.0, nms_iou_thr: float = 0.005,
+                 loss_weights: Tuple[float, float, float, float] = (1.0, 2.0, 0.25, 0.25), kd_T: float = 10.0):
+        """loss_weights = (QFL, GIoU, DFL, LD) loss_weight values of the head config."""
+        self.lib = N.load()
+        self.weights = tuple(float(w) for w in loss_weights) + (float(kd_T),)
+        self.strides, self.anchor_scale, self.nms_iou_thr = tuple(strides), float(anchor_scale), float(nms_iou_thr)
+        self._plans: Dict[tuple, Plan] = {}
+        self._ctx: Dict[int, C.c_void_p] = {}
+
+    def _context(self, device) -> C.c_void_p:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in self._ctx:
+            ctx = C.c_void_p()
+            with torch.cuda.device(idx):
+                N.check(self.lib.erd_create(C.byref(ctx)), 'erd_create')
+            self._ctx[idx] = ctx
+        return self._ctx[idx]
+
+    def plan(self, s_or_t_cls: Sequence[torch.Tensor], num_classes: int, ori: int, reg_max: int = 16) -> Plan:
+        t0 = s_or_t_cls[0]
+        if not t0.is_cuda:
+            raise RuntimeError('erd_b200 runs on CUDA tensors only; there is no CPU fallback')
+        shapes = tuple((int(t.shape[2]), int(t.shape[3])) for t in s_or_t_cls)
+        key = (int(t0.shape[0]), shapes, int(num_classes), int(ori), int(reg_max), self.strides, self.anchor_scale,
+               self.weights)
+        full = key + (t0.device,)
+        if full not in self._plans:
+            self._plans[full] = Plan(key, t0.device)
+        return self._plans[full]
+
+    # ---- individual stages (used by the parity tests and by sel_pos) -----------------
+    def ers_select(self, p: Plan, t_cls, t_box):
+        _check_level_tensors('teacher cls_scores', t_cls, p.n, p.ori, p.shapes)
+        _check_level_tensors('teacher bbox_preds', t_box, p.n, 4 * (p.reg_max + 1), p.shapes)
+        N.check(self.lib.erd_ers_select(C.byref(p.shape), _ptrs(t_cls), _ptrs(t_box), p.cls_inds.data_ptr(),
+                                        p.cls_count.data_ptr(), p.box_inds.data_ptr(), p.box_count.data_ptr(),
+                                        p.thr.data_ptr(), p.sel_flags.data_ptr(), p.ws.data_ptr(), _stream()),
+                'erd_ers_select')
+
+    def atss_assign(self, p: Plan):
+        N.check(self.lib.erd_atss_assign(C.byref(p.shape), p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(),
+                                         p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(), p.gt_inds.data_ptr(),
+                                         p.num_pos.data_ptr(), p.ws.data_ptr(), _stream()), 'erd_atss_assign')
+
+    def avg_factors(self, p: Plan, s_cls):
+        N.check(self.lib.erd_avg_factors(C.byref(p.shape), _ptrs(s_cls), p.gt_labels.data_ptr(),
+                                         p.gt_offsets.data_ptr(), p.gt_inds.data_ptr(), p.num_pos.data_ptr(),
+                                         p.avg.data_ptr(), p.ws.data_ptr(), _stream()), 'erd_avg_factors')
+
+    def teacher_nms(self, p: Plan):
+        N.check(self.lib.erd_teacher_nms(C.byref(p.shape), p.box_inds.data_ptr(), p.box_count.data_ptr(),
+                                         p.pad_hw.data_ptr(), self.nms_iou_thr, p.keep.data_ptr(),
+                                         p.keep_count.data_ptr(), p.ws.data_ptr(), _stream()), 'erd_teacher_nms')
+
+    def reduce_avg(self, p: Plan):
+        """reduce_mean of both normalisers in one 8-byte all-reduce (dist_utils.py:59-65)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            p.avg.div_(dist.get_world_size())
+            dist.all_reduce(p.avg, op=dist.ReduceOp.SUM)
+
+    def loss_fwd_bwd(self, p: Plan, t_cls, t_box, s_cls, s_box, g_cls, g_box, losses, dist_loss_weight: float,
+                     upstream: Optional[torch.Tensor] = None, skip_if_unit: bool = False):
+        N.check(self.lib.erd_loss_fwd_bwd(
+            C.byref(p.shape), _ptrs(s_cls), _ptrs(s_box), _ptrs(t_cls), _ptrs(t_box), p.gt_boxes.data_ptr(),
+            p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(), p.gt_inds.data_ptr(),
+            p.cls_count.data_ptr(), p.sel_flags.data_ptr(), p.box_inds.data_ptr(), p.keep.data_ptr(),
+            p.keep_count.data_ptr(), p.avg.data_ptr(), float(dist_loss_weight),
+            upstream.data_ptr() if upstream is not None else None, 1 if skip_if_unit else 0,
+            losses.data_ptr(), _ptrs(g_cls), _ptrs(g_box), p.ws.data_ptr(), _stream()), 'erd_loss_fwd_bwd')
+
+    # ---- fused step -------------------------------------------------------------------
+    def prepare(self, p: Plan, t_cls, t_box, s_cls):
+        N.check(self.lib.erd_step_prepare(
+            self._context(p.device), C.byref(p.shape), _ptrs(t_cls), _ptrs(t_box), _ptrs(s_cls),
+            p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(),
+            self.nms_iou_thr, C.byref(p.bufs), p.ws.data_ptr(), _stream()), 'erd_step_prepare')
+
+    def step(self, t_cls, t_box, s_cls, s_box, gt_bboxes, gt_labels, pad_shapes, num_classes: int, ori: int,
+             reg_max: int = 16, dist_loss_weight: float = 1.0, upstream: Optional[torch.Tensor] = None,
+             g_cls: Optional[List[torch.Tensor]] = None, g_box: Optional[List[torch.Tensor]] = None,
+             targets_set: bool = False):
+        """ERS + assignment + NMS + fused loss forward/backward.
+        Returns (plan, losses (3L+2N,), g_cls[5], g_box[5])."""
+        p = self.plan(s_cls, num_classes, ori, reg_max)
+        _check_level_tensors('cls_scores', s_cls, p.n, p.C, p.shapes)
+        _check_level_tensors('bbox_preds', s_box, p.n, 4 * (p.reg_max + 1), p.shapes)
+        _check_level_tensors('teacher cls_scores', t_cls, p.n, p.ori, p.shapes)
+        _check_level_tensors('teacher bbox_preds', t_box, p.n, 4 * (p.reg_max + 1), p.shapes)
+        if not targets_set:
+            p.set_targets(gt_bboxes, gt_labels, pad_shapes)
+        if g_cls is None:
+            g_cls = [torch.empty_like(t) for t in s_cls]
+        if g_box is None:
+            g_box = [torch.empty_like(t) for t in s_box]
+        losses = torch.empty(p.num_losses, dtype=torch.float32, device=p.device)
+        self.prepare(p, t_cls, t_box, s_cls)
+        self.reduce_avg(p)
+        self.loss_fwd_bwd(p, t_cls, t_box, s_cls, s_box, g_cls, g_box, losses, dist_loss_weight, upstream)
+        return p, losses, g_cls, g_box
+
+
+_default_path: Optional[ErdPath] = None
+
+
+def default_path() -> ErdPath:
+    global _default_path
+    if _default_path is None:
+        _default_path = ErdPath()
+    return _default_path

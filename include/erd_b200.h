@@ -1,0 +1,181 @@
+/*
+ * erd_b200 -- C ABI of the B200-native GFL + Elastic Response Distillation loss path.
+ *
+ * The reference (Hi-FT/ERD, an MMDetection 3.0.0 fork) is pure Python and has no FFI of
+ * its own; each entry point below names the reference Python interface (file:line under
+ * the reference root) whose work it replaces.  INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - Plain C: raw device pointers, sizes, an opaque cudaStream_t passed as void*.
+ *  - All tensors are borrowed for the duration of the call and must live on the device
+ *    that is current when the call is made.  Nothing is allocated inside the library
+ *    except in erd_create(); outputs and the workspace are caller-allocated.
+ *  - Every call is asynchronous on `stream`; no call synchronises the device.
+ *  - Return value: ERD_OK (0) or a negative ErdStatus.  Nothing throws.
+ *  - Head outputs are contiguous fp32 NCHW per pyramid level, exactly what
+ *    GFLHead.forward emits (mmdet/models/dense_heads/gfl_head.py:205-230).
+ *  - Anchor numbering inside an image: level 0 first, row-major (y * W_l + x), as produced
+ *    by AnchorGenerator.grid_priors (task_modules/prior_generators/anchor_generator.py:230-301).
+ */
+#ifndef ERD_B200_H_
+#define ERD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ERD_MAX_LEVELS 5
+#define ERD_ABI_VERSION 1
+
+typedef enum ErdStatus {
+  ERD_OK = 0,
+  ERD_ERR_BAD_SHAPE = -1,     /* unsupported level count / reg_max / class split          */
+  ERD_ERR_NULL = -2,          /* a required pointer is NULL                               */
+  ERD_ERR_WORKSPACE = -3,     /* workspace smaller than erd_workspace_bytes()             */
+  ERD_ERR_CUDA = -4,          /* a CUDA runtime call or launch failed (see erd_last_error) */
+  ERD_ERR_NO_VALID_ANCHOR = -5 /* gfl_head.py:613-617 ValueError, detected on the host from pad_hw */
+} ErdStatus;
+
+/* Static description of one batch.  Mirrors the config keys of
+ * configs/gfl_increment/gfl_r50_fpn_1x_coco_first_40_incre_last_40_cats.py:57-90. */
+typedef struct ErdShape {
+  int32_t num_imgs;                   /* N images on this rank                              */
+  int32_t num_levels;                 /* must be 5 (strides 8..128)                         */
+  int32_t num_classes;                /* C  student classes (80)                            */
+  int32_t ori_classes;                /* ori teacher classes (40 or 70); new = C - ori      */
+  int32_t reg_max;                    /* 16 -> 17 bins per side; only 16 is compiled        */
+  int32_t level_h[ERD_MAX_LEVELS];    /* feature-map heights                                */
+  int32_t level_w[ERD_MAX_LEVELS];    /* feature-map widths                                 */
+  int32_t stride[ERD_MAX_LEVELS];     /* 8,16,32,64,128 (square strides)                    */
+  int32_t total_gt;                   /* number of rows of gt_boxes (sum over images)       */
+  float anchor_scale;                 /* octave_base_scale * 2**0 = 8                       */
+  float loss_weight_cls;              /* QualityFocalLoss loss_weight (1.0), beta fixed at 2 */
+  float loss_weight_bbox;             /* GIoULoss loss_weight (2.0), eps 1e-6               */
+  float loss_weight_dfl;              /* DistributionFocalLoss loss_weight (0.25)           */
+  float loss_weight_ld;               /* KnowledgeDistillationKLDivLoss loss_weight (0.25)  */
+  float kd_temperature;               /* T (10)                                             */
+} ErdShape;
+
+/* Derived sizes a caller needs to allocate outputs. */
+typedef struct ErdSizes {
+  int64_t anchors_per_img;  /* A = sum_l H_l * W_l                                          */
+  int64_t sel_cap;          /* per-image capacity of every ERS / NMS index list: A/5 + 1
+                               (mean + 2 std selects at most A/5 rows, Cantelli)            */
+  int64_t num_losses;       /* 3 * L + 2 * N: loss_cls[L], loss_bbox[L], loss_dfl[L],
+                               loss_dist_cls[N], loss_dist_bbox[N]                          */
+  size_t workspace_bytes;
+} ErdSizes;
+
+typedef struct ErdContext ErdContext; /* per-device helper streams/events (erd_create) */
+
+int erd_abi_version(void);
+const char* erd_last_error(void);
+
+/* Sizes and workspace requirement for a shape. */
+int erd_sizes(const ErdShape* shape, ErdSizes* out);
+
+int erd_create(ErdContext** ctx);
+int erd_destroy(ErdContext* ctx);
+
+/* Elastic Response Selection.
+ * Replaces GFLIncrementERD.sel_pos / sel_pos_single
+ * (mmdet/models/detectors/gfl_increment_erd.py:143-200).
+ * t_cls[l]: (N, ori, H_l, W_l); t_box[l]: (N, 4*(reg_max+1), H_l, W_l).
+ * Outputs, ascending anchor indices per image: cls_inds/box_inds (N, sel_cap) int32 with
+ * device-side counts (N,) int32.  Also fills the per-anchor teacher cache in `ws`
+ * (max sigmoid score, argmax class, max raw box logit, softmax-integral distances) that
+ * erd_teacher_nms and erd_loss_fwd_bwd consume, `thr` (N,2) fp32 thresholds and
+ * `sel_flags` (N, A) uint8: bit 0 = row in cls_inds, bit 1 = row in box_inds. */
+int erd_ers_select(const ErdShape* shape, const float* const* t_cls, const float* const* t_box,
+                   int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds, int32_t* box_count,
+                   float* thr, uint8_t* sel_flags, void* ws, void* stream);
+
+/* Anchors, valid flags, ATSS assignment, pseudo sampling.
+ * Replaces AnchorHead.get_anchors (dense_heads/anchor_head.py:164-199),
+ * GFLHead.get_targets/_get_targets_single (dense_heads/gfl_head.py:504-679),
+ * ATSSAssigner.assign (task_modules/assigners/atss_assigner.py:74-254) and
+ * PseudoSampler.sample (task_modules/samplers/pseudo_sampler.py:26-60).
+ * gt_boxes (total_gt,4) fp32 xyxy px; gt_labels (total_gt,) int64; gt_offsets (N+1,) int32
+ * CSR offsets; pad_hw (N,2) int32 = img_meta['pad_shape'][:2].
+ * Outputs: gt_inds (N, A) int32: -1 anchor outside pad_shape (label_weight 0), 0 background,
+ * k>0 assigned to the k-th GT of its image (1-based); num_pos (N,) int32. */
+int erd_atss_assign(const ErdShape* shape, const float* gt_boxes, const int64_t* gt_labels,
+                    const int32_t* gt_offsets, const int32_t* pad_hw, int32_t* gt_inds,
+                    int32_t* num_pos, void* ws, void* stream);
+
+/* The two normalisers of the GT losses, left on the device for one 8-byte all-reduce.
+ * Replaces the reduce_mean operands of gfl_head_increment_erd.py:390-391 and :406-407
+ * (mmdet/utils/dist_utils.py:59-65): avg[0] = sum_img max(num_pos,1),
+ * avg[1] = sum over positives of max_c sigmoid(student new-class logits).
+ * The caller divides by world size, all-reduces (SUM) and hands the buffer to
+ * erd_loss_fwd_bwd, which applies clamp(min=1) to avg[1]. */
+int erd_avg_factors(const ErdShape* shape, const float* const* s_cls, const int64_t* gt_labels,
+                    const int32_t* gt_offsets, const int32_t* gt_inds, const int32_t* num_pos,
+                    float* avg, void* ws, void* stream);
+
+/* Teacher box decode + class-aware greedy IoU-NMS (threshold `iou_thr`, 0.005 in the
+ * reference) over the ERS-selected rows.  Replaces the mmcv.ops.batched_nms call and the
+ * decode in GFLHeadIncrementERD.distill_loss_by_image_single
+ * (dense_heads/gfl_head_increment_erd.py:189-202).  Needs the teacher cache written by
+ * erd_ers_select.  keep (N, sel_cap) int32 holds positions into the image's box_inds list
+ * in descending-score order (what batched_nms returns); keep_count (N,) int32. */
+int erd_teacher_nms(const ErdShape* shape, const int32_t* box_inds, const int32_t* box_count,
+                    const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count,
+                    void* ws, void* stream);
+
+/* Fused forward + backward of QFL / GIoU / DFL and both distillation losses.
+ * Replaces GFLHeadIncrementERD.loss_by_feat_single, distill_loss_by_image_single and the
+ * glue of loss_by_feat (dense_heads/gfl_head_increment_erd.py:142-454) together with
+ * quality_focal_loss / distribution_focal_loss (losses/gfocal_loss.py:12-53,143-165),
+ * giou_loss (losses/iou_loss.py:110-126), knowledge_distillation_kl_div_loss
+ * (losses/kd_loss.py:12-37) and weight_reduce_loss (losses/utils.py:30-65), and their
+ * autograd backward.
+ * upstream: NULL (every loss term has upstream gradient 1, what mmengine parse_losses
+ * produces) or (num_losses,) fp32 per-term upstream gradients on the device.
+ * skip_if_unit_upstream: when non-zero (and upstream != NULL) the call is a device-side
+ * no-op if every upstream value equals 1 -- the autograd backward uses this to re-derive
+ * gradients only when the caller weighted the loss terms, without a host sync.
+ * losses: (num_losses,) fp32 in the order of ErdSizes.num_losses.
+ * g_cls[l] (N,C,H_l,W_l) / g_box[l] (N,4*(reg_max+1),H_l,W_l): dense NCHW gradients,
+ * fully overwritten. */
+int erd_loss_fwd_bwd(const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
+                     const float* const* t_cls, const float* const* t_box, const float* gt_boxes,
+                     const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
+                     const int32_t* gt_inds, const int32_t* cls_count, const uint8_t* sel_flags,
+                     const int32_t* box_inds, const int32_t* keep, const int32_t* keep_count,
+                     const float* avg, float dist_loss_weight, const float* upstream,
+                     int32_t skip_if_unit_upstream, float* losses, float* const* g_cls, float* const* g_box, void* ws,
+                     void* stream);
+
+/* One training-step worth of the path in two calls around the caller's all-reduce:
+ * erd_step_prepare = erd_ers_select + erd_atss_assign + erd_avg_factors + erd_teacher_nms
+ * (forked over the context's helper streams, joined back into `stream`);
+ * erd_step_loss = erd_loss_fwd_bwd.  Replaces GFLIncrementERD.loss
+ * (detectors/gfl_increment_erd.py:202-220) minus the conv stacks. */
+typedef struct ErdStepBuffers {
+  int32_t* cls_inds;
+  int32_t* cls_count;
+  int32_t* box_inds;
+  int32_t* box_count;
+  float* thr;
+  uint8_t* sel_flags;
+  int32_t* gt_inds;
+  int32_t* num_pos;
+  int32_t* keep;
+  int32_t* keep_count;
+  float* avg;
+} ErdStepBuffers;
+
+int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const* t_cls,
+                     const float* const* t_box, const float* const* s_cls, const float* gt_boxes,
+                     const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
+                     float iou_thr, const ErdStepBuffers* buf, void* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERD_B200_H_ */
