@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the GFL+ERD loss path (BASELINE.json metric: anchors/s, loss fwd+bwd).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+
+One "step" = ERS selection + ATSS assignment + avg-factor all-reduce + teacher NMS + fused
+QFL/GIoU/DFL/distillation forward and backward over one batch of synthetic head outputs
+(BASELINE.json configs[1]: 40+40 split, 16 images/GPU, 800x1333 -> 22 400 anchors/image).
+Prints ONE JSON line on rank 0.  Under torchrun every rank owns its own 16 images (weak
+scaling); the only collective is the 8-byte avg-factor all-reduce (NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'anchors_per_sec_gfl_erd_loss_fwd_bwd'
+UNIT = 'anchors/s'
+IMG_HW = (800, 1333)
+IMGS_PER_GPU = 16
+ORI, NUM_CLASSES, REG_MAX = 40, 80, 16
+# compulsory fp32 traffic per anchor, fwd+bwd, 40+40 split
+BYTES_PER_ANCHOR = {'path': 1616, 'loss_main': 4 * (80 + 68) * 2, 'ers_scan': 4 * (40 + 68)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--imgs', type=int, default=IMGS_PER_GPU)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def make_inputs(n_imgs, seed):
+    from erd_b200.synth import make_batch
+    return make_batch(n_imgs, IMG_HW, ori=ORI, num_classes=NUM_CLASSES, reg_max=REG_MAX, seed=seed)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """SM clock / throttle-reason samples taken through NVML while the timed region runs
+    (2 ms period, so even a 20 ms region gets samples; nvidia-smi -lms cannot go that fast)."""
+
+    def __init__(self, index):
+        self.index, self.sm, self.mx, self.reasons, self.err = index, [], None, set(), None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'hw_thermal_slowdown': 0x40,
+                     'sw_thermal_slowdown': 0x20, 'hw_power_brake_slowdown': 0x80}
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for nm, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(nm)
+                    except Exception as e:  # keep sampling
+                        self.err = repr(e)
+                    time.sleep(0.002)
+            self._thr = threading.Thread(target=loop, daemon=True)
+            self._thr.start()
+        except Exception as e:
+            self.err = repr(e)
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        out = {'sm_mhz': statistics.median(self.sm) if self.sm else None, 'sm_max_mhz': self.mx,
+               'samples': len(self.sm), 'reasons': sorted(self.reasons)}
+        if self.err:
+            out['error'] = self.err
+        return out
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def time_cpu_oracle(n_imgs, iters, warmup, seed=1234):
+    """The oracle port (torch CPU, all host threads) on a bounded sample of the workload."""
+    from oracle import erd_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    b = make_inputs(n_imgs, seed)
+    times = []
+    for it in range(warmup + iters):
+        s_cls = [t.clone().requires_grad_() for t in b.s_cls]
+        s_box = [t.clone().requires_grad_() for t in b.s_box]
+        t0 = time.perf_counter()
+        O.erd_step(b.t_cls, b.t_box, s_cls, s_box, b.gt_bboxes, b.gt_labels, b.pad_shapes, b.ori,
+                   1.0, b.num_classes, b.reg_max)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    anchors = n_imgs * b.anchors_per_image
+    return anchors, times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    n_sample = min(2, args.imgs)
+    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    anchors, times, cores = time_cpu_oracle(n_sample, steps, warm)
+    ms = 1e3 * sum(times) / len(times)
+    val = anchors / (sum(times) / len(times))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'GFL R50-FPN 40+40 ERD loss fwd+bwd, {args.imgs} img/GPU 800x1333, 80-class head, '
+                               f'reg_max=16', 'sample': f'{n_sample} of {args.imgs} images per step'},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{n_sample} images x 22400 anchors per step, {steps} steps, torch CPU oracle port '
+                                   f'(reference is Python and cannot travel to the GPU box)'},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    import ctypes as C
+    from erd_b200 import _native as N
+    from erd_b200.head import GFLHeadIncrementERD, parse_losses
+    from erd_b200.detector import GFLIncrementERD
+
+    lib = N.load()
+    head = GFLHeadIncrementERD(NUM_CLASSES, 256, reg_max=REG_MAX, build_convs=False,
+                               train_cfg=dict(assigner=dict(type='ATSSAssigner', topk=9), allowed_border=-1,
+                                              pos_weight=-1))
+    path = head.path
+    n = args.imgs
+    host = make_inputs(n, 1234 + rank)
+    A = host.anchors_per_image
+    b = host.to(dev)
+    plan = path.plan(b.s_cls, NUM_CLASSES, ORI, REG_MAX)
+    plan.set_targets(b.gt_bboxes, b.gt_labels, b.pad_shapes)
+    g_cls = [torch.empty_like(t) for t in b.s_cls]
+    g_box = [torch.empty_like(t) for t in b.s_box]
+    losses = torch.empty(plan.num_losses, device=dev)
+
+    def step():
+        # the two C-ABI calls around the 8-byte all-reduce; grads written into fixed buffers
+        path.prepare(plan, b.t_cls, b.t_box, b.s_cls)
+        path.reduce_avg(plan)
+        path.loss_fwd_bwd(plan, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls, g_box, losses, 1.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    lib.erd_profile_enable(1)
+    launches0 = lib.erd_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.erd_launch_count() - launches0
+    lib.erd_profile_enable(0)
+    nk = lib.erd_profile_num_kernels()
+    tot, cnt = (C.c_float * nk)(), (C.c_int * nk)()
+    lib.erd_profile_collect(tot, cnt)
+    kern = {lib.erd_profile_kernel_name(i).decode(): (tot[i] / cnt[i] if cnt[i] else 0.0) for i in range(nk)}
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * n * A / (ms_step * 1e-3)
+
+    # ---- e2e: the reference-facing plugin API with HOST buffers (pinned), H2D of every head
+    # output and D2H of the loss vector inside the timed region, autograd backward included.
+    e2e = None
+    if not args.no_e2e:
+        det = GFLIncrementERD(head, ORI)
+        pin = lambda ts: [t.pin_memory() for t in ts]
+        h = dict(t_cls=pin(host.t_cls), t_box=pin(host.t_box), s_cls=pin(host.s_cls), s_box=pin(host.s_box))
+        d = {k: [torch.empty_like(t, device=dev) for t in v] for k, v in h.items()}
+        gts = [type('GT', (), dict(bboxes=x, labels=y))() for x, y in zip(b.gt_bboxes, b.gt_labels)]
+        metas = [dict(img_shape=i, pad_shape=p) for i, p in zip(host.img_shapes, host.pad_shapes)]
+        h2d = sum(t.numel() * 4 for v in h.values() for t in v)
+        loss_host = torch.empty(plan.num_losses).pin_memory()
+
+        def e2e_step():
+            with torch.no_grad():
+                for k in h:
+                    for src, dst in zip(h[k], d[k]):
+                        dst.copy_(src, non_blocking=True)
+            s_cls = [t.requires_grad_() for t in d['s_cls']]
+            s_box = [t.requires_grad_() for t in d['s_box']]
+            for t in s_cls + s_box:
+                t.grad = None
+            sel = det.sel_pos(d['t_cls'], d['t_box'])
+            out = head.loss_by_feat((d['t_cls'], d['t_box']), (s_cls, s_box), sel[0], sel[1], sel[2], sel[3],
+                                    ORI, 1.0, None, gts, metas)
+            parse_losses(out).backward()
+            vec = torch.stack(out['loss_cls'] + out['loss_bbox'] + out['loss_dfl'] + out['loss_dist_cls']
+                              + out['loss_dist_bbox']).detach()
+            loss_host.copy_(vec, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * n * A * e_steps / float(dt.item()), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': plan.num_losses * 4, 'steps': e_steps,
+               'api': 'GFLIncrementERD.sel_pos + GFLHeadIncrementERD.loss_by_feat + backward, pinned host tensors'}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        dom = 'loss_main'
+        dom_ms = kern.get(dom, 0.0)
+        achieved = (n * A * BYTES_PER_ANCHOR[dom]) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'GFL R50-FPN 40+40 ERD loss fwd+bwd, {n} img/GPU 800x1333, 80-class head, '
+                                   f'reg_max=16 (BASELINE.json configs[1])', 'anchors_per_image': A,
+                       'images_per_gpu': n, 'parallelism': f'dp{world} over images',
+                       'l2': 'inputs+grads 579 MB per step > 126 MB L2, no flush needed'},
+            'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                         'peak_source': 'measured' if peaks else 'fallback',
+                         'algorithmic_bytes_per_anchor': BYTES_PER_ANCHOR[dom],
+                         'path_bytes_per_anchor': BYTES_PER_ANCHOR['path'],
+                         'path_achieved_gbs': n * A * BYTES_PER_ANCHOR['path'] / (ms_step * 1e-3) / 1e9,
+                         'kernel_ms': {k: round(v, 5) for k, v in kern.items() if v}},
+            'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            anchors, times, cores = time_cpu_oracle(2, 5, 2)
+            line['cpu_baseline'] = {'value': anchors / (sum(times) / len(times)), 'unit': UNIT, 'cores': cores,
+                                    'kind': 'port', 'sample': '2 images x 22400 anchors per step, 5 steps, '
+                                                              'torch-CPU oracle port of the reference'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

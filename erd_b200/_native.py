@@ -52,7 +52,12 @@ SIGNATURES = {
     'erd_loss_fwd_bwd': [_SH, PtrArray, PtrArray, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                          _P, _F, _P, _I, _P, PtrArray, PtrArray, _P, _P],
     'erd_step_prepare': [_P, _SH, PtrArray, PtrArray, PtrArray, _P, _P, _P, _P, _F,
-                         C.POINTER(ErdStepBuffers), _P, _P],
+                         C.POINTER(ErdStepBuffers), _P, _P, C.c_uint32],
+    'erd_profile_enable': [C.c_int],
+    'erd_launch_count': [],
+    'erd_profile_num_kernels': [],
+    'erd_profile_kernel_name': [C.c_int],
+    'erd_profile_collect': [C.POINTER(C.c_float), C.POINTER(C.c_int)],
 }
 
 _lib = None
@@ -73,7 +78,8 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError here == header/library drift
         fn.argtypes = argtypes
-        fn.restype = C.c_char_p if name == 'erd_last_error' else C.c_int
+        fn.restype = (C.c_char_p if name in ('erd_last_error', 'erd_profile_kernel_name')
+                      else C.c_ulonglong if name == 'erd_launch_count' else C.c_int)
     if lib.erd_abi_version() != ABI_VERSION:
         raise RuntimeError(f'liberd_b200 ABI {lib.erd_abi_version()} != binding {ABI_VERSION}')
     _lib = lib

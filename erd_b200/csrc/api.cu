@@ -275,7 +275,7 @@ int erd_loss_fwd_bwd(const ErdShape* shape, const float* const* s_cls, const flo
 int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const* t_cls, const float* const* t_box,
                      const float* const* s_cls, const float* gt_boxes, const int64_t* gt_labels,
                      const int32_t* gt_offsets, const int32_t* pad_hw, float iou_thr, const ErdStepBuffers* b,
-                     void* wsp, void* stream) {
+                     void* wsp, void* stream, uint32_t flags) {
   if (!ctx || !b) return fail(ERD_ERR_NULL, "erd_step_prepare: NULL ctx/buffers");
   cudaStream_t main = (cudaStream_t)stream;
   // fork: ATSS + avg factors run beside the teacher pass; join before returning
@@ -284,7 +284,7 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork");
   int rc = erd_atss_assign(shape, gt_boxes, gt_labels, gt_offsets, pad_hw, b->gt_inds, b->num_pos, wsp, ctx->side[0]);
   if (!rc) rc = erd_avg_factors(shape, s_cls, gt_labels, gt_offsets, b->gt_inds, b->num_pos, b->avg, wsp, ctx->side[0]);
-  if (!rc)
+  if (!rc && !(flags & ERD_PREPARE_ERS_DONE))
     rc = erd_ers_select(shape, t_cls, t_box, b->cls_inds, b->cls_count, b->box_inds, b->box_count, b->thr,
                         b->sel_flags, wsp, main);
   if (!rc) rc = erd_teacher_nms(shape, b->box_inds, b->box_count, pad_hw, iou_thr, b->keep, b->keep_count, wsp, main);

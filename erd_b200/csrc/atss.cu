@@ -200,8 +200,10 @@ cudaError_t launch_atss(const Geo& g, const Workspace& ws, const float* gt_boxes
   e = cudaMemsetAsync(num_pos, 0, sizeof(int32_t) * g.n_img, st);
   if (e != cudaSuccess) return e;
   if (g.total_gt > 0)
-    atss_candidates_kernel<<<g.total_gt, kCandThreads, 0, st>>>(g, ws, gt_boxes, gt_offsets, pad_hw);
-  atss_finalize_kernel<<<dim3((g.A + 255) / 256, g.n_img), 256, 0, st>>>(g, ws, pad_hw, gt_inds, num_pos);
+    ERD_LAUNCH(kKAtssCand, st,
+               (atss_candidates_kernel<<<g.total_gt, kCandThreads, 0, st>>>(g, ws, gt_boxes, gt_offsets, pad_hw)));
+  ERD_LAUNCH(kKAtssFin, st,
+             (atss_finalize_kernel<<<dim3((g.A + 255) / 256, g.n_img), 256, 0, st>>>(g, ws, pad_hw, gt_inds, num_pos)));
   return cudaGetLastError();
 }
 

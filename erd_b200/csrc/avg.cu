@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(kAvgThreads) avg_kernel(Geo g, Workspace ws, P
 cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const int64_t* gt_labels,
                        const int32_t* gt_offsets, const int32_t* gt_inds, const int32_t* num_pos, float* avg,
                        cudaStream_t st) {
-  avg_kernel<<<g.n_img, kAvgThreads, 0, st>>>(g, ws, s_cls, gt_labels, gt_offsets, gt_inds, num_pos, avg);
+  ERD_LAUNCH(kKAvg, st,
+             (avg_kernel<<<g.n_img, kAvgThreads, 0, st>>>(g, ws, s_cls, gt_labels, gt_offsets, gt_inds, num_pos, avg)));
   return cudaGetLastError();
 }
 

@@ -135,8 +135,21 @@ struct Quad {
   }
 };
 
+// ---------------------------------------------------------------- launch accounting (profile.cu)
+enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan,
+                kKUpCheck, kKLossMain, kKKd, kKFinalize, kNumKernels };
+void prof_begin(int id, cudaStream_t st);
+void prof_end(int id, cudaStream_t st);
+// ERD_LAUNCH(id, stream, kernel<<<...>>>(...)) counts the launch and, when profiling is on,
+// brackets it with CUDA events on the launching stream.
+#define ERD_LAUNCH(id, st, ...) \
+  do {                          \
+    ::erd::prof_begin(id, st);  \
+    __VA_ARGS__;                \
+    ::erd::prof_end(id, st);    \
+  } while (0)
+
 // ---------------------------------------------------------------- host launchers (one per .cu)
-struct StepIO;  // api.cu
 
 cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box,
                        int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds, int32_t* box_count,

@@ -187,9 +187,10 @@ cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, con
                        int32_t* cls_count, int32_t* box_inds, int32_t* box_count, float* thr, uint8_t* sel_flags,
                        cudaStream_t st) {
   const int tiles = g.tile_start[kLevels];
-  ers_scan_kernel<<<dim3(tiles, g.n_img), kTileThreads, 0, st>>>(g, ws, t_cls, t_box);
-  ers_select_kernel<<<g.n_img, kSelThreads, 0, st>>>(g, ws, tiles, cls_inds, cls_count, box_inds, box_count, thr,
-                                                          sel_flags);
+  ERD_LAUNCH(kKErsScan, st, (ers_scan_kernel<<<dim3(tiles, g.n_img), kTileThreads, 0, st>>>(g, ws, t_cls, t_box)));
+  ERD_LAUNCH(kKErsSelect, st,
+             (ers_select_kernel<<<g.n_img, kSelThreads, 0, st>>>(g, ws, tiles, cls_inds, cls_count, box_inds,
+                                                                 box_count, thr, sel_flags)));
   return cudaGetLastError();
 }
 

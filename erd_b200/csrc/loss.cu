@@ -346,10 +346,11 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
   const int total = 3 * kLevels + 2 * g.n_img;
   cudaError_t e = cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * total, st);
   if (e != cudaSuccess) return e;
-  if (a.skip_flag) upstream_check_kernel<<<1, 128, 0, st>>>(ws, a.upstream, total);
-  loss_main_kernel<<<dim3(g.tile_start[kLevels], g.n_img), kTileThreads, 0, st>>>(g, ws, a);
-  kd_kernel<<<dim3(32, g.n_img), kKdThreads, 0, st>>>(g, ws, a);
-  finalize_kernel<<<1, ((total + 31) / 32) * 32, 0, st>>>(g, ws, a);
+  if (a.skip_flag) ERD_LAUNCH(kKUpCheck, st, (upstream_check_kernel<<<1, 128, 0, st>>>(ws, a.upstream, total)));
+  ERD_LAUNCH(kKLossMain, st,
+             (loss_main_kernel<<<dim3(g.tile_start[kLevels], g.n_img), kTileThreads, 0, st>>>(g, ws, a)));
+  ERD_LAUNCH(kKKd, st, (kd_kernel<<<dim3(32, g.n_img), kKdThreads, 0, st>>>(g, ws, a)));
+  ERD_LAUNCH(kKFinalize, st, (finalize_kernel<<<1, ((total + 31) / 32) * 32, 0, st>>>(g, ws, a)));
   return cudaGetLastError();
 }
 

@@ -188,10 +188,11 @@ cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_ind
     attr_done = true;
   }
   if (sort_smem > 200 * 1024) return cudaErrorInvalidValue;
-  nms_sort_kernel<<<g.n_img, kSortThreads, sort_smem, st>>>(g, ws, box_inds, box_count, pad_hw, P);
-  nms_mask_kernel<<<dim3(64, g.n_img), 64, 0, st>>>(g, ws, box_count, iou_thr);
+  ERD_LAUNCH(kKNmsSort, st,
+             (nms_sort_kernel<<<g.n_img, kSortThreads, sort_smem, st>>>(g, ws, box_inds, box_count, pad_hw, P)));
+  ERD_LAUNCH(kKNmsMask, st, (nms_mask_kernel<<<dim3(64, g.n_img), 64, 0, st>>>(g, ws, box_count, iou_thr)));
   const size_t scan_smem = sizeof(unsigned long long) * (size_t)nms_words(g.sel_cap);
-  nms_scan_kernel<<<g.n_img, 32, scan_smem, st>>>(g, ws, box_count, keep, keep_count);
+  ERD_LAUNCH(kKNmsScan, st, (nms_scan_kernel<<<g.n_img, 32, scan_smem, st>>>(g, ws, box_count, keep, keep_count)));
   return cudaGetLastError();
 }
 

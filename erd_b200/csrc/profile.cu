@@ -1,0 +1,92 @@
+// Launch accounting and optional per-kernel CUDA-event timing on the launching stream
+// (bench.py uses it for the roofline line; disabled by default, zero cost when off).
+#include <mutex>
+#include <vector>
+
+#include "erd_common.cuh"
+
+namespace erd {
+
+static const char* kKernelNames[kNumKernels] = {"ers_scan", "ers_select", "atss_candidates", "atss_finalize",
+                                                "avg", "nms_sort", "nms_mask", "nms_scan", "upstream_check",
+                                                "loss_main", "kd", "finalize"};
+
+struct ProfState {
+  std::mutex mu;
+  bool enabled = false;
+  unsigned long long launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[kNumKernels];
+  std::vector<cudaEvent_t> pool;
+};
+static ProfState g_prof;
+
+static cudaEvent_t take_event() {
+  if (!g_prof.pool.empty()) {
+    cudaEvent_t e = g_prof.pool.back();
+    g_prof.pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void prof_begin(int id, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  ++g_prof.launches;
+  if (!g_prof.enabled) return;
+  cudaEvent_t a = take_event(), b = take_event();
+  cudaEventRecord(a, st);
+  g_prof.pending[id].push_back({a, b});
+}
+
+void prof_end(int id, cudaStream_t st) {
+  if (!g_prof.enabled) return;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  if (!g_prof.pending[id].empty()) cudaEventRecord(g_prof.pending[id].back().second, st);
+}
+
+}  // namespace erd
+
+using namespace erd;
+
+extern "C" {
+
+int erd_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  g_prof.enabled = on != 0;
+  return ERD_OK;
+}
+
+unsigned long long erd_launch_count(void) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  return g_prof.launches;
+}
+
+int erd_profile_num_kernels(void) { return kNumKernels; }
+const char* erd_profile_kernel_name(int id) { return (id >= 0 && id < kNumKernels) ? kKernelNames[id] : ""; }
+
+// Sums the elapsed time of every profiled launch since the last call (blocks until those
+// launches have finished).  total_ms / count are arrays of erd_profile_num_kernels().
+int erd_profile_collect(float* total_ms, int* count) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  for (int k = 0; k < kNumKernels; ++k) {
+    float tot = 0.f;
+    int n = 0;
+    for (auto& pr : g_prof.pending[k]) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+        tot += ms;
+        ++n;
+      }
+      g_prof.pool.push_back(pr.first);
+      g_prof.pool.push_back(pr.second);
+    }
+    g_prof.pending[k].clear();
+    if (total_ms) total_ms[k] = tot;
+    if (count) count[k] = n;
+  }
+  return ERD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+"""Host-side mirror of the reference's ERD detector for the part on the hot path:
+``sel_pos`` (Elastic Response Selection) and the ``loss`` glue.
+
+Reference: ``GFLIncrementERD`` (mmdet/models/detectors/gfl_increment_erd.py:20-220).  Backbone,
+neck, teacher construction and checkpoint surgery (:67-122) are out of scope;
+the student / teacher networks are injected as modules so that the same ``loss`` sequence
+(:202-220) runs: teacher forward, ``sel_pos``, student forward, ``bbox_head.loss``.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .head import ErsSelection, GFLHeadIncrementERD
+
+
+class GFLIncrementERD(nn.Module):
+    def __init__(self, bbox_head: GFLHeadIncrementERD, ori_num_classes: int, ori_model: Optional[nn.Module] = None,
+                 extract_feat: Optional[Callable] = None, top_k: int = 100, dist_loss_weight: float = 1) -> None:
+        super().__init__()
+        self.bbox_head = bbox_head
+        self.ori_num_classes = int(ori_num_classes)
+        self.top_k = top_k                      # unused, as in the reference (:49,61)
+        self.dist_loss_weight = dist_loss_weight
+        self.ori_model = ori_model              # frozen teacher: images -> (cls_scores, bbox_preds)
+        self._extract_feat = extract_feat       # student backbone + neck
+        if ori_model is not None:
+            for p in ori_model.parameters():    # :115-116
+                p.requires_grad = False
+
+    def sel_pos(self, cls_scores: Sequence[Tensor], bbox_preds: Sequence[Tensor]):
+        """gfl_increment_erd.py:165-200.  Returns (topk_cls_inds, topk_cls_scores,
+        topk_bbox_inds, topk_bbox_preds); the index lists are lazily materialised views of the
+        device-side selection, the two gathered-value lists -- which ``loss_by_feat`` never
+        reads (:339-340) -- are gathered only on access."""
+        assert len(cls_scores) == len(bbox_preds)                                    # :180
+        head = self.bbox_head
+        t_cls = [t[:, :self.ori_num_classes].detach().contiguous() for t in cls_scores]
+        t_box = [t.detach().contiguous() for t in bbox_preds]
+        plan = head.path.plan(t_cls, head.num_classes, self.ori_num_classes, head.reg_max)
+        head.path.ers_select(plan, t_cls, t_box)
+        gen = plan.ers_generation
+        cls_sel, box_sel = ErsSelection(plan, 'cls', gen), ErsSelection(plan, 'box', gen)
+        return (cls_sel, _LazyGather(cls_sel, t_cls), box_sel, _LazyGather(box_sel, t_box))
+
+    def loss(self, batch_inputs: Tensor, batch_data_samples) -> dict:
+        """gfl_increment_erd.py:202-220."""
+        with torch.no_grad():   # the reference relies on requires_grad=False instead (:205)
+            ori_outs = self.ori_model(batch_inputs)
+        sel = self.sel_pos(*ori_outs)
+        new_outs = self.bbox_head(self._extract_feat(batch_inputs))
+        return self.bbox_head.loss(ori_outs, new_outs, batch_data_samples, *sel, self.ori_num_classes,
+                                   self.dist_loss_weight, self)
+
+
+class _LazyGather:
+    """topk_cls_scores / topk_bbox_preds of sel_pos_single (:152-153,160-161): rows of the
+    flattened (A, C) teacher tensors at the selected anchors, built on first access."""
+
+    def __init__(self, sel: ErsSelection, levels: List[Tensor]):
+        self.sel, self.levels, self._items = sel, levels, None
+
+    def _materialise(self):
+        if self._items is None:
+            n = self.levels[0].size(0)
+            flat = torch.cat([t.permute(0, 2, 3, 1).reshape(n, -1, t.size(1)) for t in self.levels], dim=1)
+            self._items = [flat[i][self.sel[i]] for i in range(n)]
+        return self._items
+
+    def __len__(self):
+        return len(self.sel)
+
+    def __getitem__(self, i):
+        return self._materialise()[i]
+
+
+try:
+    from mmdet.registry import MODELS as _MODELS  # type: ignore
+    _MODELS.register_module(name='GFLIncrementERD', module=GFLIncrementERD, force=True)
+except Exception:
+    _MODELS = None

@@ -9,9 +9,9 @@ import ctypes as C
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
-import torch.distributed as dist
 
 from . import _native as N
+from .dist_utils import reduce_mean_
 
 STRIDES = (8, 16, 32, 64, 128)
 
@@ -72,6 +72,7 @@ class Plan:
         self.meta_host = torch.zeros(3 * n + 1, dtype=torch.int32).pin_memory()
         self.gt_boxes = torch.zeros(1, 4, dtype=torch.float32, device=device)
         self.gt_labels = torch.zeros(1, dtype=torch.int64, device=device)
+        self.ers_generation = 0      # bumped every time the ERS buffers are rewritten
         self.bufs = N.ErdStepBuffers(
             self.cls_inds.data_ptr(), self.cls_count.data_ptr(), self.box_inds.data_ptr(),
             self.box_count.data_ptr(), self.thr.data_ptr(), self.sel_flags.data_ptr(), self.gt_inds.data_ptr(),
@@ -110,6 +111,26 @@ class Plan:
                 device=self.device, dtype=torch.float32).contiguous()
             self.gt_labels = torch.cat([l.reshape(-1) for l in gt_labels]).to(
                 device=self.device, dtype=torch.int64).contiguous()
+
+
+    def load_selection(self, cls_inds: Sequence[torch.Tensor], box_inds: Sequence[torch.Tensor]):
+        """Adopt caller-provided ERS index lists (the reference's ``loss_by_feat`` takes them as
+        arguments): pad them into the plan buffers and rebuild the per-anchor flags."""
+        if len(cls_inds) != self.n or len(box_inds) != self.n:
+            raise AssertionError('one index tensor per image expected')
+        self.sel_flags.zero_()
+        for lst, inds, cnt, bit in ((cls_inds, self.cls_inds, self.cls_count, 1),
+                                    (box_inds, self.box_inds, self.box_count, 2)):
+            counts = []
+            for i, x in enumerate(lst):
+                x = x.reshape(-1).to(device=self.device)
+                if x.numel() > self.sel_cap:
+                    raise ValueError(f'index list of image {i} exceeds capacity {self.sel_cap}')
+                inds[i, :x.numel()] = x.to(torch.int32)
+                row = self.sel_flags[i]
+                row[x.long()] = row[x.long()] | bit
+                counts.append(x.numel())
+            cnt.copy_(torch.tensor(counts, dtype=torch.int32), non_blocking=False)
 
 
 class ErdPath:
@@ -153,6 +174,7 @@ class ErdPath:
                                         p.cls_count.data_ptr(), p.box_inds.data_ptr(), p.box_count.data_ptr(),
                                         p.thr.data_ptr(), p.sel_flags.data_ptr(), p.ws.data_ptr(), _stream()),
                 'erd_ers_select')
+        p.ers_generation += 1
 
     def atss_assign(self, p: Plan):
         N.check(self.lib.erd_atss_assign(C.byref(p.shape), p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(),
@@ -171,9 +193,7 @@ class ErdPath:
 
     def reduce_avg(self, p: Plan):
         """reduce_mean of both normalisers in one 8-byte all-reduce (dist_utils.py:59-65)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            p.avg.div_(dist.get_world_size())
-            dist.all_reduce(p.avg, op=dist.ReduceOp.SUM)
+        reduce_mean_(p.avg)
 
     def loss_fwd_bwd(self, p: Plan, t_cls, t_box, s_cls, s_box, g_cls, g_box, losses, dist_loss_weight: float,
                      upstream: Optional[torch.Tensor] = None, skip_if_unit: bool = False):
@@ -186,16 +206,19 @@ class ErdPath:
             losses.data_ptr(), _ptrs(g_cls), _ptrs(g_box), p.ws.data_ptr(), _stream()), 'erd_loss_fwd_bwd')
 
     # ---- fused step -------------------------------------------------------------------
-    def prepare(self, p: Plan, t_cls, t_box, s_cls):
+    def prepare(self, p: Plan, t_cls, t_box, s_cls, ers_done: bool = False):
         N.check(self.lib.erd_step_prepare(
             self._context(p.device), C.byref(p.shape), _ptrs(t_cls), _ptrs(t_box), _ptrs(s_cls),
             p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(),
-            self.nms_iou_thr, C.byref(p.bufs), p.ws.data_ptr(), _stream()), 'erd_step_prepare')
+            self.nms_iou_thr, C.byref(p.bufs), p.ws.data_ptr(), _stream(), 1 if ers_done else 0),
+            'erd_step_prepare')
+        if not ers_done:
+            p.ers_generation += 1
 
     def step(self, t_cls, t_box, s_cls, s_box, gt_bboxes, gt_labels, pad_shapes, num_classes: int, ori: int,
              reg_max: int = 16, dist_loss_weight: float = 1.0, upstream: Optional[torch.Tensor] = None,
              g_cls: Optional[List[torch.Tensor]] = None, g_box: Optional[List[torch.Tensor]] = None,
-             targets_set: bool = False):
+             targets_set: bool = False, ers_done: bool = False):
         """ERS + assignment + NMS + fused loss forward/backward.
         Returns (plan, losses (3L+2N,), g_cls[5], g_box[5])."""
         p = self.plan(s_cls, num_classes, ori, reg_max)
@@ -210,7 +233,7 @@ class ErdPath:
         if g_box is None:
             g_box = [torch.empty_like(t) for t in s_box]
         losses = torch.empty(p.num_losses, dtype=torch.float32, device=p.device)
-        self.prepare(p, t_cls, t_box, s_cls)
+        self.prepare(p, t_cls, t_box, s_cls, ers_done)
         self.reduce_avg(p)
         self.loss_fwd_bwd(p, t_cls, t_box, s_cls, s_box, g_cls, g_box, losses, dist_loss_weight, upstream)
         return p, losses, g_cls, g_box

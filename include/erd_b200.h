@@ -173,7 +173,19 @@ typedef struct ErdStepBuffers {
 int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const* t_cls,
                      const float* const* t_box, const float* const* s_cls, const float* gt_boxes,
                      const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
-                     float iou_thr, const ErdStepBuffers* buf, void* ws, void* stream);
+                     float iou_thr, const ErdStepBuffers* buf, void* ws, void* stream,
+                     uint32_t flags);
+/* flags for erd_step_prepare */
+#define ERD_PREPARE_ERS_DONE 1u /* erd_ers_select already ran on these teacher tensors (sel_pos);
+                                   its lists, counts, sel_flags and the teacher cache are reused */
+
+/* Launch accounting and optional per-kernel timing (CUDA events on the launching stream).
+ * No reference counterpart; bench.py reports roofline numbers from it. */
+int erd_profile_enable(int on);
+unsigned long long erd_launch_count(void);   /* kernels launched by this library so far */
+int erd_profile_num_kernels(void);
+const char* erd_profile_kernel_name(int id);
+int erd_profile_collect(float* total_ms, int* count);
 
 #ifdef __cplusplus
 }
