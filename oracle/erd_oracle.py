@@ -226,7 +226,7 @@ def box_to_distances(pts: Tensor, box: Tensor, reg_max: int) -> Tensor:
 def qfl_elementwise(pred: Tensor, label: Tensor, score: Tensor, beta: float = 2.0) -> Tensor:
     """gfocal_loss.py:12-53, per-anchor (summed over classes)."""
     sig = pred.sigmoid()
-    loss = F.binary_cross_entropy_with_logits(pred, torch.zeros_like(pred), reduction='none') * sig.pow(beta)
+    loss = F.binary_cross_entropy_with_logits(pred, sig.new_zeros(pred.shape), reduction='none') * sig.pow(beta)
     pos = ((label >= 0) & (label < pred.size(1))).nonzero().squeeze(1)
     pl = label[pos].long()
     sf = score[pos] - sig[pos, pl]

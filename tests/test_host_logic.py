@@ -1,0 +1,102 @@
+"""Host-side logic that needs no GPU: geometry, sharding, reduce_mean over gloo (world 2),
+config validation and error behaviour of the reference-facing classes."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from erd_b200.dist_utils import shard_images
+from erd_b200.synth import level_shapes, make_batch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_level_shapes_match_survey():
+    assert level_shapes(800, 1344) == [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    assert level_shapes(1600, 1600) == [(200, 200), (100, 100), (50, 50), (25, 25), (13, 13)]
+    b = make_batch(1, (800, 1333))
+    assert b.anchors_per_image == 22400 and b.canvas == (800, 1344)
+
+
+def test_synth_is_deterministic_and_labels_in_new_class_range():
+    a, b = make_batch(2, (96, 128), seed=3, ori=70), make_batch(2, (96, 128), seed=3, ori=70)
+    assert all(torch.equal(x, y) for x, y in zip(a.s_cls + a.t_box, b.s_cls + b.t_box))
+    assert all(int(l.max()) < 10 and int(l.min()) >= 0 for l in a.gt_labels if l.numel())
+    assert a.t_cls[0].shape[1] == 70 and a.s_cls[0].shape[1] == 80
+
+
+def test_shard_images_partitions_the_batch():
+    for world in (1, 2, 3, 8):
+        parts = [shard_images(16, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(16))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_head_config_validation_mirrors_reference_contract():
+    from erd_b200.head import GFLHeadIncrementERD
+    ok = GFLHeadIncrementERD(80, 256, build_convs=False)
+    assert ok.strides == (8, 16, 32, 64, 128) and ok.reg_max == 16
+    with pytest.raises(ValueError):
+        GFLHeadIncrementERD(80, 256, build_convs=False, loss_cls=dict(type='FocalLoss'))
+    with pytest.raises(ValueError):
+        GFLHeadIncrementERD(80, 256, build_convs=False, loss_cls=dict(type='QualityFocalLoss', beta=1.0))
+    with pytest.raises(ValueError):
+        GFLHeadIncrementERD(80, 256, build_convs=False, train_cfg=dict(assigner=dict(type='ATSSAssigner', topk=5)))
+    with pytest.raises(AssertionError):   # reference asserts square strides, gfl_head_increment_erd.py:256
+        GFLHeadIncrementERD(80, 256, build_convs=False, anchor_generator=dict(
+            type='AnchorGenerator', ratios=[1.0], octave_base_scale=8, scales_per_octave=1,
+            strides=[(8, 16), 16, 32, 64, 128]))
+
+
+def test_product_path_refuses_cpu_tensors():
+    """No CPU fallback: the public API raises instead of computing on the host."""
+    from erd_b200.head import GFLHeadIncrementERD
+    head = GFLHeadIncrementERD(80, 256, build_convs=False)
+    b = make_batch(1, (96, 128))
+    gts = [type('G', (), dict(bboxes=x, labels=y))() for x, y in zip(b.gt_bboxes, b.gt_labels)]
+    with pytest.raises(RuntimeError, match='CUDA'):
+        head.loss_by_feat((b.t_cls, b.t_box), (b.s_cls, b.s_box), None, None, None, None, 40, 1.0, None, gts,
+                          [dict(pad_shape=p) for p in b.pad_shapes])
+
+
+def test_product_does_not_import_the_oracle():
+    """Nothing under erd_b200/ may import oracle/ (the oracle is test infrastructure)."""
+    pkg = os.path.join(ROOT, 'erd_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert 'import oracle' not in src and 'from oracle' not in src, fn
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from erd_b200.dist_utils import reduce_mean_, shard_images, world
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:' + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, ws = world()
+# each rank owns its shard of 5 images; avg = [sum max(num_pos,1), sum w] of its shard
+num_pos = [3, 0, 7, 1, 0]
+wsum = [0.5, 0.0, 1.25, 0.125, 0.0]
+mine = shard_images(5, rank, ws)
+avg = torch.tensor([float(sum(max(num_pos[i], 1) for i in mine)), float(sum(wsum[i] for i in mine))])
+reduce_mean_(avg)
+exp0 = sum(max(p, 1) for p in num_pos) / 2.0
+exp1 = sum(wsum) / 2.0
+assert abs(float(avg[0]) - exp0) < 1e-6 and abs(float(avg[1]) - exp1) < 1e-6, (avg, exp0, exp1)
+dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+def test_reduce_mean_world_size_two_gloo(tmp_path):
+    """The N>1 host path: one 2-float all-reduce, mean over ranks (dist_utils.py:59-65)."""
+    script = tmp_path / 'worker.py'
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 1000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all('ok' in o for o in outs)
