@@ -270,7 +270,7 @@ def level_loss(anchors: Tensor, cls_score: Tensor, bbox_pred: Tensor, labels: Te
     lw = label_weights.reshape(-1)
     lab[lab == num_classes] = cn                                                  # :270-271
     pos = ((lab >= 0) & (lab < cn)).nonzero().squeeze(1)                          # :273-274
-    score = lw.new_zeros(lab.shape)
+    score = lw.new_zeros(lab.shape, dtype=cls.dtype)   # fp32 on the reference path; fp64 for the accuracy study
     if pos.numel() > 0:
         pa = anchors[pos]
         ctr = torch.stack([(pa[:, 0] + pa[:, 2]) / 2, (pa[:, 1] + pa[:, 3]) / 2], -1) / stride  # gfl_head.py:232-243
