@@ -175,7 +175,7 @@ def run_ours(args):
 
     def step():
         # the two C-ABI calls around the 8-byte all-reduce; grads written into fixed buffers
-        path.prepare(plan, b.t_cls, b.t_box, b.s_cls)
+        path.prepare(plan, b.t_cls, b.t_box, b.s_cls, b.s_box)
         path.reduce_avg(plan)
         path.loss_fwd_bwd(plan, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls, g_box, losses, 1.0)
 

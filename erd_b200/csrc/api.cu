@@ -75,7 +75,8 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->ers_part = (double*)take((size_t)g.n_img * g.tile_start[kLevels] * 4 * 8);
   ws->atss_key = (unsigned long long*)take(NA * 8);
   ws->pos_list = (int*)take(NA * 4);
-  ws->avg_part = (double*)take((size_t)g.n_img * 8);
+  ws->pos_score = (float*)take(NA * 4);
+  ws->pre_acc = (double*)take((size_t)(2 * kLevels + 1) * 8);
   ws->counters = (unsigned int*)take(8 * 4);
   ws->nms_raw = (float4*)take(NS * 16);
   ws->nms_cls = (int*)take(NS * 4);
@@ -118,8 +119,9 @@ static MPtr5 mptr5(float* const* p) {
 }
 
 struct ErdContext {
-  cudaStream_t side[2];
-  cudaEvent_t fork, join[2];
+  cudaStream_t side[2];          // [0] assignment + positives prepass, [1] teacher NMS
+  cudaEvent_t fork, join[2], sel;
+  bool nms_pending;              // join[1] recorded by erd_step_prepare, not yet waited on
 };
 
 extern "C" {
@@ -150,6 +152,8 @@ int erd_create(ErdContext** ctx) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sel, cudaEventDisableTiming);
+  c->nms_pending = false;
   if (e != cudaSuccess) {
     delete c;
     return fail_cuda(e, "erd_create");
@@ -165,6 +169,7 @@ int erd_destroy(ErdContext* c) {
     cudaEventDestroy(c->join[i]);
   }
   cudaEventDestroy(c->fork);
+  cudaEventDestroy(c->sel);
   delete c;
   return ERD_OK;
 }
@@ -199,19 +204,20 @@ int erd_atss_assign(const ErdShape* shape, const float* gt_boxes, const int64_t*
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_atss_assign");
 }
 
-int erd_avg_factors(const ErdShape* shape, const float* const* s_cls, const int64_t* gt_labels,
-                    const int32_t* gt_offsets, const int32_t* gt_inds, const int32_t* num_pos, float* avg, void* wsp,
-                    void* stream) {
+int erd_avg_factors(const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
+                    const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                    const int32_t* gt_inds, const int32_t* num_pos, float* avg, void* wsp, void* stream) {
   Geo g;
   int rc = make_geo(shape, &g);
   if (rc) return rc;
-  if (NULLS(s_cls) || !gt_offsets || !gt_inds || !num_pos || !avg || !wsp || (g.total_gt > 0 && !gt_labels))
+  if (NULLS(s_cls) || NULLS(s_box) || !gt_offsets || !gt_inds || !num_pos || !avg || !wsp ||
+      (g.total_gt > 0 && (!gt_labels || !gt_boxes)))
     return fail(ERD_ERR_NULL, "erd_avg_factors: NULL argument");
+  if (g.total_gt > 0 && ((uintptr_t)gt_boxes & 15)) return fail(ERD_ERR_BAD_SHAPE, "gt_boxes must be 16 B aligned");
   Workspace ws;
   carve(g, wsp, &ws);
-  cudaError_t e = cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned int), (cudaStream_t)stream);
-  if (e == cudaSuccess)
-    e = launch_avg(g, ws, ptr5(s_cls), gt_labels, gt_offsets, gt_inds, num_pos, avg, (cudaStream_t)stream);
+  cudaError_t e = launch_avg(g, ws, ptr5(s_cls), ptr5(s_box), gt_boxes, gt_labels, gt_offsets, gt_inds, num_pos, avg,
+                             (cudaStream_t)stream);
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_avg_factors");
 }
 
@@ -228,19 +234,20 @@ int erd_teacher_nms(const ErdShape* shape, const int32_t* box_inds, const int32_
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_teacher_nms");
 }
 
-int erd_loss_fwd_bwd(const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
+int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
                      const float* const* t_cls, const float* const* t_box, const float* gt_boxes,
                      const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
-                     const int32_t* gt_inds, const int32_t* cls_count, const uint8_t* sel_flags, const int32_t* box_inds,
-                     const int32_t* keep, const int32_t* keep_count, const float* avg, float dist_loss_weight,
-                     const float* upstream, int32_t skip_if_unit_upstream, float* losses, float* const* g_cls,
-                     float* const* g_box, void* wsp, void* stream) {
+                     const int32_t* gt_inds, const int32_t* num_pos, const int32_t* cls_count,
+                     const uint8_t* sel_flags, const int32_t* box_inds, const int32_t* keep,
+                     const int32_t* keep_count, const float* avg, float dist_loss_weight, const float* upstream,
+                     int32_t skip_if_unit_upstream, float* losses, float* const* g_cls, float* const* g_box,
+                     void* wsp, void* stream) {
   Geo g;
   int rc = make_geo(shape, &g);
   if (rc) return rc;
   if (NULLS(s_cls) || NULLS(s_box) || NULLS(t_cls) || NULLS(t_box) || NULLS(g_cls) || NULLS(g_box) || !gt_offsets ||
-      !pad_hw || !gt_inds || !cls_count || !sel_flags || !box_inds || !keep || !keep_count || !avg || !losses || !wsp ||
-      (g.total_gt > 0 && (!gt_boxes || !gt_labels)))
+      !pad_hw || !gt_inds || !num_pos || !cls_count || !sel_flags || !box_inds || !keep || !keep_count || !avg ||
+      !losses || !wsp || (g.total_gt > 0 && (!gt_boxes || !gt_labels)))
     return fail(ERD_ERR_NULL, "erd_loss_fwd_bwd: NULL argument");
   set_vec(&g, s_cls, s_box, g_cls, g_box);
   if (g.total_gt > 0 && ((uintptr_t)gt_boxes & 15)) return fail(ERD_ERR_BAD_SHAPE, "gt_boxes must be 16 B aligned");
@@ -258,6 +265,7 @@ int erd_loss_fwd_bwd(const ErdShape* shape, const float* const* s_cls, const flo
   a.gt_offsets = gt_offsets;
   a.pad_hw = pad_hw;
   a.gt_inds = gt_inds;
+  a.num_pos = num_pos;
   a.cls_count = cls_count;
   a.sel_flags = sel_flags;
   a.box_inds = box_inds;
@@ -268,29 +276,47 @@ int erd_loss_fwd_bwd(const ErdShape* shape, const float* const* s_cls, const flo
   a.skip_flag = (upstream && skip_if_unit_upstream) ? ws.counters + 1 : nullptr;
   a.losses = losses;
   a.dlw = dist_loss_weight;
-  cudaError_t e = launch_loss(g, ws, a, (cudaStream_t)stream);
+  // the teacher NMS forked by erd_step_prepare is joined only in front of the kernel that needs it
+  cudaEvent_t nms_done = (ctx && ctx->nms_pending) ? ctx->join[1] : nullptr;
+  cudaError_t e = launch_loss(g, ws, a, (cudaStream_t)stream, nms_done);
+  if (ctx) ctx->nms_pending = false;
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_loss_fwd_bwd");
 }
 
 int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const* t_cls, const float* const* t_box,
-                     const float* const* s_cls, const float* gt_boxes, const int64_t* gt_labels,
-                     const int32_t* gt_offsets, const int32_t* pad_hw, float iou_thr, const ErdStepBuffers* b,
-                     void* wsp, void* stream, uint32_t flags) {
+                     const float* const* s_cls, const float* const* s_box, const float* gt_boxes,
+                     const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw, float iou_thr,
+                     const ErdStepBuffers* b, void* wsp, void* stream, uint32_t flags) {
   if (!ctx || !b) return fail(ERD_ERR_NULL, "erd_step_prepare: NULL ctx/buffers");
   cudaStream_t main = (cudaStream_t)stream;
-  // fork: ATSS + avg factors run beside the teacher pass; join before returning
-  cudaError_t e = cudaEventRecord(ctx->fork, main);
+  cudaError_t e = cudaSuccess;
+  if (ctx->nms_pending) {   // a previous prepare whose NMS nobody consumed: do not race its teacher cache
+    e = cudaStreamWaitEvent(main, ctx->join[1], 0);
+    ctx->nms_pending = false;
+  }
+  // stream layout: main = teacher pass (ERS scan + select); side[0] = ATSS + positives prepass
+  // (joined back before returning, the caller all-reduces avg next); side[1] = teacher NMS,
+  // forked after the selection and joined inside erd_loss_fwd_bwd in front of the KD kernel.
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->fork, main);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[0], ctx->fork, 0);
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork");
   int rc = erd_atss_assign(shape, gt_boxes, gt_labels, gt_offsets, pad_hw, b->gt_inds, b->num_pos, wsp, ctx->side[0]);
-  if (!rc) rc = erd_avg_factors(shape, s_cls, gt_labels, gt_offsets, b->gt_inds, b->num_pos, b->avg, wsp, ctx->side[0]);
+  if (!rc)
+    rc = erd_avg_factors(shape, s_cls, s_box, gt_boxes, gt_labels, gt_offsets, b->gt_inds, b->num_pos, b->avg, wsp,
+                         ctx->side[0]);
   if (!rc && !(flags & ERD_PREPARE_ERS_DONE))
     rc = erd_ers_select(shape, t_cls, t_box, b->cls_inds, b->cls_count, b->box_inds, b->box_count, b->thr,
                         b->sel_flags, wsp, main);
-  if (!rc) rc = erd_teacher_nms(shape, b->box_inds, b->box_count, pad_hw, iou_thr, b->keep, b->keep_count, wsp, main);
-  e = cudaEventRecord(ctx->join[0], ctx->side[0]);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ctx->join[0], 0);
   if (rc) return rc;
+  e = cudaEventRecord(ctx->sel, main);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[1], ctx->sel, 0);
+  if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork nms");
+  rc = erd_teacher_nms(shape, b->box_inds, b->box_count, pad_hw, iou_thr, b->keep, b->keep_count, wsp, ctx->side[1]);
+  if (rc) return rc;
+  e = cudaEventRecord(ctx->join[1], ctx->side[1]);
+  if (e == cudaSuccess) ctx->nms_pending = true;
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->join[0], ctx->side[0]);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ctx->join[0], 0);
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_step_prepare join");
 }
 

@@ -43,7 +43,8 @@ struct Workspace {
   double* ers_part;               // [N][tiles][4] per-CTA sums: m, m^2, u, u^2
   unsigned long long* atss_key;   // [N][A] packed (iou bits << 32 | ~gt) argmax table
   int* pos_list;                  // [N][A] anchors with an assigned GT (unordered)
-  double* avg_part;               // [N] per-image sum of positive weights
+  float* pos_score;               // [N][A] IoU quality score, defined at positives only
+  double* pre_acc;                // [2L+1] sum w(1-giou) per level, sum w*dfl per level, sum w
   unsigned int* counters;         // [8] last-block tickets
   float4* nms_raw;                // [N][sel_cap] decoded teacher boxes in list order
   int* nms_cls;                   // [N][sel_cap] class ids in list order
@@ -137,7 +138,7 @@ struct Quad {
 
 // ---------------------------------------------------------------- launch accounting (profile.cu)
 enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan,
-                kKUpCheck, kKLossMain, kKKd, kKFinalize, kNumKernels };
+                kKUpCheck, kKLossMain, kKPosGrad, kKKd, kKFinalize, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 // ERD_LAUNCH(id, stream, kernel<<<...>>>(...)) counts the launch and, when profiling is on,
@@ -157,9 +158,9 @@ cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, con
 cudaError_t launch_atss(const Geo& g, const Workspace& ws, const float* gt_boxes, const int64_t* gt_labels,
                         const int32_t* gt_offsets, const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos,
                         cudaStream_t st);
-cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const int64_t* gt_labels,
-                       const int32_t* gt_offsets, const int32_t* gt_inds, const int32_t* num_pos, float* avg,
-                       cudaStream_t st);
+cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
+                       const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                       const int32_t* gt_inds, const int32_t* num_pos, float* avg, cudaStream_t st);
 cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_inds, const int32_t* box_count,
                        const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count, cudaStream_t st);
 
@@ -171,6 +172,7 @@ struct LossArgs {
   const int32_t* gt_offsets;
   const int32_t* pad_hw;
   const int32_t* gt_inds;
+  const int32_t* num_pos;
   const int32_t* cls_count;
   const uint8_t* sel_flags;
   const int32_t* box_inds;
@@ -182,6 +184,7 @@ struct LossArgs {
   float* losses;
   float dlw;
 };
-cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st);
+cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st,
+                        cudaEvent_t wait_before_kd);
 
 }  // namespace erd

@@ -32,23 +32,40 @@ __device__ __forceinline__ void ers_tile(const Geo& g, const Workspace& ws, cons
   const float* bplane = box + (size_t)n * kBoxCh * HW;
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
-    float z[kBins][4];
+    // one streaming pass per side: exponentials are taken relative to the first bin, so no
+    // 17-value register tile is needed; a non-finite sum (logit spread > 88) redoes the side
+    // with the true maximum.
+    const float* splane = bplane + (size_t)(s * kBins) * HW;
+    float ref[4], sum[4], num[4], mx[4];
+    q.load(splane, ref, 0.f);
 #pragma unroll
-    for (int j = 0; j < kBins; ++j) q.load(bplane + (size_t)(s * kBins + j) * HW, z[j], 0.f);
+    for (int k = 0; k < 4; ++k) { sum[k] = 1.f; num[k] = 0.f; mx[k] = ref[k]; }
+#pragma unroll 4
+    for (int j = 1; j < kBins; ++j) {
+      float v[4];
+      q.load(splane + (size_t)j * HW, v, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float e = expf(v[k] - ref[k]);
+        sum[k] += e;
+        num[k] = fmaf((float)j, e, num[k]);
+        mx[k] = fmaxf(mx[k], v[k]);
+      }
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float mx = z[0][k];
-#pragma unroll
-      for (int j = 1; j < kBins; ++j) mx = fmaxf(mx, z[j][k]);
-      float sum = 0.f, num = 0.f;
-#pragma unroll
-      for (int j = 0; j < kBins; ++j) {
-        const float e = expf(z[j][k] - mx);
-        sum += e;
-        num = fmaf((float)j, e, num);
+      if (!(sum[k] < 3.0e38f) || !(num[k] < 3.0e38f)) {   // overflow: exact two-pass fallback
+        float s2 = 0.f, n2 = 0.f;
+        for (int j = 0; j < kBins; ++j) {
+          const float e = expf(__ldg(splane + (size_t)j * HW + q.hw[k]) - mx[k]);
+          s2 += e;
+          n2 = fmaf((float)j, e, n2);
+        }
+        sum[k] = s2;
+        num[k] = n2;
       }
-      dist[k][s] = __fdiv_rn(num, sum);
-      u[k] = fmaxf(u[k], mx);
+      dist[k][s] = __fdiv_rn(num[k], sum[k]);
+      u[k] = fmaxf(u[k], mx[k]);
     }
   }
   const size_t base = (size_t)n * g.A + g.start[l];
@@ -94,19 +111,23 @@ __global__ void __launch_bounds__(kTileThreads) ers_scan_kernel(Geo g, Workspace
 }
 
 // ----------------------------------------------------------------------------- pass 2
-// One CTA per image: thr = mean + 2 * std (unbiased), rows strictly above it are written in
-// ascending anchor order (what nonzero() yields, gfl_increment_erd.py:150-151,158-159).
-constexpr int kSelThreads = 1024;
+// thr = mean + 2 * std (unbiased); rows strictly above it, in ascending anchor order (what
+// nonzero() yields, gfl_increment_erd.py:150-151,158-159).  Each CTA owns a 2048-anchor chunk
+// of one image; it recounts the flags of the anchors before its chunk from the L2-resident
+// cache instead of waiting on a cross-CTA prefix, so one launch suffices.
+constexpr int kSelThreads = 256;
+constexpr int kSelPer = 8;
+constexpr int kSelChunk = kSelThreads * kSelPer;
 
 __global__ void __launch_bounds__(kSelThreads) ers_select_kernel(Geo g, Workspace ws, int tiles, int32_t* cls_inds,
                                                                  int32_t* cls_count, int32_t* box_inds,
                                                                  int32_t* box_count, float* thr_out,
                                                                  uint8_t* __restrict__ sel_flags) {
-  const int n = blockIdx.x;
+  const int n = blockIdx.y;
+  const int chunk0 = blockIdx.x * kSelChunk;
   __shared__ float s_thr[2];
   __shared__ int s_warp[2][kSelThreads / 32];
   __shared__ int s_base[2];
-  __shared__ int s_tot[2];
   if (threadIdx.x < 2) {
     double s1 = 0.0, s2 = 0.0;
     const double* p = ws.ers_part + (size_t)n * tiles * 4 + threadIdx.x * 2;
@@ -117,69 +138,71 @@ __global__ void __launch_bounds__(kSelThreads) ers_select_kernel(Geo g, Workspac
     if (var < 0.0) var = 0.0;
     const float t = __fadd_rn((float)mean, __fmul_rn(2.0f, (float)sqrt(var)));
     s_thr[threadIdx.x] = t;
-    thr_out[n * 2 + threadIdx.x] = t;
-    s_base[threadIdx.x] = 0;
+    if (blockIdx.x == 0) thr_out[n * 2 + threadIdx.x] = t;
   }
   __syncthreads();
   const float thr_c = s_thr[0], thr_b = s_thr[1];
   const float* m = ws.t_m + (size_t)n * g.A;
   const float* u = ws.t_u + (size_t)n * g.A;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // selected rows before this chunk
+  int pc = 0, pb = 0;
+  for (int a = threadIdx.x; a < chunk0; a += kSelThreads) {
+    pc += m[a] > thr_c;
+    pb += u[a] > thr_b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pc += __shfl_xor_sync(0xffffffffu, pc, o);
+    pb += __shfl_xor_sync(0xffffffffu, pb, o);
+  }
+  if (lane == 0) { s_warp[0][warp] = pc; s_warp[1][warp] = pb; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    int t = 0;
+    for (int w = 0; w < kSelThreads / 32; ++w) t += s_warp[threadIdx.x][w];
+    s_base[threadIdx.x] = t;
+  }
+  __syncthreads();
+  // this chunk: 8 consecutive anchors per thread, block-wide exclusive scan of the counts
+  const int a0 = chunk0 + threadIdx.x * kSelPer;
+  unsigned fc = 0, fb = 0;
+#pragma unroll
+  for (int k = 0; k < kSelPer; ++k) {
+    const bool in = a0 + k < g.A;
+    const bool c = in && (m[a0 + k] > thr_c), b = in && (u[a0 + k] > thr_b);
+    fc |= (unsigned)c << k;
+    fb |= (unsigned)b << k;
+    if (in) sel_flags[(size_t)n * g.A + a0 + k] = (uint8_t)((c ? 1 : 0) | (b ? 2 : 0));
+  }
+  const int nc = __popc(fc), nb = __popc(fb);
+  int ic = nc, ib = nb;   // inclusive warp scans
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int tc = __shfl_up_sync(0xffffffffu, ic, o);
+    const int tb = __shfl_up_sync(0xffffffffu, ib, o);
+    if (lane >= o) { ic += tc; ib += tb; }
+  }
+  __syncthreads();
+  if (lane == 31) { s_warp[0][warp] = ic; s_warp[1][warp] = ib; }
+  __syncthreads();
+  int oc = s_base[0] + ic - nc, ob = s_base[1] + ib - nb;
+  int totc = 0, totb = 0;
+  for (int w = 0; w < kSelThreads / 32; ++w) {
+    if (w < warp) { oc += s_warp[0][w]; ob += s_warp[1][w]; }
+    totc += s_warp[0][w];
+    totb += s_warp[1][w];
+  }
   int32_t* out_c = cls_inds + (size_t)n * g.sel_cap;
   int32_t* out_b = box_inds + (size_t)n * g.sel_cap;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int a0 = 0; a0 < g.A; a0 += kSelThreads * 4) {
-    const int a = a0 + threadIdx.x * 4;
-    bool fc[4], fb[4];
-    int nc = 0, nb = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool in = a + k < g.A;
-      fc[k] = in && (m[a + k] > thr_c);
-      fb[k] = in && (u[a + k] > thr_b);
-      nc += fc[k];
-      nb += fb[k];
-      if (in) sel_flags[(size_t)n * g.A + a + k] = (uint8_t)((fc[k] ? 1 : 0) | (fb[k] ? 2 : 0));
-    }
-    int pc = nc, pb = nb;   // inclusive warp scans
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int tc = __shfl_up_sync(0xffffffffu, pc, o);
-      const int tb = __shfl_up_sync(0xffffffffu, pb, o);
-      if (lane >= o) { pc += tc; pb += tb; }
-    }
-    if (lane == 31) { s_warp[0][warp] = pc; s_warp[1][warp] = pb; }
-    __syncthreads();
-    if (warp == 0) {
-      const int vc = s_warp[0][lane], vb = s_warp[1][lane];
-      int ic = vc, ib = vb;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int tc = __shfl_up_sync(0xffffffffu, ic, o);
-        const int tb = __shfl_up_sync(0xffffffffu, ib, o);
-        if (lane >= o) { ic += tc; ib += tb; }
-      }
-      s_warp[0][lane] = ic - vc;   // exclusive offsets of each warp inside this chunk
-      s_warp[1][lane] = ib - vb;
-      if (lane == 31) { s_tot[0] = ic; s_tot[1] = ib; }
-    }
-    __syncthreads();
-    int oc = s_base[0] + s_warp[0][warp] + pc - nc;
-    int ob = s_base[1] + s_warp[1][warp] + pb - nb;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (fc[k]) out_c[oc++] = a + k;
-      if (fb[k]) out_b[ob++] = a + k;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      s_base[0] += s_tot[0];
-      s_base[1] += s_tot[1];
-    }
-    __syncthreads();
+  for (int k = 0; k < kSelPer; ++k) {
+    if (fc & (1u << k)) out_c[oc++] = a0 + k;
+    if (fb & (1u << k)) out_b[ob++] = a0 + k;
   }
-  if (threadIdx.x == 0) {
-    cls_count[n] = s_base[0];
-    box_count[n] = s_base[1];
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    cls_count[n] = s_base[0] + totc;
+    box_count[n] = s_base[1] + totb;
   }
 }
 
@@ -189,7 +212,8 @@ cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, con
   const int tiles = g.tile_start[kLevels];
   ERD_LAUNCH(kKErsScan, st, (ers_scan_kernel<<<dim3(tiles, g.n_img), kTileThreads, 0, st>>>(g, ws, t_cls, t_box)));
   ERD_LAUNCH(kKErsSelect, st,
-             (ers_select_kernel<<<g.n_img, kSelThreads, 0, st>>>(g, ws, tiles, cls_inds, cls_count, box_inds,
+             (ers_select_kernel<<<dim3((g.A + kSelChunk - 1) / kSelChunk, g.n_img), kSelThreads, 0, st>>>(
+                 g, ws, tiles, cls_inds, cls_count, box_inds,
                                                                  box_count, thr, sel_flags)));
   return cudaGetLastError();
 }

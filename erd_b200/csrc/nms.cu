@@ -5,6 +5,7 @@
 // boxes_for_nms = boxes + class_id * (boxes.max() + 1); visit by descending score; area
 // (x2-x1)*(y2-y1); suppress when inter / (area_i + area_j - inter) > thr; kept indices are
 // returned in visiting order.  All box arithmetic is IEEE fp32 without contraction.
+// Pairs with an empty intersection are decided without the division (ovr = 0 <= thr).
 #include "erd_common.cuh"
 
 namespace erd {
@@ -83,98 +84,132 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(Geo g, Workspace
   (void)pow2_cap;
 }
 
-// Suppression bit matrix over score-ordered boxes: bit j of mask[i][cb] is set when box
-// cb*64+j (j > i) overlaps box i above the threshold.  Only tiles with cb >= rb are written.
-__global__ void __launch_bounds__(64) nms_mask_kernel(Geo g, Workspace ws, const int32_t* __restrict__ box_count,
-                                                      float iou_thr) {
+// Predecessor bit matrix over score-ordered boxes: bit i of pred[j][rb] is set when box
+// rb*64+i, ranked before j, overlaps box j above the threshold.  Only tiles with rb <= cb
+// are written.  256 threads per 64x64 tile: four threads share a column, 16 rows each.
+constexpr int kMaskThreads = 256;
+
+__device__ __forceinline__ bool nms_overlaps(const float4& a, float area_a, const float4& b, float area_b,
+                                             float iou_thr) {
+  const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+  const float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+  if (!(w > 0.f) || !(h > 0.f)) return 0.f > iou_thr;   // inter == 0: ovr is 0 (or NaN for empty boxes)
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return ovr > iou_thr;
+}
+
+__global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace ws,
+                                                                const int32_t* __restrict__ box_count,
+                                                                float iou_thr) {
   const int n = blockIdx.y;
   const int K = box_count[n];
   const int W = (K + 63) >> 6;
   const int Wcap = nms_words(g.sel_cap);
   const float4* boxes = ws.nms_box + (size_t)n * g.sel_cap;
-  unsigned long long* mask = ws.nms_mask + (size_t)n * g.sel_cap * Wcap;
-  __shared__ float4 s_col[64];
+  unsigned long long* pred = ws.nms_mask + (size_t)n * g.sel_cap * Wcap;
+  __shared__ float4 s_row[64];
   __shared__ float s_area[64];
+  const int col = threadIdx.x >> 2, part = threadIdx.x & 3;
   const int ntile = W * (W + 1) / 2;
   for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
-    // t -> (rb, cb) with cb >= rb, row-major over the upper triangle
-    int rb = 0, rem = t;
+    int rb = 0, rem = t;   // t -> (rb, cb), cb >= rb, row-major over the upper triangle
     while (rem >= W - rb) { rem -= W - rb; ++rb; }
     const int cb = rb + rem;
     __syncthreads();
-    const int cj = cb * 64 + threadIdx.x;
-    if (cj < K) {
-      const float4 b = boxes[cj];
-      s_col[threadIdx.x] = b;
+    if (threadIdx.x < 64) {
+      const int i = rb * 64 + threadIdx.x;
+      const float4 b = i < K ? boxes[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s_row[threadIdx.x] = b;
       s_area[threadIdx.x] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
     }
     __syncthreads();
-    const int i = rb * 64 + threadIdx.x;
-    if (i < K) {
-      const float4 a = boxes[i];
+    const int j = cb * 64 + col;
+    unsigned long long bits = 0ull;
+    if (j < K) {
+      const float4 a = boxes[j];
       const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
-      unsigned long long bits = 0ull;
-      const int ncol = min(64, K - cb * 64);
-      const int j0 = (rb == cb) ? threadIdx.x + 1 : 0;
-      for (int j = j0; j < ncol; ++j) {
-        const float4 b = s_col[j];
-        const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
-        const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
-        const float inter = __fmul_rn(w, h);
-        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, s_area[j]), inter));
-        if (ovr > iou_thr) bits |= 1ull << j;
-      }
-      mask[(size_t)i * Wcap + cb] = bits;
+      const int rmax = (rb == cb) ? col : min(64, K - rb * 64);   // only boxes ranked before j
+#pragma unroll 4
+      for (int r = part * 16; r < part * 16 + 16; ++r)
+        if (r < rmax && nms_overlaps(s_row[r], s_area[r], a, area_a, iou_thr)) bits |= 1ull << r;
     }
+    bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+    bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+    if (part == 0 && j < K) pred[(size_t)j * Wcap + rb] = bits;
   }
 }
 
-// Greedy pass, one warp per image.  64-box chunks: the in-chunk dependency is resolved on
-// the diagonal words held in registers; rows of surviving boxes are then OR-ed into the
-// running removal mask of the later chunks (lane-strided words in shared memory).
-__global__ void __launch_bounds__(32) nms_scan_kernel(Geo g, Workspace ws, const int32_t* __restrict__ box_count,
-                                                      int32_t* __restrict__ keep, int32_t* __restrict__ keep_count) {
-  extern __shared__ unsigned long long s_remv[];
+// Greedy NMS as rounds over the predecessor matrix, one CTA per image: a box is suppressed
+// as soon as a kept predecessor overlaps it and kept once every overlapping predecessor is
+// decided and none is kept -- exactly the sequential greedy result, in as many rounds as the
+// longest overlap chain.  Each round reads the previous round's state (double buffered).
+constexpr int kResThreads = 512;
+
+__global__ void __launch_bounds__(kResThreads) nms_resolve_kernel(Geo g, Workspace ws,
+                                                                  const int32_t* __restrict__ box_count,
+                                                                  int32_t* __restrict__ keep,
+                                                                  int32_t* __restrict__ keep_count) {
+  extern __shared__ unsigned long long s_state[];   // kept[W] decided[W] kept_next[W] decided_next[W]
   const int n = blockIdx.x;
-  const int lane = threadIdx.x;
   const int K = box_count[n];
   const int W = (K + 63) >> 6;
   const int Wcap = nms_words(g.sel_cap);
-  const unsigned long long* mask = ws.nms_mask + (size_t)n * g.sel_cap * Wcap;
+  unsigned long long* kept = s_state;
+  unsigned long long* dec = s_state + Wcap;
+  unsigned long long* kept_n = s_state + 2 * Wcap;
+  unsigned long long* dec_n = s_state + 3 * Wcap;
+  const unsigned long long* pred = ws.nms_mask + (size_t)n * g.sel_cap * Wcap;
+  for (int w = threadIdx.x; w < 4 * Wcap; w += kResThreads) s_state[w] = 0ull;
+  __syncthreads();
+  int pending = K > 0;
+  while (pending) {
+    int undecided = 0;
+    for (int j = threadIdx.x; j < K; j += kResThreads) {
+      const int wj = j >> 6;
+      const unsigned long long bit = 1ull << (j & 63);
+      if (dec[wj] & bit) continue;
+      bool sup = false, wait = false;
+      const unsigned long long* row = pred + (size_t)j * Wcap;
+      for (int w = 0; w <= wj; ++w) {
+        const unsigned long long pr = row[w];
+        if (!pr) continue;
+        if (pr & kept[w]) { sup = true; break; }
+        if (pr & ~dec[w]) wait = true;
+      }
+      if (sup) {
+        atomicOr(dec_n + wj, bit);
+      } else if (!wait) {
+        atomicOr(kept_n + wj, bit);
+        atomicOr(dec_n + wj, bit);
+      } else {
+        undecided = 1;
+      }
+    }
+    pending = __syncthreads_or(undecided);
+    for (int w = threadIdx.x; w < W; w += kResThreads) { kept[w] = kept_n[w]; dec[w] = dec_n[w]; }
+    __syncthreads();
+  }
+  // survivors in score order: exclusive prefix of the per-word popcounts (W <= a few hundred)
+  __shared__ int s_total;
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int w = 0; w < W; ++w) {
+      const int c = __popcll(kept[w]);
+      dec[w] = (unsigned long long)run;
+      run += c;
+    }
+    s_total = run;
+  }
+  __syncthreads();
   const int* order = ws.nms_order + (size_t)n * g.sel_cap;
   int32_t* out = keep + (size_t)n * g.sel_cap;
-  for (int w = lane; w < W; w += 32) s_remv[w] = 0ull;
-  __syncwarp();
-  int nkeep = 0;
-  for (int c = 0; c < W; ++c) {
-    const int rows = min(64, K - c * 64);
-    // diagonal words of this chunk: lane holds rows lane and lane + 32
-    const unsigned long long d_lo = lane < rows ? mask[(size_t)(c * 64 + lane) * Wcap + c] : 0ull;
-    const unsigned long long d_hi = lane + 32 < rows ? mask[(size_t)(c * 64 + lane + 32) * Wcap + c] : 0ull;
-    unsigned long long alive = ~s_remv[c];
-    if (rows < 64) alive &= (1ull << rows) - 1ull;
-#pragma unroll 4
-    for (int t = 0; t < 64; ++t) {
-      const unsigned long long d = __shfl_sync(0xffffffffu, t < 32 ? d_lo : d_hi, t & 31);
-      if ((alive >> t) & 1ull) alive &= ~d;
-    }
-    // emit survivors in score order
-    const unsigned long long below_lo = alive & ((1ull << lane) - 1ull);
-    const unsigned long long below_hi = alive & ((1ull << (lane + 32)) - 1ull);
-    if ((alive >> lane) & 1ull) out[nkeep + __popcll(below_lo)] = order[c * 64 + lane];
-    if ((alive >> (lane + 32)) & 1ull) out[nkeep + __popcll(below_hi)] = order[c * 64 + lane + 32];
-    nkeep += __popcll(alive);
-    // fold the survivors' rows into the removal mask of later chunks
-    unsigned long long todo = alive;
-    while (todo) {
-      const int t = __ffsll((long long)todo) - 1;
-      todo &= todo - 1ull;
-      const unsigned long long* row = mask + (size_t)(c * 64 + t) * Wcap;
-      for (int w = c + 1 + lane; w < W; w += 32) s_remv[w] |= row[w];
-    }
-    __syncwarp();
+  for (int j = threadIdx.x; j < K; j += kResThreads) {
+    const int wj = j >> 6;
+    const unsigned long long kw = kept[wj];
+    if (kw & (1ull << (j & 63))) out[(int)dec[wj] + __popcll(kw & ((1ull << (j & 63)) - 1ull))] = order[j];
   }
-  if (lane == 0) keep_count[n] = nkeep;
+  if (threadIdx.x == 0) keep_count[n] = s_total;
 }
 
 cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_inds, const int32_t* box_count,
@@ -190,9 +225,11 @@ cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_ind
   if (sort_smem > 200 * 1024) return cudaErrorInvalidValue;
   ERD_LAUNCH(kKNmsSort, st,
              (nms_sort_kernel<<<g.n_img, kSortThreads, sort_smem, st>>>(g, ws, box_inds, box_count, pad_hw, P)));
-  ERD_LAUNCH(kKNmsMask, st, (nms_mask_kernel<<<dim3(64, g.n_img), 64, 0, st>>>(g, ws, box_count, iou_thr)));
-  const size_t scan_smem = sizeof(unsigned long long) * (size_t)nms_words(g.sel_cap);
-  ERD_LAUNCH(kKNmsScan, st, (nms_scan_kernel<<<g.n_img, 32, scan_smem, st>>>(g, ws, box_count, keep, keep_count)));
+  ERD_LAUNCH(kKNmsMask, st,
+             (nms_mask_kernel<<<dim3(48, g.n_img), kMaskThreads, 0, st>>>(g, ws, box_count, iou_thr)));
+  const size_t res_smem = sizeof(unsigned long long) * 4 * (size_t)nms_words(g.sel_cap);
+  ERD_LAUNCH(kKNmsScan, st,
+             (nms_resolve_kernel<<<g.n_img, kResThreads, res_smem, st>>>(g, ws, box_count, keep, keep_count)));
   return cudaGetLastError();
 }
 

@@ -8,8 +8,8 @@
 namespace erd {
 
 static const char* kKernelNames[kNumKernels] = {"ers_scan", "ers_select", "atss_candidates", "atss_finalize",
-                                                "avg", "nms_sort", "nms_mask", "nms_scan", "upstream_check",
-                                                "loss_main", "kd", "finalize"};
+                                                "pos_prepass", "nms_sort", "nms_mask", "nms_resolve", "upstream_check",
+                                                "loss_main", "pos_grad", "kd", "finalize"};
 
 struct ProfState {
   std::mutex mu;

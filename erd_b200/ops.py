@@ -181,8 +181,9 @@ class ErdPath:
                                          p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(), p.gt_inds.data_ptr(),
                                          p.num_pos.data_ptr(), p.ws.data_ptr(), _stream()), 'erd_atss_assign')
 
-    def avg_factors(self, p: Plan, s_cls):
-        N.check(self.lib.erd_avg_factors(C.byref(p.shape), _ptrs(s_cls), p.gt_labels.data_ptr(),
+    def avg_factors(self, p: Plan, s_cls, s_box):
+        N.check(self.lib.erd_avg_factors(C.byref(p.shape), _ptrs(s_cls), _ptrs(s_box), p.gt_boxes.data_ptr(),
+                                         p.gt_labels.data_ptr(),
                                          p.gt_offsets.data_ptr(), p.gt_inds.data_ptr(), p.num_pos.data_ptr(),
                                          p.avg.data_ptr(), p.ws.data_ptr(), _stream()), 'erd_avg_factors')
 
@@ -198,17 +199,17 @@ class ErdPath:
     def loss_fwd_bwd(self, p: Plan, t_cls, t_box, s_cls, s_box, g_cls, g_box, losses, dist_loss_weight: float,
                      upstream: Optional[torch.Tensor] = None, skip_if_unit: bool = False):
         N.check(self.lib.erd_loss_fwd_bwd(
-            C.byref(p.shape), _ptrs(s_cls), _ptrs(s_box), _ptrs(t_cls), _ptrs(t_box), p.gt_boxes.data_ptr(),
+            self._context(p.device), C.byref(p.shape), _ptrs(s_cls), _ptrs(s_box), _ptrs(t_cls), _ptrs(t_box), p.gt_boxes.data_ptr(),
             p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(), p.gt_inds.data_ptr(),
-            p.cls_count.data_ptr(), p.sel_flags.data_ptr(), p.box_inds.data_ptr(), p.keep.data_ptr(),
+            p.num_pos.data_ptr(), p.cls_count.data_ptr(), p.sel_flags.data_ptr(), p.box_inds.data_ptr(), p.keep.data_ptr(),
             p.keep_count.data_ptr(), p.avg.data_ptr(), float(dist_loss_weight),
             upstream.data_ptr() if upstream is not None else None, 1 if skip_if_unit else 0,
             losses.data_ptr(), _ptrs(g_cls), _ptrs(g_box), p.ws.data_ptr(), _stream()), 'erd_loss_fwd_bwd')
 
     # ---- fused step -------------------------------------------------------------------
-    def prepare(self, p: Plan, t_cls, t_box, s_cls, ers_done: bool = False):
+    def prepare(self, p: Plan, t_cls, t_box, s_cls, s_box, ers_done: bool = False):
         N.check(self.lib.erd_step_prepare(
-            self._context(p.device), C.byref(p.shape), _ptrs(t_cls), _ptrs(t_box), _ptrs(s_cls),
+            self._context(p.device), C.byref(p.shape), _ptrs(t_cls), _ptrs(t_box), _ptrs(s_cls), _ptrs(s_box),
             p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(),
             self.nms_iou_thr, C.byref(p.bufs), p.ws.data_ptr(), _stream(), 1 if ers_done else 0),
             'erd_step_prepare')
@@ -233,7 +234,7 @@ class ErdPath:
         if g_box is None:
             g_box = [torch.empty_like(t) for t in s_box]
         losses = torch.empty(p.num_losses, dtype=torch.float32, device=p.device)
-        self.prepare(p, t_cls, t_box, s_cls, ers_done)
+        self.prepare(p, t_cls, t_box, s_cls, s_box, ers_done)
         self.reduce_avg(p)
         self.loss_fwd_bwd(p, t_cls, t_box, s_cls, s_box, g_cls, g_box, losses, dist_loss_weight, upstream)
         return p, losses, g_cls, g_box

@@ -112,10 +112,13 @@ int erd_atss_assign(const ErdShape* shape, const float* gt_boxes, const int64_t*
  * (mmdet/utils/dist_utils.py:59-65): avg[0] = sum_img max(num_pos,1),
  * avg[1] = sum over positives of max_c sigmoid(student new-class logits).
  * The caller divides by world size, all-reduces (SUM) and hands the buffer to
- * erd_loss_fwd_bwd, which applies clamp(min=1) to avg[1]. */
-int erd_avg_factors(const ErdShape* shape, const float* const* s_cls, const int64_t* gt_labels,
-                    const int32_t* gt_offsets, const int32_t* gt_inds, const int32_t* num_pos,
-                    float* avg, void* ws, void* stream);
+ * erd_loss_fwd_bwd, which applies clamp(min=1) to avg[1].  The same pass decodes the positives
+ * (softmax integral, gfl_head_increment_erd.py:285-292) and keeps their IoU quality scores and
+ * the GIoU / DFL loss sums in `ws` for erd_loss_fwd_bwd. */
+int erd_avg_factors(const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
+                    const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                    const int32_t* gt_inds, const int32_t* num_pos, float* avg, void* ws,
+                    void* stream);
 
 /* Teacher box decode + class-aware greedy IoU-NMS (threshold `iou_thr`, 0.005 in the
  * reference) over the ERS-selected rows.  Replaces the mmcv.ops.batched_nms call and the
@@ -141,11 +144,16 @@ int erd_teacher_nms(const ErdShape* shape, const int32_t* box_inds, const int32_
  * gradients only when the caller weighted the loss terms, without a host sync.
  * losses: (num_losses,) fp32 in the order of ErdSizes.num_losses.
  * g_cls[l] (N,C,H_l,W_l) / g_box[l] (N,4*(reg_max+1),H_l,W_l): dense NCHW gradients,
- * fully overwritten. */
-int erd_loss_fwd_bwd(const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
+ * fully overwritten.
+ * ctx: NULL, or the context erd_step_prepare ran on -- the teacher NMS it forked is then
+ * joined in front of the one kernel that needs the keep lists.  Must follow erd_avg_factors
+ * (or erd_step_prepare) on the same workspace. */
+int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const* s_cls,
+                     const float* const* s_box,
                      const float* const* t_cls, const float* const* t_box, const float* gt_boxes,
                      const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
-                     const int32_t* gt_inds, const int32_t* cls_count, const uint8_t* sel_flags,
+                     const int32_t* gt_inds, const int32_t* num_pos, const int32_t* cls_count,
+                     const uint8_t* sel_flags,
                      const int32_t* box_inds, const int32_t* keep, const int32_t* keep_count,
                      const float* avg, float dist_loss_weight, const float* upstream,
                      int32_t skip_if_unit_upstream, float* losses, float* const* g_cls, float* const* g_box, void* ws,
@@ -153,7 +161,8 @@ int erd_loss_fwd_bwd(const ErdShape* shape, const float* const* s_cls, const flo
 
 /* One training-step worth of the path in two calls around the caller's all-reduce:
  * erd_step_prepare = erd_ers_select + erd_atss_assign + erd_avg_factors + erd_teacher_nms
- * (forked over the context's helper streams, joined back into `stream`);
+ * (forked over the context's helper streams; assignment and avg factors are joined back into
+ * `stream`, the NMS is joined by erd_loss_fwd_bwd(ctx, ...));
  * erd_step_loss = erd_loss_fwd_bwd.  Replaces GFLIncrementERD.loss
  * (detectors/gfl_increment_erd.py:202-220) minus the conv stacks. */
 typedef struct ErdStepBuffers {
@@ -171,8 +180,8 @@ typedef struct ErdStepBuffers {
 } ErdStepBuffers;
 
 int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const* t_cls,
-                     const float* const* t_box, const float* const* s_cls, const float* gt_boxes,
-                     const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
+                     const float* const* t_box, const float* const* s_cls, const float* const* s_box,
+                     const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
                      float iou_thr, const ErdStepBuffers* buf, void* ws, void* stream,
                      uint32_t flags);
 /* flags for erd_step_prepare */
