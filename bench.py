@@ -184,35 +184,72 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    nk = lib.erd_profile_num_kernels()
+    names = [lib.erd_profile_kernel_name(i).decode() for i in range(nk)]
+    dom = 'loss_main'
+
+    def collect():
+        tot, cnt = (C.c_float * nk)(), (C.c_int * nk)()
+        lib.erd_profile_collect(tot, cnt)
+        return {names[i]: (tot[i] / cnt[i] if cnt[i] else 0.0) for i in range(nk)}
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     barrier()
-    lib.erd_profile_enable(1)
+    # (1) eager launches, K steps, CUDA events around the dominant kernel only (roofline line)
+    lib.erd_profile_enable(1 << names.index(dom))
     launches0 = lib.erd_launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_eager = timed(step, args.steps)
     launches = lib.erd_launch_count() - launches0
     lib.erd_profile_enable(0)
-    nk = lib.erd_profile_num_kernels()
-    tot, cnt = (C.c_float * nk)(), (C.c_int * nk)()
-    lib.erd_profile_collect(tot, cnt)
-    kern = {lib.erd_profile_kernel_name(i).decode(): (tot[i] / cnt[i] if cnt[i] else 0.0) for i in range(nk)}
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    dom_ms = collect()[dom]
+    # (2) the same K steps replayed from one CUDA graph (no per-launch CPU cost): the headline value
+    sampler = ClockSampler(local)
+    ms_graph, graph_err = None, None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        for _ in range(warm):
+            graph.replay()
+        if rank == 0:
+            sampler.start()
+        ms_graph = timed(graph.replay, args.steps)
+    except Exception as e:  # fall back to the eager number, say why
+        graph_err = repr(e)[:200]
+        if rank == 0:
+            sampler.start()
+        ms_eager = timed(step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ms_graph if ms_graph is not None else ms_eager
     ms_step = ms_total / args.steps
     value = world * n * A / (ms_step * 1e-3)
+    # (3) per-kernel breakdown (all kernels bracketed by events; informational, not the timed run)
+    lib.erd_profile_enable((1 << nk) - 1)
+    for _ in range(10):
+        step()
+    torch.cuda.synchronize()
+    lib.erd_profile_enable(0)
+    kern = collect()
 
     # ---- e2e: the reference-facing plugin API with HOST buffers (pinned), H2D of every head
     # output and D2H of the loss vector inside the timed region, autograd backward included.
@@ -267,12 +304,10 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get('hbm_gbs', 6650.0))
-        dom = 'loss_main'
-        dom_ms = kern.get(dom, 0.0)
         achieved = (n * A * BYTES_PER_ANCHOR[dom]) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'GFL R50-FPN 40+40 ERD loss fwd+bwd, {n} img/GPU 800x1333, 80-class head, '
                                    f'reg_max=16 (BASELINE.json configs[1])', 'anchors_per_image': A,
@@ -284,7 +319,10 @@ def run_ours(args):
                          'algorithmic_bytes_per_anchor': BYTES_PER_ANCHOR[dom],
                          'path_bytes_per_anchor': BYTES_PER_ANCHOR['path'],
                          'path_achieved_gbs': n * A * BYTES_PER_ANCHOR['path'] / (ms_step * 1e-3) / 1e9,
-                         'kernel_ms': {k: round(v, 5) for k, v in kern.items() if v}},
+                         'kernel_ms_dominant_in_timed_eager_run': round(dom_ms, 5),
+                         'kernel_ms_breakdown_pass': {k: round(v, 5) for k, v in kern.items() if v}},
+            'launch_mode': {'value_from': 'cuda_graph_replay' if ms_graph is not None else 'eager',
+                            'ms_per_step_eager': ms_eager / args.steps, 'graph_error': graph_err},
             'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e,
         }
         if not args.no_cpu_baseline and world == 1:

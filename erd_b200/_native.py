@@ -53,7 +53,7 @@ SIGNATURES = {
                          _P, _P, _F, _P, _I, _P, PtrArray, PtrArray, _P, _P],
     'erd_step_prepare': [_P, _SH, PtrArray, PtrArray, PtrArray, PtrArray, _P, _P, _P, _P, _F,
                          C.POINTER(ErdStepBuffers), _P, _P, C.c_uint32],
-    'erd_profile_enable': [C.c_int],
+    'erd_profile_enable': [C.c_uint],
     'erd_launch_count': [],
     'erd_profile_num_kernels': [],
     'erd_profile_kernel_name': [C.c_int],

@@ -32,12 +32,24 @@ struct QflTerm {
   float loss, grad;
 };
 
-// sigma and softplus from one exp: e = exp(-|x|)
+// sigma and softplus from one exp: e = exp(-|x|) in (0, 1].
+//   sigma    = 1/(1+e) for x >= 0, e/(1+e) otherwise
+//   softplus = max(x, 0) + log1p(e), with log1p(e) = 2 atanh(s), s = e / (2 + e) in [0, 1/3]:
+//              the odd series through s^13 is exact to ~1e-7 relative on the whole range,
+//              without the cancellation a log(1+e) has for the small e of background anchors.
 __device__ __forceinline__ void sig_sp(float x, float& sig, float& sp) {
   const float e = __expf(-fabsf(x));
   const float r = __fdividef(1.0f, 1.0f + e);
   sig = x >= 0.f ? r : e * r;
-  sp = fmaxf(x, 0.f) + log1pf(e);
+  const float s = __fdividef(e, 2.0f + e);
+  const float s2 = s * s;
+  float p = fmaf(s2, 1.0f / 13.0f, 1.0f / 11.0f);
+  p = fmaf(p, s2, 1.0f / 9.0f);
+  p = fmaf(p, s2, 1.0f / 7.0f);
+  p = fmaf(p, s2, 1.0f / 5.0f);
+  p = fmaf(p, s2, 1.0f / 3.0f);
+  p = fmaf(p, s2, 1.0f);
+  sp = fmaf(2.0f * s, p, fmaxf(x, 0.f));
 }
 
 // negatives: BCE(x, 0) * sigma^2 (gfocal_loss.py:36-41)

@@ -13,7 +13,7 @@ static const char* kKernelNames[kNumKernels] = {"ers_scan", "ers_select", "atss_
 
 struct ProfState {
   std::mutex mu;
-  bool enabled = false;
+  unsigned int mask = 0;   // bit k: time kernel k
   unsigned long long launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[kNumKernels];
   std::vector<cudaEvent_t> pool;
@@ -34,15 +34,15 @@ static cudaEvent_t take_event() {
 void prof_begin(int id, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
   ++g_prof.launches;
-  if (!g_prof.enabled) return;
+  if (!(g_prof.mask >> id & 1u)) return;
   cudaEvent_t a = take_event(), b = take_event();
   cudaEventRecord(a, st);
   g_prof.pending[id].push_back({a, b});
 }
 
 void prof_end(int id, cudaStream_t st) {
-  if (!g_prof.enabled) return;
   std::lock_guard<std::mutex> lk(g_prof.mu);
+  if (!(g_prof.mask >> id & 1u)) return;
   if (!g_prof.pending[id].empty()) cudaEventRecord(g_prof.pending[id].back().second, st);
 }
 
@@ -52,9 +52,9 @@ using namespace erd;
 
 extern "C" {
 
-int erd_profile_enable(int on) {
+int erd_profile_enable(unsigned int kernel_mask) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
-  g_prof.enabled = on != 0;
+  g_prof.mask = kernel_mask;
   return ERD_OK;
 }
 

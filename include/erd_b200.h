@@ -190,7 +190,7 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
 
 /* Launch accounting and optional per-kernel timing (CUDA events on the launching stream).
  * No reference counterpart; bench.py reports roofline numbers from it. */
-int erd_profile_enable(int on);
+int erd_profile_enable(unsigned int kernel_mask);   /* bit k set: time kernel id k; 0 = off */
 unsigned long long erd_launch_count(void);   /* kernels launched by this library so far */
 int erd_profile_num_kernels(void);
 const char* erd_profile_kernel_name(int id);
