@@ -21,7 +21,8 @@ class ErdShape(C.Structure):
                 ('stride', C.c_int32 * MAX_LEVELS), ('total_gt', C.c_int32),
                 ('anchor_scale', C.c_float), ('loss_weight_cls', C.c_float),
                 ('loss_weight_bbox', C.c_float), ('loss_weight_dfl', C.c_float),
-                ('loss_weight_ld', C.c_float), ('kd_temperature', C.c_float)]
+                ('loss_weight_ld', C.c_float), ('kd_temperature', C.c_float),
+                ('max_gt_per_img', C.c_int32)]
 
 
 class ErdSizes(C.Structure):

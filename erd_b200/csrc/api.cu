@@ -54,6 +54,11 @@ static int make_geo(const ErdShape* s, Geo* g) {
   g->tile_start[kLevels] = t;
   g->A = a;
   g->sel_cap = a / 5 + 1;
+  {
+    const long long mg = s->max_gt_per_img > 0 ? s->max_gt_per_img : 128;
+    const long long cap = (long long)kTopK * kLevels * mg;
+    g->pos_cap = (int)(cap < a ? cap : a);
+  }
   return ERD_OK;
 }
 
@@ -77,6 +82,11 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->pos_list = (int*)take(NA * 4);
   ws->pos_score = (float*)take(NA * 4);
   ws->pre_acc = (double*)take((size_t)(2 * kLevels + 1) * 8);
+  ws->kd_acc = (double*)take((size_t)g.n_img * 8);
+  ws->pos_slot = (int*)take(NA * 4);
+  ws->kd_slot = (int*)take(NA * 4);
+  ws->pos_rows = (float*)take((size_t)g.n_img * g.pos_cap * kBoxCh * 4);
+  ws->kd_rows = (float*)take(NS * kBoxCh * 4);
   ws->counters = (unsigned int*)take(8 * 4);
   ws->nms_raw = (float4*)take(NS * 16);
   ws->nms_cls = (int*)take(NS * 4);
@@ -120,7 +130,7 @@ static MPtr5 mptr5(float* const* p) {
 
 struct ErdContext {
   cudaStream_t side[2];          // [0] assignment + positives prepass, [1] teacher NMS
-  cudaEvent_t fork, join[2], sel;
+  cudaEvent_t fork, join[2], sel, kd_wait, kd_done;
   bool nms_pending;              // join[1] recorded by erd_step_prepare, not yet waited on
 };
 
@@ -153,6 +163,8 @@ int erd_create(ErdContext** ctx) {
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sel, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->kd_wait, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->kd_done, cudaEventDisableTiming);
   c->nms_pending = false;
   if (e != cudaSuccess) {
     delete c;
@@ -170,6 +182,8 @@ int erd_destroy(ErdContext* c) {
   }
   cudaEventDestroy(c->fork);
   cudaEventDestroy(c->sel);
+  cudaEventDestroy(c->kd_wait);
+  cudaEventDestroy(c->kd_done);
   delete c;
   return ERD_OK;
 }
@@ -276,10 +290,15 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
   a.skip_flag = (upstream && skip_if_unit_upstream) ? ws.counters + 1 : nullptr;
   a.losses = losses;
   a.dlw = dist_loss_weight;
-  // the teacher NMS forked by erd_step_prepare is joined only in front of the kernel that needs it
-  cudaEvent_t nms_done = (ctx && ctx->nms_pending) ? ctx->join[1] : nullptr;
-  cudaError_t e = launch_loss(g, ws, a, (cudaStream_t)stream, nms_done);
-  if (ctx) ctx->nms_pending = false;
+  // With a context the KD rows are computed on the NMS side stream (behind the NMS that
+  // erd_step_prepare queued there) while the class sweep runs on the caller's stream.
+  cudaError_t e;
+  if (ctx) {
+    e = launch_loss(g, ws, a, (cudaStream_t)stream, ctx->side[1], ctx->kd_wait, ctx->kd_done);
+    ctx->nms_pending = false;   // kd_done, which `stream` now waits on, is behind the NMS
+  } else {
+    e = launch_loss(g, ws, a, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+  }
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_loss_fwd_bwd");
 }
 

@@ -30,6 +30,7 @@ struct Geo {
   int vec[kLevels];             // 1 when hw % 4 == 0 and all level pointers are 16 B aligned
   float half[kLevels];          // anchor half size = 0.5 * stride * scale
   int sel_cap;                  // A/5 + 1
+  int pos_cap;                  // min(A, 45 * max_gt_per_img): rows of the positives' gradient buffer
   int total_gt;
   float w_cls, w_bbox, w_dfl, w_ld, T;   // loss weights and KD temperature
 };
@@ -45,6 +46,11 @@ struct Workspace {
   int* pos_list;                  // [N][A] anchors with an assigned GT (unordered)
   float* pos_score;               // [N][A] IoU quality score, defined at positives only
   double* pre_acc;                // [2L+1] sum w(1-giou) per level, sum w*dfl per level, sum w
+  double* kd_acc;                 // [N] sum w * KL per image
+  int* pos_slot;                  // [N][A] row of pos_rows, defined at positives only
+  int* kd_slot;                   // [N][A] row of kd_rows, defined at NMS survivors only
+  float* pos_rows;                // [N][pos_cap][68] box-logit gradient rows of the positives
+  float* kd_rows;                 // [N][sel_cap][68] box-logit gradient rows of the NMS survivors
   unsigned int* counters;         // [8] last-block tickets
   float4* nms_raw;                // [N][sel_cap] decoded teacher boxes in list order
   int* nms_cls;                   // [N][sel_cap] class ids in list order
@@ -138,7 +144,7 @@ struct Quad {
 
 // ---------------------------------------------------------------- launch accounting (profile.cu)
 enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan,
-                kKUpCheck, kKLossMain, kKPosGrad, kKKd, kKFinalize, kNumKernels };
+                kKUpCheck, kKLossMain, kKPosGrad, kKKd, kKBoxSweep, kKFinalize, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 // ERD_LAUNCH(id, stream, kernel<<<...>>>(...)) counts the launch and, when profiling is on,
@@ -184,7 +190,7 @@ struct LossArgs {
   float* losses;
   float dlw;
 };
-cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st,
-                        cudaEvent_t wait_before_kd);
+cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, cudaStream_t kd_stream,
+                        cudaEvent_t kd_wait, cudaEvent_t kd_done);
 
 }  // namespace erd

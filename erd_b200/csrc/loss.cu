@@ -10,10 +10,14 @@
 // Kernels
 //   pos_kernel<false>  (prepare phase) 4 threads per positive anchor: weight, softmax-integral
 //                      decode, IoU score, GIoU/DFL loss sums, and the two avg factors.
-//   loss_main_kernel   the streaming sweep: QFL on the new-class channels of every anchor,
-//                      zero fill of every other gradient element, class-response L2 rows.
-//   pos_kernel<true>   box-logit gradients of the positives (needs the reduced avg factor).
-//   kd_kernel          DFL-distribution KL on the NMS survivors, added onto the box gradients.
+//   pos_kernel<true>   box-logit gradient rows of the positives (needs the reduced avg factor),
+//                      written to a compact row buffer.
+//   cls_sweep_kernel   streaming sweep over the class logits: QFL on the new-class channels of
+//                      every anchor, class-response L2 on the old-class channels (zero off
+//                      the ERS rows), gradients written once, densely.
+//   kd_kernel          DFL-distribution KL on the NMS survivors -> compact gradient rows.
+//   box_sweep_kernel   dense write of the box-logit gradients: zero, plus the compact rows of
+//                      positives and NMS survivors merged in on the fly (no read-modify-write).
 //   finalize_kernel    accumulators -> the reference's loss values.
 #include "erd_common.cuh"
 
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, P
   }
   const float avg2 = GRAD ? fmaxf(A.avg[1], 1.0f) : 1.0f;
   // whole warps stay together (8 positives per warp) so the quad shuffles are convergent
-  for (int p = (blockIdx.x * kPosThreads + threadIdx.x) >> 2; p < ((np + 7) & ~7);
+  for (int p = (blockIdx.x * kPosThreads + threadIdx.x) >> 2; p < ((np + 7) & ~7) && p < g.pos_cap;
        p += (gridDim.x * kPosThreads) >> 2) {
     const bool live = p < np;
     const int a = live ? ws.pos_list[(size_t)n * g.A + p] : 0;
@@ -201,14 +205,20 @@ __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, P
       else gd = g_uni * wid + g_ih * pick_gt(ty2, py2) + g_eh * pick_gt(py2, ty2);                  // d/dy2
       const float cb = upstream_of(A.upstream, acc_bbox(l)) * g.w_bbox / (1.0f + kEps32) / avg2 * w * gd;
       const float cd = upstream_of(A.upstream, acc_dfl(l)) * g.w_dfl / 4.0f / avg2 * w;
-      float* gplane = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW + hw;
+      float* row = ws.pos_rows + ((size_t)n * g.pos_cap + p) * kBoxCh + side * kBins;
 #pragma unroll
       for (int j = 0; j < kBins; ++j) {
         const float pj = z[j] * inv;
         float gr = cb * pj * ((float)j - dmine);
         gr += cd * (wl * (pj - (j == yl ? 1.f : 0.f)) + wr * (pj - (j == yl + 1 ? 1.f : 0.f)));
-        gplane[(size_t)j * HW] = gr;
+        row[j] = gr;
       }
+      if (side == 0) ws.pos_slot[(size_t)n * g.A + a] = p;
+    } else if (GRAD && live) {   // assigned to a GT whose label lies outside the new-class range: no box loss
+      float* row = ws.pos_rows + ((size_t)n * g.pos_cap + p) * kBoxCh + side * kBins;
+#pragma unroll
+      for (int j = 0; j < kBins; ++j) row[j] = 0.f;
+      if (side == 0) ws.pos_slot[(size_t)n * g.A + a] = p;
     }
   }
   if (GRAD) return;
@@ -232,20 +242,60 @@ __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, P
   }
 }
 
-// ----------------------------------------------------------------------------- the sweep
-struct LossTileOut {
-  float cls, dcls;
-};
+// ----------------------------------------------------------------------------- class sweep
+// grid (tile, image, part): a part is a group of kSweepCh class channels that lies entirely
+// in the old-class range [0, ori) or in the new-class range [ori, C).
+constexpr int kSweepCh = 8;
 
 template <bool VEC>
-__device__ __forceinline__ void loss_tile(const Geo& g, const Workspace& ws, const LossArgs& A, int n, int l,
-                                          int hw0, LossTileOut& out) {
+__device__ __forceinline__ void cls_tile(const Geo& g, const Workspace& ws, const LossArgs& A, int n, int l,
+                                         int hw0, int part, float& out_loss) {
   const int HW = g.hw[l];
   const Quad<VEC> q(hw0, HW);
   const size_t abase = (size_t)n * g.A + g.start[l];
+  const int parts_old = (g.ori + kSweepCh - 1) / kSweepCh;
+  const float* scls = A.s_cls.p[l] + (size_t)n * g.C * HW;
+  float* gcls = A.g_cls.p[l] + (size_t)n * g.C * HW;
+  if (part < parts_old) {
+    // classification-response distillation: 2 (x_s - x_t) / (K ori) on the ERS rows, zero elsewhere
+    // (gfl_head_increment_erd.py:181-186,324-332).  A thread whose four anchors are all
+    // unselected issues no loads at all.
+    const int c0 = part * kSweepCh, c1 = min(c0 + kSweepCh, g.ori);
+    float sel[4];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sel[k] = (q.ok[k] && (A.sel_flags[abase + q.hw[k]] & 1)) ? 1.0f : 0.0f;   // gfl_increment_erd.py:149-151
+      any |= sel[k] != 0.f;
+    }
+    if (!any) {
+      for (int c = c0; c < c1; ++c) q.store_zero(gcls + (size_t)c * HW);
+      return;
+    }
+    const float kc = (float)A.cls_count[n] * (float)g.ori;
+    const float scale_dc = upstream_of(A.upstream, acc_dcls(n)) * A.dlw * 2.0f / kc;
+    const float* tcls = A.t_cls.p[l] + (size_t)n * g.ori * HW;
+    float sq = 0.f;
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c) {
+      float xs[4], xt[4], gr[4];
+      q.load(scls + (size_t)c * HW, xs, 0.f);
+      q.load(tcls + (size_t)c * HW, xt, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float df = sel[k] * (xs[k] - xt[k]);
+        sq = fmaf(df, df, sq);
+        gr[k] = scale_dc * df;
+      }
+      q.store(gcls + (size_t)c * HW, gr);
+    }
+    out_loss += sq;
+    return;
+  }
+  // QFL over new-class channels of every anchor (:260-261,317-320)
+  const int c0 = (part - parts_old) * kSweepCh, c1 = min(c0 + kSweepCh, g.cn);
   int label[4];
   float score[4], lw[4];
-  unsigned selmask = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int gi = q.ok[k] ? A.gt_inds[abase + q.hw[k]] : -1;
@@ -254,27 +304,17 @@ __device__ __forceinline__ void loss_tile(const Geo& g, const Workspace& ws, con
     score[k] = 0.f;
     if (gi > 0) {
       const long long lab = A.gt_labels[A.gt_offsets[n] + gi - 1];
-      if (lab >= 0 && lab < g.cn) {
+      if (lab >= c0 && lab < c1) {
         label[k] = (int)lab;
         score[k] = ws.pos_score[abase + q.hw[k]];
       }
     }
-    if (q.ok[k] && (A.sel_flags[abase + q.hw[k]] & 1)) selmask |= 1u << k;   // ERS rows, gfl_increment_erd.py:149-151
   }
   const float inv_avg1 = 1.0f / (float)((double)A.avg[0] + (double)kEps32);            // losses/utils.py:60-61
   const float scale_cls = upstream_of(A.upstream, acc_cls(l)) * g.w_cls * inv_avg1;
-
-  // box-logit gradients: zero everywhere; positives and NMS survivors are written afterwards
-  float* gbox = A.g_box.p[l] + (size_t)n * kBoxCh * HW;
-#pragma unroll 4
-  for (int c = 0; c < kBoxCh; ++c) q.store_zero(gbox + (size_t)c * HW);
-
-  // QFL over the new-class channels of every anchor (:260-261,317-320)
-  const float* scls = A.s_cls.p[l] + (size_t)n * g.C * HW;
-  float* gcls = A.g_cls.p[l] + (size_t)n * g.C * HW;
   float loss_cls = 0.f;
 #pragma unroll 4
-  for (int c = 0; c < g.cn; ++c) {
+  for (int c = c0; c < c1; ++c) {
     float x[4], gr[4];
     q.load(scls + (size_t)(g.ori + c) * HW, x, 0.f);
 #pragma unroll
@@ -285,72 +325,93 @@ __device__ __forceinline__ void loss_tile(const Geo& g, const Workspace& ws, con
     }
     q.store(gcls + (size_t)(g.ori + c) * HW, gr);
   }
-  out.cls += loss_cls;
+  out_loss += loss_cls;
+}
 
-  // old-class channels: zero, except the classification-response L2 on ERS rows (:181-186,324-332).
-  // The warp handles its selected anchors together: lanes stride over the old-class channels.
-#pragma unroll 4
-  for (int c = 0; c < g.ori; ++c) q.store_zero(gcls + (size_t)c * HW);
-  unsigned any = __ballot_sync(0xffffffffu, selmask != 0);
-  if (any) {
-    __syncwarp();
-    const float kc = (float)A.cls_count[n] * (float)g.ori;
-    const float scale_dc = upstream_of(A.upstream, acc_dcls(n)) * A.dlw * 2.0f / kc;
-    const float* tcls = A.t_cls.p[l] + (size_t)n * g.ori * HW;
-    const int lane = threadIdx.x & 31;
-    float sq = 0.f;
-    while (any) {
-      const int src = __ffs(any) - 1;
-      any &= any - 1;
-      const unsigned mk = __shfl_sync(0xffffffffu, selmask, src);
-      const int hw_first = __shfl_sync(0xffffffffu, q.hw[0], src);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (!(mk & (1u << k))) continue;
-        const int hw = VEC ? hw_first + k : hw_first + kTileThreads * k;
-        for (int c = lane; c < g.ori; c += 32) {
-          const float df = __ldg(scls + (size_t)c * HW + hw) - __ldg(tcls + (size_t)c * HW + hw);
-          sq = fmaf(df, df, sq);
-          gcls[(size_t)c * HW + hw] = scale_dc * df;
-        }
-      }
-    }
-    out.dcls += sq;
+__global__ void __launch_bounds__(kTileThreads) cls_sweep_kernel(Geo g, Workspace ws, LossArgs A) {
+  if (A.skip_flag && *A.skip_flag == 0u) return;
+  const int n = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int part = blockIdx.z;
+  const int l = level_of_tile(g, tile);
+  const int hw0 = (tile - g.tile_start[l]) * kTile;
+  float out = 0.f;
+  if (g.vec[l])
+    cls_tile<true>(g, ws, A, n, l, hw0, part, out);
+  else
+    cls_tile<false>(g, ws, A, n, l, hw0, part, out);
+  __shared__ float red[kTileThreads / 32];
+  out = warp_sum(out);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = out;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kTileThreads / 32; ++w) s += (double)red[w];
+    const bool old_part = part < (g.ori + kSweepCh - 1) / kSweepCh;
+    if (s != 0.0) atomicAdd(ws.loss_acc + (old_part ? acc_dcls(n) : acc_cls(l)), s);
   }
 }
 
-__global__ void __launch_bounds__(kTileThreads) loss_main_kernel(Geo g, Workspace ws, LossArgs A) {
+// ----------------------------------------------------------------------------- box sweep
+// grid (tile, image, side).  Every box-logit gradient element is written exactly once: zero,
+// plus the compact rows of positives (pos_kernel<true>) and NMS survivors (kd_kernel).
+template <bool VEC>
+__device__ __forceinline__ void box_tile(const Geo& g, const Workspace& ws, const LossArgs& A, int n, int l,
+                                         int hw0, int side) {
+  const int HW = g.hw[l];
+  const Quad<VEC> q(hw0, HW);
+  const size_t abase = (size_t)n * g.A + g.start[l];
+  const float* prow[4];
+  const float* krow[4];
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    prow[k] = nullptr;
+    krow[k] = nullptr;
+    if (!q.ok[k]) continue;
+    const size_t a = abase + q.hw[k];
+    if (A.gt_inds[a] > 0) prow[k] = ws.pos_rows + ((size_t)n * g.pos_cap + ws.pos_slot[a]) * kBoxCh + side * kBins;
+    if (A.sel_flags[a] & 4) krow[k] = ws.kd_rows + ((size_t)n * g.sel_cap + ws.kd_slot[a]) * kBoxCh + side * kBins;
+    any |= prow[k] != nullptr || krow[k] != nullptr;
+  }
+  float* gbox = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW;
+  if (!any) {
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) q.store_zero(gbox + (size_t)j * HW);
+    return;
+  }
+  for (int j = 0; j < kBins; ++j) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = 0.f;
+      if (prow[k]) v[k] += prow[k][j];
+      if (krow[k]) v[k] += krow[k][j];
+    }
+    q.store(gbox + (size_t)j * HW, v);
+  }
+}
+
+__global__ void __launch_bounds__(kTileThreads) box_sweep_kernel(Geo g, Workspace ws, LossArgs A) {
   if (A.skip_flag && *A.skip_flag == 0u) return;
   const int n = blockIdx.y;
   const int tile = blockIdx.x;
   const int l = level_of_tile(g, tile);
   const int hw0 = (tile - g.tile_start[l]) * kTile;
-  LossTileOut out = {0.f, 0.f};
   if (g.vec[l])
-    loss_tile<true>(g, ws, A, n, l, hw0, out);
+    box_tile<true>(g, ws, A, n, l, hw0, blockIdx.z);
   else
-    loss_tile<false>(g, ws, A, n, l, hw0, out);
-  __shared__ float red[kTileThreads / 32][2];
-  const float a = warp_sum(out.cls), b = warp_sum(out.dcls);
-  if ((threadIdx.x & 31) == 0) {
-    red[threadIdx.x >> 5][0] = a;
-    red[threadIdx.x >> 5][1] = b;
-  }
-  __syncthreads();
-  if (threadIdx.x < 2) {
-    double s = 0.0;
-    for (int w = 0; w < kTileThreads / 32; ++w) s += (double)red[w][threadIdx.x];
-    if (s != 0.0) atomicAdd(ws.loss_acc + (threadIdx.x == 0 ? acc_cls(l) : acc_dcls(n)), s);
-  }
+    box_tile<false>(g, ws, A, n, l, hw0, blockIdx.z);
 }
 
 // ----------------------------------------------------------------------------- box distillation
 // DFL-distribution distillation on the NMS survivors: KL(T) between student and teacher box
 // distributions, weighted by the student's max old-class score (:204-221, kd_loss.py:12-37).
-// Four threads per kept row, one per side; gradients are added onto what is already there.
+// Four threads per kept row, one per side; the gradient row goes to a compact buffer that
+// box_sweep_kernel merges into its dense stores, and bit 2 of the anchor's flag byte marks it.
 constexpr int kKdThreads = 256;
 
-__global__ void __launch_bounds__(kKdThreads) kd_kernel(Geo g, Workspace ws, LossArgs A) {
+__global__ void __launch_bounds__(kKdThreads) kd_kernel(Geo g, Workspace ws, LossArgs A, uint8_t* sel_flags) {
   if (A.skip_flag && *A.skip_flag == 0u) return;
   const int n = blockIdx.y;
   const int side = threadIdx.x & 3;
@@ -375,7 +436,6 @@ __global__ void __launch_bounds__(kKdThreads) kd_kernel(Geo g, Workspace ws, Los
     const size_t off = ((size_t)n * kBoxCh + side * kBins) * HW + hw;
     const float* sp = A.s_box.p[l] + off;
     const float* tp = A.t_box.p[l] + off;
-    float* gp = A.g_box.p[l] + off;
     float zs[kBins], zt[kBins];
 #pragma unroll
     for (int j = 0; j < kBins; ++j) {
@@ -386,22 +446,27 @@ __global__ void __launch_bounds__(kKdThreads) kd_kernel(Geo g, Workspace ws, Los
 #pragma unroll
     for (int j = 1; j < kBins; ++j) { ms = fmaxf(ms, zs[j]); mt = fmaxf(mt, zt[j]); }
     float ss = 0.f, st = 0.f;
-    float es[kBins], et[kBins];
 #pragma unroll
     for (int j = 0; j < kBins; ++j) {
-      es[j] = expf(zs[j] - ms);
-      et[j] = expf(zt[j] - mt);
-      ss += es[j];
-      st += et[j];
+      zs[j] -= ms;
+      zt[j] -= mt;
+      ss += expf(zs[j]);
+      st += expf(zt[j]);
     }
-    const float lss = logf(ss), lst = logf(st), iss = 1.0f / ss, ist = 1.0f / st;
+    const float lss = logf(ss), lst = logf(st);
     float kl = 0.f;
     const float gs = scale * w;
+    float* row = ws.kd_rows + ((size_t)n * g.sel_cap + r) * kBoxCh + side * kBins;
 #pragma unroll
     for (int j = 0; j < kBins; ++j) {
-      const float ps = es[j] * iss, pt = et[j] * ist;
-      if (pt > 0.f) kl += pt * ((zt[j] - mt - lst) - (zs[j] - ms - lss));
-      gp[(size_t)j * HW] += gs * (ps - pt);
+      const float lps = zs[j] - lss, lpt = zt[j] - lst;
+      const float ps = expf(lps), pt = expf(lpt);
+      if (pt > 0.f) kl += pt * (lpt - lps);
+      row[j] = gs * (ps - pt);
+    }
+    if (side == 0) {
+      ws.kd_slot[(size_t)n * g.A + a] = r;
+      sel_flags[(size_t)n * g.A + a] |= 4;
     }
     lsum += w * (kl / (float)kBins * (kT * kT));                                   // .mean(1) * T*T
   }
@@ -412,7 +477,7 @@ __global__ void __launch_bounds__(kKdThreads) kd_kernel(Geo g, Workspace ws, Los
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int w = 0; w < kKdThreads / 32; ++w) s += (double)red[w];
-    if (s != 0.0) atomicAdd(ws.loss_acc + acc_dbox(g, n), s);
+    if (s != 0.0) atomicAdd(ws.kd_acc + n, s);
   }
 }
 
@@ -442,15 +507,13 @@ __global__ void finalize_kernel(Geo g, Workspace ws, LossArgs A) {
     const int n = i - 3 * kLevels;
     out = A.dlw * (float)(ws.loss_acc[i] / ((double)A.cls_count[n] * (double)g.ori));   // mean over K*ori; 0/0 -> NaN
   } else {
-    out = A.dlw * (g.w_ld * ((float)ws.loss_acc[i] / 4.0f));
+    out = A.dlw * (g.w_ld * ((float)ws.kd_acc[i - 3 * kLevels - g.n_img] / 4.0f));
   }
   A.losses[i] = out;
 }
 
 static int pos_grid_x(const Geo& g) {
-  const long long cap = (long long)kTopK * kLevels * (long long)(g.total_gt > 0 ? g.total_gt : 1);
-  const long long per_img = cap < g.A ? cap : g.A;
-  long long blocks = (per_img * 4 + kPosThreads - 1) / kPosThreads;
+  long long blocks = ((long long)g.pos_cap * 4 + kPosThreads - 1) / kPosThreads;
   return (int)(blocks < 1 ? 1 : (blocks > 32 ? 32 : blocks));
 }
 
@@ -476,14 +539,32 @@ cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, con
   return cudaGetLastError();
 }
 
-cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st,
-                        cudaEvent_t wait_before_kd) {
+// KD rows: runs on whichever stream holds the NMS result (the NMS side stream in erd_step_prepare
+// order, or the caller's stream), before box_sweep_kernel.
+cudaError_t launch_kd(const Geo& g, const Workspace& ws, const LossArgs& a, uint8_t* sel_flags, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(ws.kd_acc, 0, sizeof(double) * g.n_img, st);
+  if (e != cudaSuccess) return e;
+  ERD_LAUNCH(kKKd, st, (kd_kernel<<<dim3(16, g.n_img), kKdThreads, 0, st>>>(g, ws, a, sel_flags)));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, cudaStream_t kd_stream,
+                        cudaEvent_t kd_wait, cudaEvent_t kd_done) {
   const int total = 3 * kLevels + 2 * g.n_img;
   cudaError_t e = cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * total, st);
   if (e != cudaSuccess) return e;
   if (a.skip_flag) ERD_LAUNCH(kKUpCheck, st, (upstream_check_kernel<<<1, 128, 0, st>>>(ws, a.upstream, total)));
-  ERD_LAUNCH(kKLossMain, st,
-             (loss_main_kernel<<<dim3(g.tile_start[kLevels], g.n_img), kTileThreads, 0, st>>>(g, ws, a)));
+  // KD rows need only the NMS result: on the side stream they overlap the class sweep
+  uint8_t* flags = const_cast<uint8_t*>(a.sel_flags);
+  if (kd_stream && kd_stream != st) {
+    if (a.skip_flag) {   // the KD kernel reads the flag the check kernel above writes
+      e = cudaEventRecord(kd_wait, st);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(kd_stream, kd_wait, 0);
+    }
+    if (e == cudaSuccess) e = launch_kd(g, ws, a, flags, kd_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(kd_done, kd_stream);
+    if (e != cudaSuccess) return e;
+  }
   PosArgs p;
   p.s_cls = a.s_cls;
   p.s_box = a.s_box;
@@ -497,11 +578,17 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
   p.upstream = a.upstream;
   p.skip_flag = a.skip_flag;
   ERD_LAUNCH(kKPosGrad, st, (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, st>>>(g, ws, p)));
-  if (wait_before_kd) {
-    e = cudaStreamWaitEvent(st, wait_before_kd, 0);
-    if (e != cudaSuccess) return e;
+  const int parts = (g.ori + kSweepCh - 1) / kSweepCh + (g.cn + kSweepCh - 1) / kSweepCh;
+  ERD_LAUNCH(kKLossMain, st,
+             (cls_sweep_kernel<<<dim3(g.tile_start[kLevels], g.n_img, parts), kTileThreads, 0, st>>>(g, ws, a)));
+  if (kd_stream && kd_stream != st) {
+    e = cudaStreamWaitEvent(st, kd_done, 0);
+  } else {
+    e = launch_kd(g, ws, a, flags, st);
   }
-  ERD_LAUNCH(kKKd, st, (kd_kernel<<<dim3(16, g.n_img), kKdThreads, 0, st>>>(g, ws, a)));
+  if (e != cudaSuccess) return e;
+  ERD_LAUNCH(kKBoxSweep, st,
+             (box_sweep_kernel<<<dim3(g.tile_start[kLevels], g.n_img, 4), kTileThreads, 0, st>>>(g, ws, a)));
   ERD_LAUNCH(kKFinalize, st, (finalize_kernel<<<1, ((total + 31) / 32) * 32, 0, st>>>(g, ws, a)));
   return cudaGetLastError();
 }

@@ -9,7 +9,7 @@ namespace erd {
 
 static const char* kKernelNames[kNumKernels] = {"ers_scan", "ers_select", "atss_candidates", "atss_finalize",
                                                 "pos_prepass", "nms_sort", "nms_mask", "nms_resolve", "upstream_check",
-                                                "loss_main", "pos_grad", "kd", "finalize"};
+                                                "cls_sweep", "pos_grad", "kd", "box_sweep", "finalize"};
 
 struct ProfState {
   std::mutex mu;

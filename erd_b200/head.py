@@ -180,7 +180,8 @@ class GFLHeadIncrementERD(nn.Module):
         s_box = [t.contiguous() for t in bbox_preds]
         t_cls = [t[:, :ori_num_classes].detach().contiguous() for t in t_cls]
         t_box = [t.detach().contiguous() for t in t_box]
-        plan = self.path.plan(s_cls, self.num_classes, int(ori_num_classes), self.reg_max)
+        plan = self.path.plan(s_cls, self.num_classes, int(ori_num_classes), self.reg_max,
+                              max((int(g.bboxes.shape[0]) for g in batch_gt_instances), default=0))
         ers_done = self._adopt_selection(plan, t_cls, t_box, ori_topk_cls_inds, ori_topk_bbox_inds)
         plan.set_targets([g.bboxes for g in batch_gt_instances], [g.labels for g in batch_gt_instances],
                          [m['pad_shape'][:2] for m in batch_img_metas])

@@ -38,7 +38,8 @@ class Plan:
     """Buffers for one static batch geometry on one device (reused across steps)."""
 
     def __init__(self, key, device):
-        n, shapes, num_classes, ori, reg_max, strides, scale, weights = key
+        n, shapes, num_classes, ori, reg_max, strides, scale, weights, max_gt = key
+        self.max_gt = max_gt
         self.key, self.device = key, device
         self.n, self.shapes, self.C, self.ori, self.reg_max = n, shapes, num_classes, ori, reg_max
         self.shape = N.ErdShape()
@@ -51,6 +52,7 @@ class Plan:
         self.shape.anchor_scale = scale
         (self.shape.loss_weight_cls, self.shape.loss_weight_bbox, self.shape.loss_weight_dfl,
          self.shape.loss_weight_ld, self.shape.kd_temperature) = weights
+        self.shape.max_gt_per_img = max_gt
         sizes = N.ErdSizes()
         N.check(N.load().erd_sizes(C.byref(self.shape), C.byref(sizes)), 'erd_sizes')
         self.A, self.sel_cap = int(sizes.anchors_per_img), int(sizes.sel_cap)
@@ -97,6 +99,8 @@ class Plan:
         for i in range(n):
             self.meta_host[i] = off
             off += int(gt_bboxes[i].shape[0])
+            if int(gt_bboxes[i].shape[0]) > self.max_gt:
+                raise ValueError(f'image {i} has {int(gt_bboxes[i].shape[0])} GT boxes, plan capacity is {self.max_gt}')
             ph, pw = int(pad_shapes[i][0]), int(pad_shapes[i][1])
             if ph < 1 or pw < 1:
                 # reference: ValueError when an image has no valid anchor (gfl_head.py:613-617)
@@ -143,6 +147,7 @@ class ErdPath:
         self.weights = tuple(float(w) for w in loss_weights) + (float(kd_T),)
         self.strides, self.anchor_scale, self.nms_iou_thr = tuple(strides), float(anchor_scale), float(nms_iou_thr)
         self._plans: Dict[tuple, Plan] = {}
+        self._cap: Dict[tuple, int] = {}
         self._ctx: Dict[int, C.c_void_p] = {}
 
     def _context(self, device) -> C.c_void_p:
@@ -154,13 +159,22 @@ class ErdPath:
             self._ctx[idx] = ctx
         return self._ctx[idx]
 
-    def plan(self, s_or_t_cls: Sequence[torch.Tensor], num_classes: int, ori: int, reg_max: int = 16) -> Plan:
+    def plan(self, s_or_t_cls: Sequence[torch.Tensor], num_classes: int, ori: int, reg_max: int = 16,
+             max_gt: int = 0) -> Plan:
+        """``max_gt``: most GT boxes any image of the batch holds (rounded up to a power of two,
+        at least 128); the plan with the largest capacity seen so far is reused."""
         t0 = s_or_t_cls[0]
         if not t0.is_cuda:
             raise RuntimeError('erd_b200 runs on CUDA tensors only; there is no CPU fallback')
         shapes = tuple((int(t.shape[2]), int(t.shape[3])) for t in s_or_t_cls)
-        key = (int(t0.shape[0]), shapes, int(num_classes), int(ori), int(reg_max), self.strides, self.anchor_scale,
-               self.weights)
+        cap = 128
+        while cap < max_gt:
+            cap *= 2
+        base = (int(t0.shape[0]), shapes, int(num_classes), int(ori), int(reg_max), self.strides, self.anchor_scale,
+                self.weights)
+        cap = max(cap, self._cap.get(base + (t0.device,), 128))
+        self._cap[base + (t0.device,)] = cap
+        key = base + (cap,)
         full = key + (t0.device,)
         if full not in self._plans:
             self._plans[full] = Plan(key, t0.device)
@@ -222,7 +236,8 @@ class ErdPath:
              targets_set: bool = False, ers_done: bool = False):
         """ERS + assignment + NMS + fused loss forward/backward.
         Returns (plan, losses (3L+2N,), g_cls[5], g_box[5])."""
-        p = self.plan(s_cls, num_classes, ori, reg_max)
+        p = self.plan(s_cls, num_classes, ori, reg_max,
+                      max((int(b.shape[0]) for b in gt_bboxes), default=0) if gt_bboxes is not None else 0)
         _check_level_tensors('cls_scores', s_cls, p.n, p.C, p.shapes)
         _check_level_tensors('bbox_preds', s_box, p.n, 4 * (p.reg_max + 1), p.shapes)
         _check_level_tensors('teacher cls_scores', t_cls, p.n, p.ori, p.shapes)

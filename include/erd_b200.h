@@ -58,6 +58,8 @@ typedef struct ErdShape {
   float loss_weight_dfl;              /* DistributionFocalLoss loss_weight (0.25)           */
   float loss_weight_ld;               /* KnowledgeDistillationKLDivLoss loss_weight (0.25)  */
   float kd_temperature;               /* T (10)                                             */
+  int32_t max_gt_per_img;             /* capacity: most GT boxes any image may hold (0 -> 128);
+                                         sizes the positives' gradient-row buffer (45 rows / GT) */
 } ErdShape;
 
 /* Derived sizes a caller needs to allocate outputs. */
