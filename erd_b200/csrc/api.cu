@@ -82,11 +82,12 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->pos_list = (int*)take(NA * 4);
   ws->pos_score = (float*)take(NA * 4);
   ws->pre_acc = (double*)take((size_t)(2 * kLevels + 1) * 8);
-  ws->kd_acc = (double*)take((size_t)g.n_img * 8);
   ws->pos_slot = (int*)take(NA * 4);
   ws->kd_slot = (int*)take(NA * 4);
-  ws->pos_rows = (float*)take((size_t)g.n_img * g.pos_cap * kBoxCh * 4);
   ws->kd_rows = (float*)take(NS * kBoxCh * 4);
+  ws->kd_loss = (float*)take(NS * 4);
+  ws->pos_rows = (float*)take((size_t)g.n_img * g.pos_cap * kBoxCh * 4);
+  ws->nms_nz = (unsigned long long*)take(NS * nms_nz_words(g.sel_cap) * 8);
   ws->counters = (unsigned int*)take(8 * 4);
   ws->nms_raw = (float4*)take(NS * 16);
   ws->nms_cls = (int*)take(NS * 4);
@@ -129,8 +130,8 @@ static MPtr5 mptr5(float* const* p) {
 }
 
 struct ErdContext {
-  cudaStream_t side[2];          // [0] assignment + positives prepass, [1] teacher NMS
-  cudaEvent_t fork, join[2], sel, kd_wait, kd_done;
+  cudaStream_t side[3];          // [0] assignment + positives prepass, [1] teacher NMS, [2] KD rows
+  cudaEvent_t fork, join[3], sel, early_done;
   bool nms_pending;              // join[1] recorded by erd_step_prepare, not yet waited on
 };
 
@@ -157,14 +158,13 @@ int erd_create(ErdContext** ctx) {
   if (!ctx) return fail(ERD_ERR_NULL, "ctx is NULL");
   ErdContext* c = new ErdContext();
   cudaError_t e = cudaSuccess;
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
     e = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sel, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->kd_wait, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->kd_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->early_done, cudaEventDisableTiming);
   c->nms_pending = false;
   if (e != cudaSuccess) {
     delete c;
@@ -176,14 +176,13 @@ int erd_create(ErdContext** ctx) {
 
 int erd_destroy(ErdContext* c) {
   if (!c) return ERD_OK;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     cudaStreamDestroy(c->side[i]);
     cudaEventDestroy(c->join[i]);
   }
   cudaEventDestroy(c->fork);
   cudaEventDestroy(c->sel);
-  cudaEventDestroy(c->kd_wait);
-  cudaEventDestroy(c->kd_done);
+  cudaEventDestroy(c->early_done);
   delete c;
   return ERD_OK;
 }
@@ -236,16 +235,31 @@ int erd_avg_factors(const ErdShape* shape, const float* const* s_cls, const floa
 }
 
 int erd_teacher_nms(const ErdShape* shape, const int32_t* box_inds, const int32_t* box_count, const int32_t* pad_hw,
-                    float iou_thr, int32_t* keep, int32_t* keep_count, void* wsp, void* stream) {
+                    float iou_thr, int32_t* keep, int32_t* keep_count, uint8_t* sel_flags, void* wsp, void* stream) {
   Geo g;
   int rc = make_geo(shape, &g);
   if (rc) return rc;
-  if (!box_inds || !box_count || !pad_hw || !keep || !keep_count || !wsp)
+  if (!box_inds || !box_count || !pad_hw || !keep || !keep_count || !sel_flags || !wsp)
     return fail(ERD_ERR_NULL, "erd_teacher_nms: NULL argument");
   Workspace ws;
   carve(g, wsp, &ws);
-  cudaError_t e = launch_nms(g, ws, box_inds, box_count, pad_hw, iou_thr, keep, keep_count, (cudaStream_t)stream);
+  cudaError_t e = launch_nms(g, ws, box_inds, box_count, pad_hw, iou_thr, keep, keep_count, sel_flags,
+                             (cudaStream_t)stream);
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_teacher_nms");
+}
+
+int erd_kd_rows(const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
+                const float* const* t_box, const int32_t* box_inds, const int32_t* box_count, void* wsp,
+                void* stream) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (NULLS(s_cls) || NULLS(s_box) || NULLS(t_box) || !box_inds || !box_count || !wsp)
+    return fail(ERD_ERR_NULL, "erd_kd_rows: NULL argument");
+  Workspace ws;
+  carve(g, wsp, &ws);
+  cudaError_t e = launch_kd_rows(g, ws, ptr5(s_cls), ptr5(s_box), ptr5(t_box), box_inds, box_count, (cudaStream_t)stream);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_kd_rows");
 }
 
 int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
@@ -290,14 +304,21 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
   a.skip_flag = (upstream && skip_if_unit_upstream) ? ws.counters + 1 : nullptr;
   a.losses = losses;
   a.dlw = dist_loss_weight;
-  // With a context the KD rows are computed on the NMS side stream (behind the NMS that
-  // erd_step_prepare queued there) while the class sweep runs on the caller's stream.
+  // With a context the box sectors that cannot depend on the NMS are written on a helper
+  // stream beside the class sweep; the NMS forked by erd_step_prepare is joined only in front
+  // of the late box launch.
   cudaError_t e;
   if (ctx) {
-    e = launch_loss(g, ws, a, (cudaStream_t)stream, ctx->side[1], ctx->kd_wait, ctx->kd_done);
-    ctx->nms_pending = false;   // kd_done, which `stream` now waits on, is behind the NMS
+    LossStreams ls;
+    ls.early = ctx->side[0];
+    ls.fork = ctx->fork;
+    ls.early_done = ctx->early_done;
+    ls.nms_done = ctx->nms_pending ? ctx->join[1] : nullptr;
+    ls.kd_done = ctx->nms_pending ? ctx->join[2] : nullptr;
+    e = launch_loss(g, ws, a, (cudaStream_t)stream, &ls);
+    ctx->nms_pending = false;
   } else {
-    e = launch_loss(g, ws, a, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+    e = launch_loss(g, ws, a, (cudaStream_t)stream, nullptr);
   }
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_loss_fwd_bwd");
 }
@@ -311,11 +332,13 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   cudaError_t e = cudaSuccess;
   if (ctx->nms_pending) {   // a previous prepare whose NMS nobody consumed: do not race its teacher cache
     e = cudaStreamWaitEvent(main, ctx->join[1], 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ctx->join[2], 0);
     ctx->nms_pending = false;
   }
   // stream layout: main = teacher pass (ERS scan + select); side[0] = ATSS + positives prepass
-  // (joined back before returning, the caller all-reduces avg next); side[1] = teacher NMS,
-  // forked after the selection and joined inside erd_loss_fwd_bwd in front of the KD kernel.
+  // (joined back before returning, the caller all-reduces avg next); side[1] = teacher NMS and
+  // side[2] = distillation rows of every box candidate, both forked after the selection and
+  // joined inside erd_loss_fwd_bwd in front of the late box sweep.
   if (e == cudaSuccess) e = cudaEventRecord(ctx->fork, main);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[0], ctx->fork, 0);
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork");
@@ -330,9 +353,14 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   e = cudaEventRecord(ctx->sel, main);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[1], ctx->sel, 0);
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork nms");
-  rc = erd_teacher_nms(shape, b->box_inds, b->box_count, pad_hw, iou_thr, b->keep, b->keep_count, wsp, ctx->side[1]);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[2], ctx->sel, 0);
+  if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork kd");
+  rc = erd_teacher_nms(shape, b->box_inds, b->box_count, pad_hw, iou_thr, b->keep, b->keep_count, b->sel_flags, wsp,
+                       ctx->side[1]);
+  if (!rc) rc = erd_kd_rows(shape, s_cls, s_box, t_box, b->box_inds, b->box_count, wsp, ctx->side[2]);
   if (rc) return rc;
   e = cudaEventRecord(ctx->join[1], ctx->side[1]);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->join[2], ctx->side[2]);
   if (e == cudaSuccess) ctx->nms_pending = true;
   if (e == cudaSuccess) e = cudaEventRecord(ctx->join[0], ctx->side[0]);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ctx->join[0], 0);

@@ -46,11 +46,12 @@ struct Workspace {
   int* pos_list;                  // [N][A] anchors with an assigned GT (unordered)
   float* pos_score;               // [N][A] IoU quality score, defined at positives only
   double* pre_acc;                // [2L+1] sum w(1-giou) per level, sum w*dfl per level, sum w
-  double* kd_acc;                 // [N] sum w * KL per image
   int* pos_slot;                  // [N][A] row of pos_rows, defined at positives only
-  int* kd_slot;                   // [N][A] row of kd_rows, defined at NMS survivors only
+  int* kd_slot;                   // [N][A] list position of an NMS survivor (row of kd_rows)
+  float* kd_rows;                 // [N][sel_cap][68] w * (p_s - p_t) of every ERS box candidate
+  float* kd_loss;                 // [N][sel_cap] weighted KL of every ERS box candidate
   float* pos_rows;                // [N][pos_cap][68] box-logit gradient rows of the positives
-  float* kd_rows;                 // [N][sel_cap][68] box-logit gradient rows of the NMS survivors
+  unsigned long long* nms_nz;     // [N][sel_cap][nz_words] which words of a predecessor row are non-zero
   unsigned int* counters;         // [8] last-block tickets
   float4* nms_raw;                // [N][sel_cap] decoded teacher boxes in list order
   int* nms_cls;                   // [N][sel_cap] class ids in list order
@@ -62,6 +63,7 @@ struct Workspace {
 };
 
 inline __host__ __device__ int nms_words(int sel_cap) { return (sel_cap + 63) / 64; }
+inline __host__ __device__ int nms_nz_words(int sel_cap) { return (nms_words(sel_cap) + 63) / 64; }
 
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ int level_of_tile(const Geo& g, int tile) {
@@ -144,7 +146,7 @@ struct Quad {
 
 // ---------------------------------------------------------------- launch accounting (profile.cu)
 enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan,
-                kKUpCheck, kKLossMain, kKPosGrad, kKKd, kKBoxSweep, kKFinalize, kNumKernels };
+                kKKdRows, kKUpCheck, kKLossMain, kKPosGrad, kKBoxEarly, kKBoxSweep, kKFinalize, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 // ERD_LAUNCH(id, stream, kernel<<<...>>>(...)) counts the launch and, when profiling is on,
@@ -168,7 +170,8 @@ cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, con
                        const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
                        const int32_t* gt_inds, const int32_t* num_pos, float* avg, cudaStream_t st);
 cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_inds, const int32_t* box_count,
-                       const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count, cudaStream_t st);
+                       const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count, uint8_t* sel_flags,
+                       cudaStream_t st);
 
 struct LossArgs {
   Ptr5 s_cls, s_box, t_cls, t_box;
@@ -190,7 +193,14 @@ struct LossArgs {
   float* losses;
   float dlw;
 };
-cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, cudaStream_t kd_stream,
-                        cudaEvent_t kd_wait, cudaEvent_t kd_done);
+cudaError_t launch_kd_rows(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box, const Ptr5& t_box,
+                           const int32_t* box_inds, const int32_t* box_count, cudaStream_t st);
+struct LossStreams {
+  cudaStream_t early;                 // helper stream for the NMS-independent box sectors
+  cudaEvent_t fork, early_done;
+  cudaEvent_t nms_done;               // may be null: NMS already ordered before the caller's stream
+  cudaEvent_t kd_done;                // may be null: likewise for the distillation rows
+};
+cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, const LossStreams* ls);
 
 }  // namespace erd

@@ -15,9 +15,10 @@
 //   cls_sweep_kernel   streaming sweep over the class logits: QFL on the new-class channels of
 //                      every anchor, class-response L2 on the old-class channels (zero off
 //                      the ERS rows), gradients written once, densely.
-//   kd_kernel          DFL-distribution KL on the NMS survivors -> compact gradient rows.
-//   box_sweep_kernel   dense write of the box-logit gradients: zero, plus the compact rows of
-//                      positives and NMS survivors merged in on the fly (no read-modify-write).
+//   kd_rows_kernel     (prepare phase, beside the NMS) DFL-distribution KL rows of every ERS
+//                      box candidate.
+//   box_sweep_kernel   dense write of the box-logit gradients: zero, the compact rows of the
+//                      positives, and the distillation rows of the NMS survivors.
 //   finalize_kernel    accumulators -> the reference's loss values.
 #include "erd_common.cuh"
 
@@ -352,95 +353,43 @@ __global__ void __launch_bounds__(kTileThreads) cls_sweep_kernel(Geo g, Workspac
   }
 }
 
-// ----------------------------------------------------------------------------- box sweep
-// grid (tile, image, side).  Every box-logit gradient element is written exactly once: zero,
-// plus the compact rows of positives (pos_kernel<true>) and NMS survivors (kd_kernel).
-template <bool VEC>
-__device__ __forceinline__ void box_tile(const Geo& g, const Workspace& ws, const LossArgs& A, int n, int l,
-                                         int hw0, int side) {
-  const int HW = g.hw[l];
-  const Quad<VEC> q(hw0, HW);
-  const size_t abase = (size_t)n * g.A + g.start[l];
-  const float* prow[4];
-  const float* krow[4];
-  bool any = false;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    prow[k] = nullptr;
-    krow[k] = nullptr;
-    if (!q.ok[k]) continue;
-    const size_t a = abase + q.hw[k];
-    if (A.gt_inds[a] > 0) prow[k] = ws.pos_rows + ((size_t)n * g.pos_cap + ws.pos_slot[a]) * kBoxCh + side * kBins;
-    if (A.sel_flags[a] & 4) krow[k] = ws.kd_rows + ((size_t)n * g.sel_cap + ws.kd_slot[a]) * kBoxCh + side * kBins;
-    any |= prow[k] != nullptr || krow[k] != nullptr;
-  }
-  float* gbox = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW;
-  if (!any) {
-#pragma unroll
-    for (int j = 0; j < kBins; ++j) q.store_zero(gbox + (size_t)j * HW);
-    return;
-  }
-  for (int j = 0; j < kBins; ++j) {
-    float v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = 0.f;
-      if (prow[k]) v[k] += prow[k][j];
-      if (krow[k]) v[k] += krow[k][j];
-    }
-    q.store(gbox + (size_t)j * HW, v);
-  }
-}
-
-__global__ void __launch_bounds__(kTileThreads) box_sweep_kernel(Geo g, Workspace ws, LossArgs A) {
-  if (A.skip_flag && *A.skip_flag == 0u) return;
-  const int n = blockIdx.y;
-  const int tile = blockIdx.x;
-  const int l = level_of_tile(g, tile);
-  const int hw0 = (tile - g.tile_start[l]) * kTile;
-  if (g.vec[l])
-    box_tile<true>(g, ws, A, n, l, hw0, blockIdx.z);
-  else
-    box_tile<false>(g, ws, A, n, l, hw0, blockIdx.z);
-}
-
-// ----------------------------------------------------------------------------- box distillation
-// DFL-distribution distillation on the NMS survivors: KL(T) between student and teacher box
-// distributions, weighted by the student's max old-class score (:204-221, kd_loss.py:12-37).
-// Four threads per kept row, one per side; the gradient row goes to a compact buffer that
-// box_sweep_kernel merges into its dense stores, and bit 2 of the anchor's flag byte marks it.
+// ----------------------------------------------------------------------------- box distillation rows
+// DFL-distribution distillation (KL at temperature T between student and teacher box
+// distributions, weighted by the student's max old-class score; :204-221, kd_loss.py:12-37)
+// for EVERY ERS box candidate, four threads per candidate (one per side), all loads in flight
+// at once.  It depends only on the selection, so it runs beside the NMS; the box sweep later
+// merges the rows of the candidates the NMS kept.  Rows hold w * (p_s - p_t); the constant
+// factor (upstream, dist_loss_weight, loss weight, T) is applied at merge time.
 constexpr int kKdThreads = 256;
 
-__global__ void __launch_bounds__(kKdThreads) kd_kernel(Geo g, Workspace ws, LossArgs A, uint8_t* sel_flags) {
-  if (A.skip_flag && *A.skip_flag == 0u) return;
+__global__ void __launch_bounds__(kKdThreads) kd_rows_kernel(Geo g, Workspace ws, Ptr5 s_cls, Ptr5 s_box, Ptr5 t_box,
+                                                             const int32_t* __restrict__ box_inds,
+                                                             const int32_t* __restrict__ box_count) {
   const int n = blockIdx.y;
   const int side = threadIdx.x & 3;
-  const int M = A.keep_count[n];
-  const float kT = g.T;
-  const float scale = upstream_of(A.upstream, acc_dbox(g, n)) * A.dlw * g.w_ld / 4.0f * (kT * kT / (float)kBins) / kT;
-  float lsum = 0.f;
-  for (int r = (blockIdx.x * kKdThreads + threadIdx.x) >> 2; r < ((M + 7) & ~7); r += (gridDim.x * kKdThreads) >> 2) {
-    const bool on = r < M;
-    const int a = on ? A.box_inds[(size_t)n * g.sel_cap + A.keep[(size_t)n * g.sel_cap + r]] : 0;
+  const int K = box_count[n];
+  const float inv_T = 1.0f / g.T;
+  for (int r = (blockIdx.x * kKdThreads + threadIdx.x) >> 2; r < ((K + 7) & ~7); r += (gridDim.x * kKdThreads) >> 2) {
+    const bool on = r < K;
+    const int a = on ? box_inds[(size_t)n * g.sel_cap + r] : 0;
     const int l = level_of_anchor(g, a);
     const int HW = g.hw[l];
     const int hw = a - g.start[l];
     float mx = -INFINITY;
     if (on) {
-      const float* cplane = A.s_cls.p[l] + (size_t)n * g.C * HW + hw;
+      const float* cplane = s_cls.p[l] + (size_t)n * g.C * HW + hw;
       for (int c = side; c < g.ori; c += 4) mx = fmaxf(mx, __ldg(cplane + (size_t)c * HW));
     }
     mx = quad_max(mx);
-    if (!on) continue;
     const float w = sigmoid_ref(mx);                                               // :217-218
     const size_t off = ((size_t)n * kBoxCh + side * kBins) * HW + hw;
-    const float* sp = A.s_box.p[l] + off;
-    const float* tp = A.t_box.p[l] + off;
+    const float* sp = s_box.p[l] + off;
+    const float* tp = t_box.p[l] + off;
     float zs[kBins], zt[kBins];
 #pragma unroll
     for (int j = 0; j < kBins; ++j) {
-      zs[j] = __fdiv_rn(__ldg(sp + (size_t)j * HW), kT);
-      zt[j] = __fdiv_rn(__ldg(tp + (size_t)j * HW), kT);
+      zs[j] = on ? __ldg(sp + (size_t)j * HW) * inv_T : 0.f;
+      zt[j] = on ? __ldg(tp + (size_t)j * HW) * inv_T : 0.f;
     }
     float ms = zs[0], mt = zt[0];
 #pragma unroll
@@ -455,29 +404,102 @@ __global__ void __launch_bounds__(kKdThreads) kd_kernel(Geo g, Workspace ws, Los
     }
     const float lss = logf(ss), lst = logf(st);
     float kl = 0.f;
-    const float gs = scale * w;
     float* row = ws.kd_rows + ((size_t)n * g.sel_cap + r) * kBoxCh + side * kBins;
 #pragma unroll
     for (int j = 0; j < kBins; ++j) {
       const float lps = zs[j] - lss, lpt = zt[j] - lst;
       const float ps = expf(lps), pt = expf(lpt);
       if (pt > 0.f) kl += pt * (lpt - lps);
-      row[j] = gs * (ps - pt);
+      if (on) row[j] = w * (ps - pt);
     }
-    if (side == 0) {
-      ws.kd_slot[(size_t)n * g.A + a] = r;
-      sel_flags[(size_t)n * g.A + a] |= 4;
-    }
-    lsum += w * (kl / (float)kBins * (kT * kT));                                   // .mean(1) * T*T
+    kl += __shfl_xor_sync(0xffffffffu, kl, 1);
+    kl += __shfl_xor_sync(0xffffffffu, kl, 2);
+    if (on && side == 0) ws.kd_loss[(size_t)n * g.sel_cap + r] = w * (kl / (float)kBins * (g.T * g.T));   // .mean(1) * T*T
   }
-  __shared__ float red[kKdThreads / 32];
-  lsum = warp_sum(lsum);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+}
+
+// ----------------------------------------------------------------------------- box sweep
+// grid (tile, image, side).  Every box-logit gradient element is written exactly once, densely:
+// zero, plus the compact row of a positive (pos_kernel<true>), plus the distillation row of an
+// NMS survivor (kd_rows_kernel, marked by the NMS resolve pass).
+//
+// MODE 0: everything in one launch.  MODE 1 ("early", runs beside the NMS): only 8-anchor
+// groups that hold no ERS box candidate, i.e. whose result cannot depend on the NMS.
+// MODE 2 ("late", after the NMS): the remaining groups.  Groups are whole 32 B sectors, so
+// the two launches never share a sector.
+template <bool VEC, int MODE>
+__device__ __forceinline__ void box_tile(const Geo& g, const Workspace& ws, const LossArgs& A, int n, int l,
+                                         int hw0, int side, float& kd_loss) {
+  if (!VEC && MODE == 1) return;   // scalar levels (a few % of the anchors) are handled late
+  const int HW = g.hw[l];
+  const Quad<VEC> q(hw0, HW);
+  const size_t abase = (size_t)n * g.A + g.start[l];
+  const float* prow[4];
+  const float* krow[4];
+  bool any = false, cand = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    prow[k] = nullptr;
+    krow[k] = nullptr;
+    if (!q.ok[k]) continue;
+    const size_t a = abase + q.hw[k];
+    const unsigned flags = A.sel_flags[a];
+    cand |= (flags & 2) != 0;
+    if (MODE != 1 && (flags & 4)) {
+      const size_t slot = (size_t)n * g.sel_cap + ws.kd_slot[a];
+      krow[k] = ws.kd_rows + slot * kBoxCh + side * kBins;
+      if (side == 0) kd_loss += ws.kd_loss[slot];
+    }
+    if (A.gt_inds[a] > 0)
+      prow[k] = ws.pos_rows + ((size_t)n * g.pos_cap + ws.pos_slot[a]) * kBoxCh + side * kBins;
+    any |= prow[k] != nullptr || krow[k] != nullptr;
+  }
+  if (VEC && MODE != 0) {
+    const int neighbour = __shfl_xor_sync(0xffffffffu, cand ? 1 : 0, 1);   // every lane takes part
+    const bool group = cand || neighbour != 0;
+    if ((MODE == 1) == group) return;
+  }
+  float* gbox = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW;
+  if (!any) {
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) q.store_zero(gbox + (size_t)j * HW);
+    return;
+  }
+  const float kT = g.T;
+  const float scale = upstream_of(A.upstream, acc_dbox(g, n)) * A.dlw * g.w_ld / 4.0f * (kT * kT / (float)kBins) / kT;
+  for (int j = 0; j < kBins; ++j) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = 0.f;
+      if (prow[k]) v[k] += prow[k][j];
+      if (krow[k]) v[k] = fmaf(scale, krow[k][j], v[k]);
+    }
+    q.store(gbox + (size_t)j * HW, v);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTileThreads) box_sweep_kernel(Geo g, Workspace ws, LossArgs A) {
+  if (A.skip_flag && *A.skip_flag == 0u) return;
+  const int n = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int l = level_of_tile(g, tile);
+  const int hw0 = (tile - g.tile_start[l]) * kTile;
+  float kd = 0.f;
+  if (g.vec[l])
+    box_tile<true, MODE>(g, ws, A, n, l, hw0, blockIdx.z, kd);
+  else
+    box_tile<false, MODE>(g, ws, A, n, l, hw0, blockIdx.z, kd);
+  if (MODE == 1) return;
+  __shared__ float red[kTileThreads / 32];
+  kd = warp_sum(kd);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = kd;
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int w = 0; w < kKdThreads / 32; ++w) s += (double)red[w];
-    if (s != 0.0) atomicAdd(ws.kd_acc + n, s);
+    for (int w = 0; w < kTileThreads / 32; ++w) s += (double)red[w];
+    if (s != 0.0) atomicAdd(ws.loss_acc + acc_dbox(g, n), s);
   }
 }
 
@@ -507,7 +529,7 @@ __global__ void finalize_kernel(Geo g, Workspace ws, LossArgs A) {
     const int n = i - 3 * kLevels;
     out = A.dlw * (float)(ws.loss_acc[i] / ((double)A.cls_count[n] * (double)g.ori));   // mean over K*ori; 0/0 -> NaN
   } else {
-    out = A.dlw * (g.w_ld * ((float)ws.kd_acc[i - 3 * kLevels - g.n_img] / 4.0f));
+    out = A.dlw * (g.w_ld * ((float)ws.loss_acc[i] / 4.0f));
   }
   A.losses[i] = out;
 }
@@ -539,32 +561,21 @@ cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, con
   return cudaGetLastError();
 }
 
-// KD rows: runs on whichever stream holds the NMS result (the NMS side stream in erd_step_prepare
-// order, or the caller's stream), before box_sweep_kernel.
-cudaError_t launch_kd(const Geo& g, const Workspace& ws, const LossArgs& a, uint8_t* sel_flags, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(ws.kd_acc, 0, sizeof(double) * g.n_img, st);
-  if (e != cudaSuccess) return e;
-  ERD_LAUNCH(kKKd, st, (kd_kernel<<<dim3(16, g.n_img), kKdThreads, 0, st>>>(g, ws, a, sel_flags)));
+cudaError_t launch_kd_rows(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box, const Ptr5& t_box,
+                           const int32_t* box_inds, const int32_t* box_count, cudaStream_t st) {
+  ERD_LAUNCH(kKKdRows, st,
+             (kd_rows_kernel<<<dim3(16, g.n_img), kKdThreads, 0, st>>>(g, ws, s_cls, s_box, t_box, box_inds, box_count)));
   return cudaGetLastError();
 }
 
-cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, cudaStream_t kd_stream,
-                        cudaEvent_t kd_wait, cudaEvent_t kd_done) {
+// Sequence on the caller's stream `st`; with helper streams (erd_step_prepare's context) the
+// box gradients of every sector that cannot depend on the NMS are written on `early` while the
+// NMS is still running on its own stream, and `st` joins both before the late box launch.
+cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, const LossStreams* ls) {
   const int total = 3 * kLevels + 2 * g.n_img;
   cudaError_t e = cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * total, st);
   if (e != cudaSuccess) return e;
   if (a.skip_flag) ERD_LAUNCH(kKUpCheck, st, (upstream_check_kernel<<<1, 128, 0, st>>>(ws, a.upstream, total)));
-  // KD rows need only the NMS result: on the side stream they overlap the class sweep
-  uint8_t* flags = const_cast<uint8_t*>(a.sel_flags);
-  if (kd_stream && kd_stream != st) {
-    if (a.skip_flag) {   // the KD kernel reads the flag the check kernel above writes
-      e = cudaEventRecord(kd_wait, st);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(kd_stream, kd_wait, 0);
-    }
-    if (e == cudaSuccess) e = launch_kd(g, ws, a, flags, kd_stream);
-    if (e == cudaSuccess) e = cudaEventRecord(kd_done, kd_stream);
-    if (e != cudaSuccess) return e;
-  }
   PosArgs p;
   p.s_cls = a.s_cls;
   p.s_box = a.s_box;
@@ -578,17 +589,27 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
   p.upstream = a.upstream;
   p.skip_flag = a.skip_flag;
   ERD_LAUNCH(kKPosGrad, st, (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, st>>>(g, ws, p)));
+  const dim3 box_grid(g.tile_start[kLevels], g.n_img, 4);
+  if (ls) {   // fork: early box sectors beside the class sweep
+    e = cudaEventRecord(ls->fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ls->early, ls->fork, 0);
+    if (e != cudaSuccess) return e;
+    ERD_LAUNCH(kKBoxEarly, ls->early, (box_sweep_kernel<1><<<box_grid, kTileThreads, 0, ls->early>>>(g, ws, a)));
+    e = cudaEventRecord(ls->early_done, ls->early);
+    if (e != cudaSuccess) return e;
+  }
   const int parts = (g.ori + kSweepCh - 1) / kSweepCh + (g.cn + kSweepCh - 1) / kSweepCh;
   ERD_LAUNCH(kKLossMain, st,
              (cls_sweep_kernel<<<dim3(g.tile_start[kLevels], g.n_img, parts), kTileThreads, 0, st>>>(g, ws, a)));
-  if (kd_stream && kd_stream != st) {
-    e = cudaStreamWaitEvent(st, kd_done, 0);
+  if (ls) {
+    e = cudaStreamWaitEvent(st, ls->early_done, 0);
+    if (e == cudaSuccess && ls->nms_done) e = cudaStreamWaitEvent(st, ls->nms_done, 0);
+    if (e == cudaSuccess && ls->kd_done) e = cudaStreamWaitEvent(st, ls->kd_done, 0);
+    if (e != cudaSuccess) return e;
+    ERD_LAUNCH(kKBoxSweep, st, (box_sweep_kernel<2><<<box_grid, kTileThreads, 0, st>>>(g, ws, a)));
   } else {
-    e = launch_kd(g, ws, a, flags, st);
+    ERD_LAUNCH(kKBoxSweep, st, (box_sweep_kernel<0><<<box_grid, kTileThreads, 0, st>>>(g, ws, a)));
   }
-  if (e != cudaSuccess) return e;
-  ERD_LAUNCH(kKBoxSweep, st,
-             (box_sweep_kernel<<<dim3(g.tile_start[kLevels], g.n_img, 4), kTileThreads, 0, st>>>(g, ws, a)));
   ERD_LAUNCH(kKFinalize, st, (finalize_kernel<<<1, ((total + 31) / 32) * 32, 0, st>>>(g, ws, a)));
   return cudaGetLastError();
 }

@@ -6,6 +6,9 @@
 // (x2-x1)*(y2-y1); suppress when inter / (area_i + area_j - inter) > thr; kept indices are
 // returned in visiting order.  All box arithmetic is IEEE fp32 without contraction.
 // Pairs with an empty intersection are decided without the division (ovr = 0 <= thr).
+//
+// Three launches: sort (one CTA per image), predecessor bit matrix (many CTAs per image),
+// resolve (one CTA per image; also marks the survivors for the box sweep).
 #include "erd_common.cuh"
 
 namespace erd {
@@ -17,7 +20,7 @@ constexpr int kSortThreads = 1024;
 __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(Geo g, Workspace ws,
                                                                 const int32_t* __restrict__ box_inds,
                                                                 const int32_t* __restrict__ box_count,
-                                                                const int32_t* __restrict__ pad_hw, int pow2_cap) {
+                                                                const int32_t* __restrict__ pad_hw) {
   extern __shared__ unsigned long long s_key[];
   __shared__ float s_max[kSortThreads / 32];
   const int n = blockIdx.x;
@@ -74,19 +77,22 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(Geo g, Workspace
   const float unit = __fadd_rn(maxc, 1.0f);
   float4* sorted = ws.nms_box + (size_t)n * g.sel_cap;
   int* order = ws.nms_order + (size_t)n * g.sel_cap;
+  const int NZ = nms_nz_words(g.sel_cap);
+  unsigned long long* nz = ws.nms_nz + (size_t)n * g.sel_cap * NZ;
   for (int i = threadIdx.x; i < K; i += kSortThreads) {
     const int r = (int)(unsigned int)(s_key[i] & 0xffffffffull);
     const float4 b = raw[r];
     const float off = __fmul_rn((float)cls[r], unit);
     sorted[i] = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
     order[i] = r;
+    for (int w = 0; w < NZ; ++w) nz[(size_t)i * NZ + w] = 0ull;
   }
-  (void)pow2_cap;
 }
 
 // Predecessor bit matrix over score-ordered boxes: bit i of pred[j][rb] is set when box
-// rb*64+i, ranked before j, overlaps box j above the threshold.  Only tiles with rb <= cb
-// are written.  256 threads per 64x64 tile: four threads share a column, 16 rows each.
+// rb*64+i, ranked before j, overlaps box j above the threshold.  A word is stored only when
+// it is non-zero, and then flagged in the per-box map nz[j] so the resolve pass touches nothing
+// else.  256 threads per 64x64 tile: four threads share a column, 16 rows each.
 constexpr int kMaskThreads = 256;
 
 __device__ __forceinline__ bool nms_overlaps(const float4& a, float area_a, const float4& b, float area_b,
@@ -99,6 +105,12 @@ __device__ __forceinline__ bool nms_overlaps(const float4& a, float area_a, cons
   return ovr > iou_thr;
 }
 
+__device__ __forceinline__ void nms_tile_of(int t, int W, int& rb, int& cb) {
+  rb = 0;   // t -> (rb, cb), cb >= rb, row-major over the upper triangle
+  while (t >= W - rb) { t -= W - rb; ++rb; }
+  cb = rb + t;
+}
+
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace ws,
                                                                 const int32_t* __restrict__ box_count,
                                                                 float iou_thr) {
@@ -106,37 +118,53 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace
   const int K = box_count[n];
   const int W = (K + 63) >> 6;
   const int Wcap = nms_words(g.sel_cap);
+  const int NZ = nms_nz_words(g.sel_cap);
   const float4* boxes = ws.nms_box + (size_t)n * g.sel_cap;
   unsigned long long* pred = ws.nms_mask + (size_t)n * g.sel_cap * Wcap;
-  __shared__ float4 s_row[64];
-  __shared__ float s_area[64];
+  unsigned long long* nz = ws.nms_nz + (size_t)n * g.sel_cap * NZ;
+  __shared__ float4 s_row[2][64];
   const int col = threadIdx.x >> 2, part = threadIdx.x & 3;
   const int ntile = W * (W + 1) / 2;
-  for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
-    int rb = 0, rem = t;   // t -> (rb, cb), cb >= rb, row-major over the upper triangle
-    while (rem >= W - rb) { rem -= W - rb; ++rb; }
-    const int cb = rb + rem;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-      const int i = rb * 64 + threadIdx.x;
-      const float4 b = i < K ? boxes[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      s_row[threadIdx.x] = b;
-      s_area[threadIdx.x] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; the boxes of the next tile
+  // are fetched while the current one is evaluated
+  int t = blockIdx.x;
+  if (t >= ntile) return;
+  int rb, cb;
+  nms_tile_of(t, W, rb, cb);
+  float4 next_row = (threadIdx.x < 64 && rb * 64 + threadIdx.x < K) ? boxes[rb * 64 + threadIdx.x] : zero4;
+  float4 next_col = cb * 64 + col < K ? boxes[cb * 64 + col] : zero4;
+  int buf = 0;
+  while (t < ntile) {
+    if (threadIdx.x < 64) s_row[buf][threadIdx.x] = next_row;
+    const float4 a = next_col;
+    const int crb = rb, ccb = cb;
+    const int tn = t + gridDim.x;
+    if (tn < ntile) {
+      nms_tile_of(tn, W, rb, cb);
+      next_row = (threadIdx.x < 64 && rb * 64 + threadIdx.x < K) ? boxes[rb * 64 + threadIdx.x] : zero4;
+      next_col = cb * 64 + col < K ? boxes[cb * 64 + col] : zero4;
     }
     __syncthreads();
-    const int j = cb * 64 + col;
+    const int j = ccb * 64 + col;
     unsigned long long bits = 0ull;
     if (j < K) {
-      const float4 a = boxes[j];
       const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
-      const int rmax = (rb == cb) ? col : min(64, K - rb * 64);   // only boxes ranked before j
-#pragma unroll 4
-      for (int r = part * 16; r < part * 16 + 16; ++r)
-        if (r < rmax && nms_overlaps(s_row[r], s_area[r], a, area_a, iou_thr)) bits |= 1ull << r;
+      const int rmax = (crb == ccb) ? col : min(64, K - crb * 64);   // only boxes ranked before j
+      for (int r = part * 16; r < part * 16 + 16 && r < rmax; ++r) {
+        const float4 b = s_row[buf][r];
+        if (nms_overlaps(b, __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)), a, area_a, iou_thr))
+          bits |= 1ull << r;
+      }
     }
     bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
     bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-    if (part == 0 && j < K) pred[(size_t)j * Wcap + rb] = bits;
+    if (part == 0 && bits) {
+      pred[(size_t)j * Wcap + crb] = bits;
+      atomicOr(nz + (size_t)j * NZ + (crb >> 6), 1ull << (crb & 63));
+    }
+    buf ^= 1;
+    t = tn;
   }
 }
 
@@ -144,22 +172,28 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace
 // as soon as a kept predecessor overlaps it and kept once every overlapping predecessor is
 // decided and none is kept -- exactly the sequential greedy result, in as many rounds as the
 // longest overlap chain.  Each round reads the previous round's state (double buffered).
+// Epilogue: survivors in score order; each survivor is flagged (bit 2 of its anchor's flag
+// byte) and its list position recorded so the box sweep finds its distillation row.
 constexpr int kResThreads = 512;
 
 __global__ void __launch_bounds__(kResThreads) nms_resolve_kernel(Geo g, Workspace ws,
+                                                                  const int32_t* __restrict__ box_inds,
                                                                   const int32_t* __restrict__ box_count,
                                                                   int32_t* __restrict__ keep,
-                                                                  int32_t* __restrict__ keep_count) {
+                                                                  int32_t* __restrict__ keep_count,
+                                                                  uint8_t* __restrict__ sel_flags) {
   extern __shared__ unsigned long long s_state[];   // kept[W] decided[W] kept_next[W] decided_next[W]
   const int n = blockIdx.x;
   const int K = box_count[n];
   const int W = (K + 63) >> 6;
   const int Wcap = nms_words(g.sel_cap);
+  const int NZ = nms_nz_words(g.sel_cap);
   unsigned long long* kept = s_state;
   unsigned long long* dec = s_state + Wcap;
   unsigned long long* kept_n = s_state + 2 * Wcap;
   unsigned long long* dec_n = s_state + 3 * Wcap;
   const unsigned long long* pred = ws.nms_mask + (size_t)n * g.sel_cap * Wcap;
+  const unsigned long long* nz = ws.nms_nz + (size_t)n * g.sel_cap * NZ;
   for (int w = threadIdx.x; w < 4 * Wcap; w += kResThreads) s_state[w] = 0ull;
   __syncthreads();
   int pending = K > 0;
@@ -170,12 +204,15 @@ __global__ void __launch_bounds__(kResThreads) nms_resolve_kernel(Geo g, Workspa
       const unsigned long long bit = 1ull << (j & 63);
       if (dec[wj] & bit) continue;
       bool sup = false, wait = false;
-      const unsigned long long* row = pred + (size_t)j * Wcap;
-      for (int w = 0; w <= wj; ++w) {
-        const unsigned long long pr = row[w];
-        if (!pr) continue;
-        if (pr & kept[w]) { sup = true; break; }
-        if (pr & ~dec[w]) wait = true;
+      for (int zw = 0; zw < NZ && !sup; ++zw) {
+        unsigned long long m = nz[(size_t)j * NZ + zw];
+        while (m) {
+          const int w = (zw << 6) + __ffsll((long long)m) - 1;
+          m &= m - 1ull;
+          const unsigned long long pr = pred[(size_t)j * Wcap + w];
+          if (pr & kept[w]) { sup = true; break; }
+          if (pr & ~dec[w]) wait = true;
+        }
       }
       if (sup) {
         atomicOr(dec_n + wj, bit);
@@ -190,8 +227,7 @@ __global__ void __launch_bounds__(kResThreads) nms_resolve_kernel(Geo g, Workspa
     for (int w = threadIdx.x; w < W; w += kResThreads) { kept[w] = kept_n[w]; dec[w] = dec_n[w]; }
     __syncthreads();
   }
-  // survivors in score order: exclusive prefix of the per-word popcounts (W <= a few hundred)
-  __shared__ int s_total;
+  // survivors in score order: exclusive prefix of the per-word popcounts
   if (threadIdx.x == 0) {
     int run = 0;
     for (int w = 0; w < W; ++w) {
@@ -199,21 +235,28 @@ __global__ void __launch_bounds__(kResThreads) nms_resolve_kernel(Geo g, Workspa
       dec[w] = (unsigned long long)run;
       run += c;
     }
-    s_total = run;
+    keep_count[n] = run;
   }
   __syncthreads();
   const int* order = ws.nms_order + (size_t)n * g.sel_cap;
   int32_t* out = keep + (size_t)n * g.sel_cap;
+  const int32_t* list = box_inds + (size_t)n * g.sel_cap;
   for (int j = threadIdx.x; j < K; j += kResThreads) {
     const int wj = j >> 6;
     const unsigned long long kw = kept[wj];
-    if (kw & (1ull << (j & 63))) out[(int)dec[wj] + __popcll(kw & ((1ull << (j & 63)) - 1ull))] = order[j];
+    if (!(kw & (1ull << (j & 63)))) continue;
+    const int pos = order[j];
+    out[(int)dec[wj] + __popcll(kw & ((1ull << (j & 63)) - 1ull))] = pos;
+    // mark the survivor for the box sweep: flag bit 2 and the row of its distillation gradient
+    const int a = list[pos];
+    ws.kd_slot[(size_t)n * g.A + a] = pos;
+    sel_flags[(size_t)n * g.A + a] |= 4;
   }
-  if (threadIdx.x == 0) keep_count[n] = s_total;
 }
 
 cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_inds, const int32_t* box_count,
-                       const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count, cudaStream_t st) {
+                       const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count, uint8_t* sel_flags,
+                       cudaStream_t st) {
   int P = 1;
   while (P < g.sel_cap) P <<= 1;
   const size_t sort_smem = sizeof(unsigned long long) * (size_t)P;
@@ -224,12 +267,13 @@ cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_ind
   }
   if (sort_smem > 200 * 1024) return cudaErrorInvalidValue;
   ERD_LAUNCH(kKNmsSort, st,
-             (nms_sort_kernel<<<g.n_img, kSortThreads, sort_smem, st>>>(g, ws, box_inds, box_count, pad_hw, P)));
+             (nms_sort_kernel<<<g.n_img, kSortThreads, sort_smem, st>>>(g, ws, box_inds, box_count, pad_hw)));
   ERD_LAUNCH(kKNmsMask, st,
              (nms_mask_kernel<<<dim3(48, g.n_img), kMaskThreads, 0, st>>>(g, ws, box_count, iou_thr)));
   const size_t res_smem = sizeof(unsigned long long) * 4 * (size_t)nms_words(g.sel_cap);
   ERD_LAUNCH(kKNmsScan, st,
-             (nms_resolve_kernel<<<g.n_img, kResThreads, res_smem, st>>>(g, ws, box_count, keep, keep_count)));
+             (nms_resolve_kernel<<<g.n_img, kResThreads, res_smem, st>>>(g, ws, box_inds, box_count, keep,
+                                                                         keep_count, sel_flags)));
   return cudaGetLastError();
 }
 

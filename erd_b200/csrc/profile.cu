@@ -8,8 +8,8 @@
 namespace erd {
 
 static const char* kKernelNames[kNumKernels] = {"ers_scan", "ers_select", "atss_candidates", "atss_finalize",
-                                                "pos_prepass", "nms_sort", "nms_mask", "nms_resolve", "upstream_check",
-                                                "cls_sweep", "pos_grad", "kd", "box_sweep", "finalize"};
+                                                "pos_prepass", "nms_sort", "nms_mask", "nms_resolve", "kd_rows", "upstream_check",
+                                                "cls_sweep", "pos_grad", "box_early", "box_sweep", "finalize"};
 
 struct ProfState {
   std::mutex mu;

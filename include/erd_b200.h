@@ -127,10 +127,20 @@ int erd_avg_factors(const ErdShape* shape, const float* const* s_cls, const floa
  * decode in GFLHeadIncrementERD.distill_loss_by_image_single
  * (dense_heads/gfl_head_increment_erd.py:189-202).  Needs the teacher cache written by
  * erd_ers_select.  keep (N, sel_cap) int32 holds positions into the image's box_inds list
- * in descending-score order (what batched_nms returns); keep_count (N,) int32. */
+ * in descending-score order (what batched_nms returns); keep_count (N,) int32.  Survivors are
+ * also marked in sel_flags (bit 2) for erd_loss_fwd_bwd. */
 int erd_teacher_nms(const ErdShape* shape, const int32_t* box_inds, const int32_t* box_count,
                     const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count,
-                    void* ws, void* stream);
+                    uint8_t* sel_flags, void* ws, void* stream);
+
+/* DFL-distribution distillation rows (KL at temperature T, weighted by the student's max
+ * old-class score) of every ERS box candidate; erd_loss_fwd_bwd merges the rows of the NMS
+ * survivors.  Replaces the gathers, weight and loss_ld call of distill_loss_by_image_single
+ * (dense_heads/gfl_head_increment_erd.py:204-221; losses/kd_loss.py:12-37).  Independent of
+ * erd_teacher_nms (may run concurrently with it); both must precede erd_loss_fwd_bwd. */
+int erd_kd_rows(const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
+                const float* const* t_box, const int32_t* box_inds, const int32_t* box_count,
+                void* ws, void* stream);
 
 /* Fused forward + backward of QFL / GIoU / DFL and both distillation losses.
  * Replaces GFLHeadIncrementERD.loss_by_feat_single, distill_loss_by_image_single and the
@@ -162,7 +172,8 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
                      void* stream);
 
 /* One training-step worth of the path in two calls around the caller's all-reduce:
- * erd_step_prepare = erd_ers_select + erd_atss_assign + erd_avg_factors + erd_teacher_nms
+ * erd_step_prepare = erd_ers_select + erd_atss_assign + erd_avg_factors + erd_teacher_nms +
+ * erd_kd_rows
  * (forked over the context's helper streams; assignment and avg factors are joined back into
  * `stream`, the NMS is joined by erd_loss_fwd_bwd(ctx, ...));
  * erd_step_loss = erd_loss_fwd_bwd.  Replaces GFLIncrementERD.loss
