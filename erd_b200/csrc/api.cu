@@ -48,6 +48,7 @@ static int make_geo(const ErdShape* s, Geo* g) {
     g->tile_start[l] = t;
     g->half[l] = 0.5f * (float)s->stride[l] * (s->anchor_scale > 0.f ? s->anchor_scale : 8.0f);
     g->vec[l] = (g->hw[l] % 4 == 0) ? 1 : 0;
+    g->vec2[l] = (g->hw[l] % 2 == 0) ? 1 : 0;
     a += g->hw[l];
     t += (g->hw[l] + kTile - 1) / kTile;
   }
@@ -77,7 +78,7 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->t_arg = (int*)take(NA * 4);
   ws->t_u = (float*)take(NA * 4);
   ws->t_dist = (float4*)take(NA * 16);
-  ws->ers_part = (double*)take((size_t)g.n_img * g.tile_start[kLevels] * 4 * 8);
+  ws->ers_part = (double*)take((size_t)g.n_img * (g.A / 64 + kLevels) * 4 * 8);
   ws->atss_key = (unsigned long long*)take(NA * 8);
   ws->pos_list = (int*)take(NA * 4);
   ws->pos_score = (float*)take(NA * 4);
@@ -107,6 +108,7 @@ static void set_vec(Geo* g, const float* const* a, const float* const* b = nullp
     if (c) bits |= (uintptr_t)c[l];
     if (d) bits |= (uintptr_t)d[l];
     if (bits & 15) g->vec[l] = 0;
+    if (bits & 7) g->vec2[l] = 0;
   }
 }
 

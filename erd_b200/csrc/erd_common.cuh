@@ -28,6 +28,7 @@ struct Geo {
   int h[kLevels], w[kLevels], hw[kLevels], stride[kLevels], start[kLevels];
   int tile_start[kLevels + 1];  // prefix sum of ceil(hw/kTile): CTA index -> level
   int vec[kLevels];             // 1 when hw % 4 == 0 and all level pointers are 16 B aligned
+  int vec2[kLevels];            // 1 when hw % 2 == 0 and all level pointers are 8 B aligned
   float half[kLevels];          // anchor half size = 0.5 * stride * scale
   int sel_cap;                  // A/5 + 1
   int pos_cap;                  // min(A, 45 * max_gt_per_img): rows of the positives' gradient buffer

@@ -3,6 +3,8 @@
 // Reference: GFLIncrementERD.sel_pos / sel_pos_single
 // (mmdet/models/detectors/gfl_increment_erd.py:143-200); the Integral decode fused into the
 // pass is gfl_head_increment_erd.py:40-54,189-195.
+#include <stdlib.h>
+
 #include "erd_common.cuh"
 
 namespace erd {
@@ -11,103 +13,152 @@ namespace erd {
 // Per anchor: m = max_c sigmoid(t_cls) (sigmoid is monotone, so sigmoid(max logit)), the
 // first argmax class, u = max_j raw box logit, and the four softmax-integral distances.
 // Per CTA: sums of m, m^2, u, u^2 in fp64 (deterministic two-level reduction).
-template <bool VEC>
-__device__ __forceinline__ void ers_tile(const Geo& g, const Workspace& ws, const float* __restrict__ cls,
-                                         const float* __restrict__ box, int n, int l, int hw0, double (&acc)[4]) {
-  const int HW = g.hw[l];
-  const Quad<VEC> q(hw0, HW);
-  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-  int arg[4] = {0, 0, 0, 0};
-  const float* cplane = cls + (size_t)n * g.ori * HW;
-#pragma unroll 8
-  for (int c = 0; c < g.ori; ++c) {
-    float v[4];
-    q.load(cplane + (size_t)c * HW, v, -INFINITY);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (v[k] > best[k]) { best[k] = v[k]; arg[k] = c; }
-  }
-  float u[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-  float dist[4][4];
-  const float* bplane = box + (size_t)n * kBoxCh * HW;
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    // one streaming pass per side: exponentials are taken relative to the first bin, so no
-    // 17-value register tile is needed; a non-finite sum (logit spread > 88) redoes the side
-    // with the true maximum.
-    const float* splane = bplane + (size_t)(s * kBins) * HW;
-    float ref[4], sum[4], num[4], mx[4];
-    q.load(splane, ref, 0.f);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { sum[k] = 1.f; num[k] = 0.f; mx[k] = ref[k]; }
-#pragma unroll 4
-    for (int j = 1; j < kBins; ++j) {
-      float v[4];
-      q.load(splane + (size_t)j * HW, v, 0.f);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float e = expf(v[k] - ref[k]);
-        sum[k] += e;
-        num[k] = fmaf((float)j, e, num[k]);
-        mx[k] = fmaxf(mx[k], v[k]);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (!(sum[k] < 3.0e38f) || !(num[k] < 3.0e38f)) {   // overflow: exact two-pass fallback
-        float s2 = 0.f, n2 = 0.f;
-        for (int j = 0; j < kBins; ++j) {
-          const float e = expf(__ldg(splane + (size_t)j * HW + q.hw[k]) - mx[k]);
-          s2 += e;
-          n2 = fmaf((float)j, e, n2);
-        }
-        sum[k] = s2;
-        num[k] = n2;
-      }
-      dist[k][s] = __fdiv_rn(num[k], sum[k]);
-      u[k] = fmaxf(u[k], mx[k]);
-    }
-  }
-  const size_t base = (size_t)n * g.A + g.start[l];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (!q.ok[k]) continue;
-    const float m = sigmoid_ref(best[k]);
-    const size_t a = base + q.hw[k];
-    ws.t_m[a] = m;
-    ws.t_arg[a] = arg[k];
-    ws.t_u[a] = u[k];
-    ws.t_dist[a] = make_float4(dist[k][0], dist[k][1], dist[k][2], dist[k][3]);
-    acc[0] += (double)m;
-    acc[1] += (double)m * (double)m;
-    acc[2] += (double)u[k];
-    acc[3] += (double)u[k] * (double)u[k];
+//
+// Loads are decoupled from the arithmetic: a CTA owns T consecutive anchors of one (image,
+// level) and requests its whole [ori + 68] x T logit tile up front with bulk asynchronous
+// copies (cp.async.bulk, completion on mbarriers, one barrier per channel group); every
+// thread then reduces its own anchor's column out of shared memory while the co-resident
+// CTAs' copies are in flight.  This keeps > 200 KB of HBM requests outstanding per SM
+// independent of register pressure (a register-staged version of this pass sat at 2.7 TB/s,
+// latency-bound).  Bulk copies need 16 B aligned rows (hw % 4 == 0); tiles of the other levels
+// (a few % of the anchors) are filled with ordinary loads.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   }
 }
 
-__global__ void __launch_bounds__(kTileThreads) ers_scan_kernel(Geo g, Workspace ws, Ptr5 t_cls, Ptr5 t_box) {
+template <int T>
+__global__ void __launch_bounds__(T) ers_scan_kernel(Geo g, Workspace ws, Ptr5 t_cls, Ptr5 t_box) {
+  extern __shared__ __align__(128) float s_tile[];   // [ori + 68][T]
+  __shared__ __align__(8) unsigned long long s_bar[5];
+  __shared__ double s_red[T / 32][4];
   const int n = blockIdx.y;
-  const int tile = blockIdx.x;
-  const int l = level_of_tile(g, tile);
-  const int hw0 = (tile - g.tile_start[l]) * kTile;
+  int tile = blockIdx.x, l = 0;
+#pragma unroll
+  for (int i = 0; i < kLevels - 1; ++i) {
+    const int tl = (g.hw[i] + T - 1) / T;
+    if (l == i && tile >= tl) { tile -= tl; ++l; }
+  }
+  const int HW = g.hw[l];
+  const int hw0 = tile * T;
+  const int cnt = min(T, HW - hw0);
+  const int ori = g.ori;
+  const bool bulk = g.vec[l] != 0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int b = 0; b < 5; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[b])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (!bulk) {
+    // unaligned level: every thread fetches its own column, 8 loads in flight
+    if ((int)threadIdx.x < cnt) {
+      const float* cb = t_cls.p[l] + (size_t)n * ori * HW + hw0 + threadIdx.x;
+#pragma unroll 8
+      for (int c = 0; c < ori; ++c) s_tile[(size_t)c * T + threadIdx.x] = __ldg(cb + (size_t)c * HW);
+      const float* bb = t_box.p[l] + (size_t)n * kBoxCh * HW + hw0 + threadIdx.x;
+#pragma unroll 8
+      for (int c = 0; c < kBoxCh; ++c) s_tile[(size_t)(ori + c) * T + threadIdx.x] = __ldg(bb + (size_t)c * HW);
+    }
+  } else if (threadIdx.x < 32) {
+    const uint32_t row_bytes = (uint32_t)cnt * 4u;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar[0])), "r"(row_bytes * (uint32_t)ori) : "memory");
+#pragma unroll
+      for (int b = 1; b < 5; ++b)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar[b])), "r"(row_bytes * (uint32_t)kBins) : "memory");
+    }
+    __syncwarp();
+    const float* cbase = t_cls.p[l] + (size_t)n * ori * HW + hw0;
+    for (int c = threadIdx.x; c < ori; c += 32)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(s_tile + (size_t)c * T)), "l"(cbase + (size_t)c * HW), "r"(row_bytes), "r"(smem_u32(&s_bar[0])) : "memory");
+    const float* bbase = t_box.p[l] + (size_t)n * kBoxCh * HW + hw0;
+    for (int c = threadIdx.x; c < kBoxCh; c += 32)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(s_tile + (size_t)(ori + c) * T)), "l"(bbase + (size_t)c * HW), "r"(row_bytes),
+                     "r"(smem_u32(&s_bar[1 + c / kBins])) : "memory");
+  }
+  const bool on = (int)threadIdx.x < cnt;
+  const float* col = s_tile + threadIdx.x;
+  // class logits: first maximum (argmax semantics of torch.max) and its sigmoid
+  if (bulk) mbar_wait(&s_bar[0], 0);
+  float best = -INFINITY;
+  int arg = 0;
+  if (on) {
+#pragma unroll 8
+    for (int c = 0; c < ori; ++c) {
+      const float v = col[(size_t)c * T];
+      if (v > best) { best = v; arg = c; }
+    }
+  }
+  float u = -INFINITY;
+  float dist[4];
+#pragma unroll
+  for (int sd = 0; sd < 4; ++sd) {
+    if (bulk) mbar_wait(&s_bar[1 + sd], 0);
+    const float* scol = col + (size_t)(ori + sd * kBins) * T;
+    float z[kBins];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) {
+      z[j] = on ? scol[(size_t)j * T] : 0.f;
+      mx = fmaxf(mx, z[j]);
+    }
+    float sum = 0.f, num = 0.f;
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) {
+      const float e = __expf(z[j] - mx);
+      sum += e;
+      num = fmaf((float)j, e, num);
+    }
+    dist[sd] = __fdiv_rn(num, sum);
+    u = fmaxf(u, mx);
+  }
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  if (g.vec[l])
-    ers_tile<true>(g, ws, t_cls.p[l], t_box.p[l], n, l, hw0, acc);
-  else
-    ers_tile<false>(g, ws, t_cls.p[l], t_box.p[l], n, l, hw0, acc);
-  __shared__ double red[kTileThreads / 32][4];
+  if (on) {
+    const float m = sigmoid_ref(best);
+    const size_t a = (size_t)n * g.A + g.start[l] + hw0 + threadIdx.x;
+    ws.t_m[a] = m;
+    ws.t_arg[a] = arg;
+    ws.t_u[a] = u;
+    ws.t_dist[a] = make_float4(dist[0], dist[1], dist[2], dist[3]);
+    acc[0] = (double)m;
+    acc[1] = (double)m * (double)m;
+    acc[2] = (double)u;
+    acc[3] = (double)u * (double)u;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) acc[i] = warp_sum(acc[i]);
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) red[threadIdx.x >> 5][i] = acc[i];
+    for (int i = 0; i < 4; ++i) s_red[threadIdx.x >> 5][i] = acc[i];
   }
   __syncthreads();
   if (threadIdx.x < 4) {
-    double s = 0.0;
-    for (int w = 0; w < kTileThreads / 32; ++w) s += red[w][threadIdx.x];
-    ws.ers_part[((size_t)n * gridDim.x + tile) * 4 + threadIdx.x] = s;
+    double sm = 0.0;
+    for (int w = 0; w < T / 32; ++w) sm += s_red[w][threadIdx.x];
+    ws.ers_part[((size_t)n * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = sm;
   }
+}
+
+template <int T>
+static int launch_scan(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box, cudaStream_t st) {
+  int tiles = 0;
+  for (int l = 0; l < kLevels; ++l) tiles += (g.hw[l] + T - 1) / T;
+  const size_t smem = (size_t)(g.ori + kBoxCh) * T * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(ers_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  ERD_LAUNCH(kKErsScan, st, (ers_scan_kernel<T><<<dim3(tiles, g.n_img), T, smem, st>>>(g, ws, t_cls, t_box)));
+  return tiles;
 }
 
 // ----------------------------------------------------------------------------- pass 2
@@ -128,17 +179,34 @@ __global__ void __launch_bounds__(kSelThreads) ers_select_kernel(Geo g, Workspac
   __shared__ float s_thr[2];
   __shared__ int s_warp[2][kSelThreads / 32];
   __shared__ int s_base[2];
-  if (threadIdx.x < 2) {
-    double s1 = 0.0, s2 = 0.0;
-    const double* p = ws.ers_part + (size_t)n * tiles * 4 + threadIdx.x * 2;
-    for (int t = 0; t < tiles; ++t) { s1 += p[t * 4]; s2 += p[t * 4 + 1]; }
-    const double A = (double)g.A;
-    const double mean = s1 / A;
-    double var = (s2 - s1 * s1 / A) / (A - 1.0);   // A == 1 -> NaN, as torch.std
-    if (var < 0.0) var = 0.0;
-    const float t = __fadd_rn((float)mean, __fmul_rn(2.0f, (float)sqrt(var)));
-    s_thr[threadIdx.x] = t;
-    if (blockIdx.x == 0) thr_out[n * 2 + threadIdx.x] = t;
+  {
+    // image statistics from the per-CTA partial sums of pass 1: fixed thread -> partial mapping
+    // and a fixed reduction tree, so the thresholds are bit-reproducible run to run
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* p = ws.ers_part + (size_t)n * tiles * 4;
+    for (int t = threadIdx.x; t < tiles; t += kSelThreads) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] += p[t * 4 + i];
+    }
+    __shared__ double s_red[kSelThreads / 32][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = warp_sum(acc[i]);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_red[threadIdx.x >> 5][i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int w = 0; w < kSelThreads / 32; ++w) { s1 += s_red[w][threadIdx.x * 2]; s2 += s_red[w][threadIdx.x * 2 + 1]; }
+      const double A = (double)g.A;
+      const double mean = s1 / A;
+      double var = (s2 - s1 * s1 / A) / (A - 1.0);   // A == 1 -> NaN, as torch.std
+      if (var < 0.0) var = 0.0;
+      const float t = __fadd_rn((float)mean, __fmul_rn(2.0f, (float)sqrt(var)));
+      s_thr[threadIdx.x] = t;
+      if (blockIdx.x == 0) thr_out[n * 2 + threadIdx.x] = t;
+    }
   }
   __syncthreads();
   const float thr_c = s_thr[0], thr_b = s_thr[1];
@@ -147,9 +215,21 @@ __global__ void __launch_bounds__(kSelThreads) ers_select_kernel(Geo g, Workspac
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // selected rows before this chunk
   int pc = 0, pb = 0;
-  for (int a = threadIdx.x; a < chunk0; a += kSelThreads) {
-    pc += m[a] > thr_c;
-    pb += u[a] > thr_b;
+  if ((((uintptr_t)m | (uintptr_t)u) & 15) == 0) {   // chunk0 is a multiple of 2048: 16 B loads, 4 in flight
+    const float4* m4 = reinterpret_cast<const float4*>(m);
+    const float4* u4 = reinterpret_cast<const float4*>(u);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < chunk0 / 4; i += kSelThreads) {
+      const float4 a = m4[i], b = u4[i];
+      pc += (a.x > thr_c) + (a.y > thr_c) + (a.z > thr_c) + (a.w > thr_c);
+      pb += (b.x > thr_b) + (b.y > thr_b) + (b.z > thr_b) + (b.w > thr_b);
+    }
+  } else {
+#pragma unroll 8
+    for (int a = threadIdx.x; a < chunk0; a += kSelThreads) {
+      pc += m[a] > thr_c;
+      pb += u[a] > thr_b;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -209,8 +289,19 @@ __global__ void __launch_bounds__(kSelThreads) ers_select_kernel(Geo g, Workspac
 cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box, int32_t* cls_inds,
                        int32_t* cls_count, int32_t* box_inds, int32_t* box_count, float* thr, uint8_t* sel_flags,
                        cudaStream_t st) {
-  const int tiles = g.tile_start[kLevels];
-  ERD_LAUNCH(kKErsScan, st, (ers_scan_kernel<<<dim3(tiles, g.n_img), kTileThreads, 0, st>>>(g, ws, t_cls, t_box)));
+  // anchors per CTA: the largest tile that still lets two CTAs share an SM's shared memory
+  const size_t row = (size_t)(g.ori + kBoxCh) * sizeof(float);
+  static int forced = -1;   // ERD_SCAN_TILE=64|128|256 overrides (tuning)
+  if (forced < 0) {
+    const char* e = getenv("ERD_SCAN_TILE");
+    forced = e ? atoi(e) : 0;
+  }
+  int T = forced ? forced : (row * 256 <= 110 * 1024 ? 256 : row * 128 <= 110 * 1024 ? 128 : 64);
+  if (row * T > 220 * 1024) return cudaErrorInvalidValue;
+  int tiles;
+  if (T == 256) tiles = launch_scan<256>(g, ws, t_cls, t_box, st);
+  else if (T == 128) tiles = launch_scan<128>(g, ws, t_cls, t_box, st);
+  else tiles = launch_scan<64>(g, ws, t_cls, t_box, st);
   ERD_LAUNCH(kKErsSelect, st,
              (ers_select_kernel<<<dim3((g.A + kSelChunk - 1) / kSelChunk, g.n_img), kSelThreads, 0, st>>>(
                  g, ws, tiles, cls_inds, cls_count, box_inds,
