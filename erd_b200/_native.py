@@ -52,7 +52,7 @@ SIGNATURES = {
     'erd_teacher_nms': [_SH, _P, _P, _P, _F, _P, _P, _P, _P, _P],
     'erd_kd_rows': [_SH, PtrArray, PtrArray, PtrArray, _P, _P, _P, _P],
     'erd_loss_fwd_bwd': [_P, _SH, PtrArray, PtrArray, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                         _P, _P, _F, _P, _I, _P, PtrArray, PtrArray, _P, _P],
+                         _P, _P, _P, _F, _P, _I, _P, PtrArray, PtrArray, _P, _P],
     'erd_step_prepare': [_P, _SH, PtrArray, PtrArray, PtrArray, PtrArray, _P, _P, _P, _P, _F,
                          C.POINTER(ErdStepBuffers), _P, _P, C.c_uint32],
     'erd_profile_enable': [C.c_uint],
@@ -60,6 +60,8 @@ SIGNATURES = {
     'erd_profile_num_kernels': [],
     'erd_profile_kernel_name': [C.c_int],
     'erd_profile_collect': [C.POINTER(C.c_float), C.POINTER(C.c_int)],
+    'erd_profile_mark': [_P],
+    'erd_profile_timeline': [C.POINTER(C.c_float), C.POINTER(C.c_float)],
 }
 
 _lib = None

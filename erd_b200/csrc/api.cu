@@ -90,10 +90,9 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->pos_rows = (float*)take((size_t)g.n_img * g.pos_cap * kBoxCh * 4);
   ws->nms_nz = (unsigned long long*)take(NS * nms_nz_words(g.sel_cap) * 8);
   ws->counters = (unsigned int*)take(8 * 4);
-  ws->nms_raw = (float4*)take(NS * 16);
+  ws->nms_score = (float*)take(NS * 4);
   ws->nms_cls = (int*)take(NS * 4);
   ws->nms_box = (float4*)take(NS * 16);
-  ws->nms_order = (int*)take(NS * 4);
   ws->nms_mask = (unsigned long long*)take(NS * nms_words(g.sel_cap) * 8);
   ws->loss_acc = (double*)take((size_t)(3 * kLevels + 2 * g.n_img) * 8);
   ws->bytes = off;
@@ -133,7 +132,7 @@ static MPtr5 mptr5(float* const* p) {
 
 struct ErdContext {
   cudaStream_t side[3];          // [0] assignment + positives prepass, [1] teacher NMS, [2] KD rows
-  cudaEvent_t fork, join[3], sel, early_done;
+  cudaEvent_t fork, join[3], sel, early_done, nms_all;
   bool nms_pending;              // join[1] recorded by erd_step_prepare, not yet waited on
 };
 
@@ -160,13 +159,18 @@ int erd_create(ErdContext** ctx) {
   if (!ctx) return fail(ERD_ERR_NULL, "ctx is NULL");
   ErdContext* c = new ErdContext();
   cudaError_t e = cudaSuccess;
+  // the NMS chain is short, serial and latency-bound: give it the highest priority so its few
+  // CTAs are not queued behind the bandwidth-bound kernels running beside it
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
-    e = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
+    e = cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, i == 1 ? prio_greatest : prio_least);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sel, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->early_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->nms_all, cudaEventDisableTiming);
   c->nms_pending = false;
   if (e != cudaSuccess) {
     delete c;
@@ -185,6 +189,7 @@ int erd_destroy(ErdContext* c) {
   cudaEventDestroy(c->fork);
   cudaEventDestroy(c->sel);
   cudaEventDestroy(c->early_done);
+  cudaEventDestroy(c->nms_all);
   delete c;
   return ERD_OK;
 }
@@ -246,8 +251,23 @@ int erd_teacher_nms(const ErdShape* shape, const int32_t* box_inds, const int32_
   Workspace ws;
   carve(g, wsp, &ws);
   cudaError_t e = launch_nms(g, ws, box_inds, box_count, pad_hw, iou_thr, keep, keep_count, sel_flags,
-                             (cudaStream_t)stream);
+                             (cudaStream_t)stream, nullptr, nullptr);
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_teacher_nms");
+}
+
+// erd_teacher_nms on the context's NMS stream: `resolved` fires as soon as the survivors are
+// marked (all the loss needs), `all_done` after the keep list has been put in score order.
+static int nms_on_side_stream(ErdContext* ctx, const ErdShape* shape, const ErdStepBuffers* b, const int32_t* pad_hw,
+                              float iou_thr, void* wsp) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  Workspace ws;
+  carve(g, wsp, &ws);
+  cudaError_t e = launch_nms(g, ws, b->box_inds, b->box_count, pad_hw, iou_thr, b->keep, b->keep_count, b->sel_flags,
+                             ctx->side[1], ctx->sel, ctx->join[1]);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->nms_all, ctx->side[1]);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_step_prepare nms");
 }
 
 int erd_kd_rows(const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
@@ -268,7 +288,8 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
                      const float* const* t_cls, const float* const* t_box, const float* gt_boxes,
                      const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
                      const int32_t* gt_inds, const int32_t* num_pos, const int32_t* cls_count,
-                     const uint8_t* sel_flags, const int32_t* box_inds, const int32_t* keep,
+                     const uint8_t* sel_flags, const int32_t* box_inds, const int32_t* box_count,
+                     const int32_t* keep,
                      const int32_t* keep_count, const float* avg, float dist_loss_weight, const float* upstream,
                      int32_t skip_if_unit_upstream, float* losses, float* const* g_cls, float* const* g_box,
                      void* wsp, void* stream) {
@@ -276,7 +297,8 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
   int rc = make_geo(shape, &g);
   if (rc) return rc;
   if (NULLS(s_cls) || NULLS(s_box) || NULLS(t_cls) || NULLS(t_box) || NULLS(g_cls) || NULLS(g_box) || !gt_offsets ||
-      !pad_hw || !gt_inds || !num_pos || !cls_count || !sel_flags || !box_inds || !keep || !keep_count || !avg ||
+      !pad_hw || !gt_inds || !num_pos || !cls_count || !sel_flags || !box_inds || !box_count || !keep || !keep_count ||
+      !avg ||
       !losses || !wsp || (g.total_gt > 0 && (!gt_boxes || !gt_labels)))
     return fail(ERD_ERR_NULL, "erd_loss_fwd_bwd: NULL argument");
   set_vec(&g, s_cls, s_box, g_cls, g_box);
@@ -299,6 +321,7 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
   a.cls_count = cls_count;
   a.sel_flags = sel_flags;
   a.box_inds = box_inds;
+  a.box_count = box_count;
   a.keep = keep;
   a.keep_count = keep_count;
   a.avg = avg;
@@ -317,7 +340,10 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
     ls.early_done = ctx->early_done;
     ls.nms_done = ctx->nms_pending ? ctx->join[1] : nullptr;
     ls.kd_done = ctx->nms_pending ? ctx->join[2] : nullptr;
+    const bool had_nms = ctx->nms_pending;
     e = launch_loss(g, ws, a, (cudaStream_t)stream, &ls);
+    // the score-ordered keep list is an output only: join it last
+    if (e == cudaSuccess && had_nms) e = cudaStreamWaitEvent((cudaStream_t)stream, ctx->nms_all, 0);
     ctx->nms_pending = false;
   } else {
     e = launch_loss(g, ws, a, (cudaStream_t)stream, nullptr);
@@ -333,7 +359,7 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   cudaStream_t main = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
   if (ctx->nms_pending) {   // a previous prepare whose NMS nobody consumed: do not race its teacher cache
-    e = cudaStreamWaitEvent(main, ctx->join[1], 0);
+    e = cudaStreamWaitEvent(main, ctx->nms_all, 0);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ctx->join[2], 0);
     ctx->nms_pending = false;
   }
@@ -355,14 +381,16 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   e = cudaEventRecord(ctx->sel, main);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[1], ctx->sel, 0);
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork nms");
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[2], ctx->sel, 0);
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork kd");
-  rc = erd_teacher_nms(shape, b->box_inds, b->box_count, pad_hw, iou_thr, b->keep, b->keep_count, b->sel_flags, wsp,
-                       ctx->side[1]);
+  if (!b->box_inds || !b->box_count || !pad_hw || !b->keep || !b->keep_count || !b->sel_flags || !wsp)
+    return fail(ERD_ERR_NULL, "erd_step_prepare: NULL NMS buffer");
+  rc = nms_on_side_stream(ctx, shape, b, pad_hw, iou_thr, wsp);
+  // the distillation rows (random DRAM gathers) start once the NMS has finished its own gathers
+  // (ctx->sel is re-recorded behind nms_prep), so they do not stretch the latency-bound chain
+  if (!rc && cudaStreamWaitEvent(ctx->side[2], ctx->sel, 0) != cudaSuccess) rc = fail(ERD_ERR_CUDA, "fork kd");
   if (!rc) rc = erd_kd_rows(shape, s_cls, s_box, t_box, b->box_inds, b->box_count, wsp, ctx->side[2]);
   if (rc) return rc;
-  e = cudaEventRecord(ctx->join[1], ctx->side[1]);
-  if (e == cudaSuccess) e = cudaEventRecord(ctx->join[2], ctx->side[2]);
+  e = cudaEventRecord(ctx->join[2], ctx->side[2]);
   if (e == cudaSuccess) ctx->nms_pending = true;
   if (e == cudaSuccess) e = cudaEventRecord(ctx->join[0], ctx->side[0]);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ctx->join[0], 0);

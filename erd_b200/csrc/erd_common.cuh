@@ -54,11 +54,10 @@ struct Workspace {
   float* pos_rows;                // [N][pos_cap][68] box-logit gradient rows of the positives
   unsigned long long* nms_nz;     // [N][sel_cap][nz_words] which words of a predecessor row are non-zero
   unsigned int* counters;         // [8] last-block tickets
-  float4* nms_raw;                // [N][sel_cap] decoded teacher boxes in list order
+  float* nms_score;               // [N][sel_cap] teacher confidence of each selected row, list order
   int* nms_cls;                   // [N][sel_cap] class ids in list order
-  float4* nms_box;                // [N][sel_cap] offset boxes in score order
-  int* nms_order;                 // [N][sel_cap] list position of each score-ordered box
-  unsigned long long* nms_mask;   // [N][sel_cap][W] suppression bit matrix, W = ceil(sel_cap/64)
+  float4* nms_box;                // [N][sel_cap] class-offset teacher boxes, list order
+  unsigned long long* nms_mask;   // [N][sel_cap][W] predecessor bit matrix, W = ceil(sel_cap/64)
   double* loss_acc;               // [3L + 2N]
   size_t bytes;
 };
@@ -146,7 +145,7 @@ struct Quad {
 };
 
 // ---------------------------------------------------------------- launch accounting (profile.cu)
-enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan,
+enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan, kKNmsOrder,
                 kKKdRows, kKUpCheck, kKLossMain, kKPosGrad, kKBoxEarly, kKBoxSweep, kKFinalize, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
@@ -172,7 +171,7 @@ cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, con
                        const int32_t* gt_inds, const int32_t* num_pos, float* avg, cudaStream_t st);
 cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_inds, const int32_t* box_count,
                        const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count, uint8_t* sel_flags,
-                       cudaStream_t st);
+                       cudaStream_t st, cudaEvent_t prepped, cudaEvent_t resolved);
 
 struct LossArgs {
   Ptr5 s_cls, s_box, t_cls, t_box;
@@ -186,6 +185,7 @@ struct LossArgs {
   const int32_t* cls_count;
   const uint8_t* sel_flags;
   const int32_t* box_inds;
+  const int32_t* box_count;
   const int32_t* keep;
   const int32_t* keep_count;
   const float* avg;

@@ -166,8 +166,8 @@ static int launch_scan(const Geo& g, const Workspace& ws, const Ptr5& t_cls, con
 // nonzero() yields, gfl_increment_erd.py:150-151,158-159).  Each CTA owns a 2048-anchor chunk
 // of one image; it recounts the flags of the anchors before its chunk from the L2-resident
 // cache instead of waiting on a cross-CTA prefix, so one launch suffices.
-constexpr int kSelThreads = 256;
-constexpr int kSelPer = 8;
+constexpr int kSelThreads = 1024;
+constexpr int kSelPer = 2;
 constexpr int kSelChunk = kSelThreads * kSelPer;
 
 __global__ void __launch_bounds__(kSelThreads) ers_select_kernel(Geo g, Workspace ws, int tiles, int32_t* cls_inds,

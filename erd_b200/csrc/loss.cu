@@ -423,16 +423,16 @@ __global__ void __launch_bounds__(kKdThreads) kd_rows_kernel(Geo g, Workspace ws
 // zero, plus the compact row of a positive (pos_kernel<true>), plus the distillation row of an
 // NMS survivor (kd_rows_kernel, marked by the NMS resolve pass).
 //
-// MODE 0: everything in one launch.  MODE 1 ("early", runs beside the NMS): only 8-anchor
-// groups that hold no ERS box candidate, i.e. whose result cannot depend on the NMS.
-// MODE 2 ("late", after the NMS): the remaining groups.  Groups are whole 32 B sectors, so
-// the two launches never share a sector.
+// MODE 0: everything in one launch.  MODE 1 ("early", runs beside the NMS): only the groups
+// that hold no ERS box candidate, i.e. whose result cannot depend on the NMS; the remaining
+// groups are written after the NMS by box_late_kernel, one warp per candidate.  On 16 B aligned
+// levels a group is 8 consecutive anchors = one 32 B sector per channel, so the two launches
+// never share a sector; on the other levels (a few % of the anchors) a group is one anchor.
 template <bool VEC, int MODE>
 __device__ __forceinline__ void box_tile(const Geo& g, const Workspace& ws, const LossArgs& A, int n, int l,
                                          int hw0, int side, float& kd_loss) {
-  if (!VEC && MODE == 1) return;   // scalar levels (a few % of the anchors) are handled late
   const int HW = g.hw[l];
-  const Quad<VEC> q(hw0, HW);
+  Quad<VEC> q(hw0, HW);
   const size_t abase = (size_t)n * g.A + g.start[l];
   const float* prow[4];
   const float* krow[4];
@@ -445,6 +445,7 @@ __device__ __forceinline__ void box_tile(const Geo& g, const Workspace& ws, cons
     const size_t a = abase + q.hw[k];
     const unsigned flags = A.sel_flags[a];
     cand |= (flags & 2) != 0;
+    if (!VEC && MODE == 1 && (flags & 2)) { q.ok[k] = false; continue; }   // scalar levels: groups are single anchors
     if (MODE != 1 && (flags & 4)) {
       const size_t slot = (size_t)n * g.sel_cap + ws.kd_slot[a];
       krow[k] = ws.kd_rows + slot * kBoxCh + side * kBins;
@@ -500,6 +501,68 @@ __global__ void __launch_bounds__(kTileThreads) box_sweep_kernel(Geo g, Workspac
     double s = 0.0;
     for (int w = 0; w < kTileThreads / 32; ++w) s += (double)red[w];
     if (s != 0.0) atomicAdd(ws.loss_acc + acc_dbox(g, n), s);
+  }
+}
+
+// Late box gradients, list driven: one warp per ERS box candidate writes the whole group the
+// candidate lives in (lane = anchor-in-group x side), merging positives' rows and, where the
+// NMS kept the anchor, its distillation row.  A group shared by several candidates is written
+// by the warp of its first candidate only.
+constexpr int kLateThreads = 256;
+
+__global__ void __launch_bounds__(kLateThreads) box_late_kernel(Geo g, Workspace ws, LossArgs A,
+                                                                const int32_t* __restrict__ box_count) {
+  if (A.skip_flag && *A.skip_flag == 0u) return;
+  const int n = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K = box_count[n];
+  const float kT = g.T;
+  const float scale = upstream_of(A.upstream, acc_dbox(g, n)) * A.dlw * g.w_ld / 4.0f * (kT * kT / (float)kBins) / kT;
+  float kd = 0.f;
+  for (int r = blockIdx.x * (kLateThreads / 32) + warp; r < K; r += gridDim.x * (kLateThreads / 32)) {
+    const int a = A.box_inds[(size_t)n * g.sel_cap + r];
+    const int l = level_of_anchor(g, a);
+    const int HW = g.hw[l];
+    const int hw = a - g.start[l];
+    const size_t abase = (size_t)n * g.A + g.start[l];
+    const bool vec = g.vec[l] != 0;
+    const int g0 = vec ? (hw & ~7) : hw;
+    const int k = vec ? (lane & 7) : 0;
+    const int side = vec ? (lane >> 3) : lane;
+    const int hwk = g0 + k;
+    const bool live = hwk < HW && side < 4;
+    const unsigned flags = live ? A.sel_flags[abase + hwk] : 0u;
+    if (vec) {   // the first candidate of the group owns it
+      const unsigned cands = __ballot_sync(0xffffffffu, (flags & 2) != 0) & 0xffu;
+      if (g0 + __ffs(cands) - 1 != hw) continue;
+    }
+    if (!live) continue;
+    const float* prow = nullptr;
+    const float* krow = nullptr;
+    if (A.gt_inds[abase + hwk] > 0)
+      prow = ws.pos_rows + ((size_t)n * g.pos_cap + ws.pos_slot[abase + hwk]) * kBoxCh + side * kBins;
+    if (flags & 4) {
+      const size_t slot = (size_t)n * g.sel_cap + ws.kd_slot[abase + hwk];
+      krow = ws.kd_rows + slot * kBoxCh + side * kBins;
+      if (side == 0) kd += ws.kd_loss[slot];
+    }
+    float* gp = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW + hwk;
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) {
+      float v = 0.f;
+      if (prow) v = prow[j];
+      if (krow) v = fmaf(scale, krow[j], v);
+      gp[(size_t)j * HW] = v;
+    }
+  }
+  __shared__ float red[kLateThreads / 32];
+  kd = warp_sum(kd);
+  if (lane == 0) red[warp] = kd;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s2 = 0.0;
+    for (int w = 0; w < kLateThreads / 32; ++w) s2 += (double)red[w];
+    if (s2 != 0.0) atomicAdd(ws.loss_acc + acc_dbox(g, n), s2);
   }
 }
 
@@ -588,12 +651,15 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
   p.avg = const_cast<float*>(a.avg);
   p.upstream = a.upstream;
   p.skip_flag = a.skip_flag;
-  ERD_LAUNCH(kKPosGrad, st, (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, st>>>(g, ws, p)));
   const dim3 box_grid(g.tile_start[kLevels], g.n_img, 4);
   if (ls) {   // fork: early box sectors beside the class sweep
     e = cudaEventRecord(ls->fork, st);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ls->early, ls->fork, 0);
     if (e != cudaSuccess) return e;
+    // the positives' gradient rows are consumed by the box kernels only: keep them off the
+    // class sweep's stream
+    ERD_LAUNCH(kKPosGrad, ls->early,
+               (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, ls->early>>>(g, ws, p)));
     ERD_LAUNCH(kKBoxEarly, ls->early, (box_sweep_kernel<1><<<box_grid, kTileThreads, 0, ls->early>>>(g, ws, a)));
     e = cudaEventRecord(ls->early_done, ls->early);
     if (e != cudaSuccess) return e;
@@ -606,8 +672,9 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
     if (e == cudaSuccess && ls->nms_done) e = cudaStreamWaitEvent(st, ls->nms_done, 0);
     if (e == cudaSuccess && ls->kd_done) e = cudaStreamWaitEvent(st, ls->kd_done, 0);
     if (e != cudaSuccess) return e;
-    ERD_LAUNCH(kKBoxSweep, st, (box_sweep_kernel<2><<<box_grid, kTileThreads, 0, st>>>(g, ws, a)));
+    ERD_LAUNCH(kKBoxSweep, st, (box_late_kernel<<<dim3(32, g.n_img), kLateThreads, 0, st>>>(g, ws, a, a.box_count)));
   } else {
+    ERD_LAUNCH(kKPosGrad, st, (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, st>>>(g, ws, p)));
     ERD_LAUNCH(kKBoxSweep, st, (box_sweep_kernel<0><<<box_grid, kTileThreads, 0, st>>>(g, ws, a)));
   }
   ERD_LAUNCH(kKFinalize, st, (finalize_kernel<<<1, ((total + 31) / 32) * 32, 0, st>>>(g, ws, a)));

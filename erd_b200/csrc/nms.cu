@@ -7,92 +7,74 @@
 // returned in visiting order.  All box arithmetic is IEEE fp32 without contraction.
 // Pairs with an empty intersection are decided without the division (ovr = 0 <= thr).
 //
-// Three launches: sort (one CTA per image), predecessor bit matrix (many CTAs per image),
-// resolve (one CTA per image; also marks the survivors for the box sweep).
+// Launches: prep (one CTA per image: decode, class offsets), predecessor bit matrix (many CTAs
+// per image), resolve (one CTA per image; also marks the survivors for the box sweep), and --
+// off the critical path -- the ordering of the survivors by score that batched_nms returns.
+// Nothing before the resolve pass needs the boxes sorted: "i is visited before j" is evaluated
+// per pair as (score_i > score_j) or (equal scores and i earlier in the list).
 #include "erd_common.cuh"
 
 namespace erd {
 
-constexpr int kSortThreads = 1024;
+constexpr int kPrepThreads = 1024;
 
-// One CTA per image: build boxes, find the coordinate maximum, sort by (score desc, list
-// position asc), apply the class offset, write boxes in score order.
-__global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(Geo g, Workspace ws,
+// One CTA per image: teacher boxes of the selected rows, the coordinate maximum, class offsets;
+// zeroes the image's slice of the predecessor matrix and map.
+__global__ void __launch_bounds__(kPrepThreads) nms_prep_kernel(Geo g, Workspace ws,
                                                                 const int32_t* __restrict__ box_inds,
                                                                 const int32_t* __restrict__ box_count,
                                                                 const int32_t* __restrict__ pad_hw) {
-  extern __shared__ unsigned long long s_key[];
-  __shared__ float s_max[kSortThreads / 32];
+  __shared__ float s_max[kPrepThreads / 32];
   const int n = blockIdx.x;
   const int K = box_count[n];
-  if (K == 0) return;
-  int P = 1;
-  while (P < K) P <<= 1;
   const int pad_h = pad_hw[n * 2], pad_w = pad_hw[n * 2 + 1];
   const int32_t* list = box_inds + (size_t)n * g.sel_cap;
-  float4* raw = ws.nms_raw + (size_t)n * g.sel_cap;
+  float4* boxes = ws.nms_box + (size_t)n * g.sel_cap;
+  float* score = ws.nms_score + (size_t)n * g.sel_cap;
   int* cls = ws.nms_cls + (size_t)n * g.sel_cap;
   float mx = -INFINITY;
-  for (int r = threadIdx.x; r < P; r += kSortThreads) {
-    unsigned long long key = ~0ull;
-    if (r < K) {
-      const int a = list[r];
-      const size_t ga = (size_t)n * g.A + a;
-      const int l = level_of_anchor(g, a);
-      const int rel = a - g.start[l];
-      const int x = rel % g.w[l], y = rel / g.w[l];
-      const int s = g.stride[l];
-      // anchors handed to the distillation step were unmap()ed with fill 0
-      // (gfl_head.py:660): anchors outside pad_shape sit at the origin.
-      const bool valid = x < min((pad_w + s - 1) / s, g.w[l]) && y < min((pad_h + s - 1) / s, g.h[l]);
-      const float cx = valid ? (float)(x * s) : 0.f, cy = valid ? (float)(y * s) : 0.f;
-      const float4 d = ws.t_dist[ga];   // bin units used as pixels (no * stride), :189-192
-      const float4 b = make_float4(__fsub_rn(cx, d.x), __fsub_rn(cy, d.y), __fadd_rn(cx, d.z), __fadd_rn(cy, d.w));
-      raw[r] = b;
-      cls[r] = ws.t_arg[ga];
-      mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
-      key = ((unsigned long long)(~__float_as_uint(ws.t_m[ga])) << 32) | (unsigned int)r;
-    }
-    s_key[r] = key;
+  for (int r = threadIdx.x; r < K; r += kPrepThreads) {
+    const int a = list[r];
+    const size_t ga = (size_t)n * g.A + a;
+    const int l = level_of_anchor(g, a);
+    const int rel = a - g.start[l];
+    const int x = rel % g.w[l], y = rel / g.w[l];
+    const int s = g.stride[l];
+    // anchors handed to the distillation step were unmap()ed with fill 0
+    // (gfl_head.py:660): anchors outside pad_shape sit at the origin.
+    const bool valid = x < min((pad_w + s - 1) / s, g.w[l]) && y < min((pad_h + s - 1) / s, g.h[l]);
+    const float cx = valid ? (float)(x * s) : 0.f, cy = valid ? (float)(y * s) : 0.f;
+    const float4 d = ws.t_dist[ga];   // bin units used as pixels (no * stride), :189-192
+    const float4 b = make_float4(__fsub_rn(cx, d.x), __fsub_rn(cy, d.y), __fadd_rn(cx, d.z), __fadd_rn(cy, d.w));
+    boxes[r] = b;
+    cls[r] = ws.t_arg[ga];
+    score[r] = ws.t_m[ga];
+    mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
   }
+  // zero the predecessor words / map of the K rows in use
+  const int W = (K + 63) >> 6;
+  const int Wcap = nms_words(g.sel_cap), NZ = nms_nz_words(g.sel_cap);
+  unsigned long long* pred = ws.nms_mask + (size_t)n * g.sel_cap * Wcap;
+  unsigned long long* nz = ws.nms_nz + (size_t)n * g.sel_cap * NZ;
+  for (int i = threadIdx.x; i < K * W; i += kPrepThreads) pred[(size_t)(i / W) * Wcap + (i % W)] = 0ull;
+  for (int i = threadIdx.x; i < K * NZ; i += kPrepThreads) nz[i] = 0ull;
   mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
   __syncthreads();
-  // bitonic sort, ascending on key = descending score, ties by list position
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < P; i += kSortThreads) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = s_key[i], b = s_key[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) { s_key[i] = b; s_key[ixj] = a; }
-        }
-      }
-      __syncthreads();
-    }
-  }
   float maxc = s_max[0];
-  for (int w = 1; w < kSortThreads / 32; ++w) maxc = fmaxf(maxc, s_max[w]);
-  const float unit = __fadd_rn(maxc, 1.0f);
-  float4* sorted = ws.nms_box + (size_t)n * g.sel_cap;
-  int* order = ws.nms_order + (size_t)n * g.sel_cap;
-  const int NZ = nms_nz_words(g.sel_cap);
-  unsigned long long* nz = ws.nms_nz + (size_t)n * g.sel_cap * NZ;
-  for (int i = threadIdx.x; i < K; i += kSortThreads) {
-    const int r = (int)(unsigned int)(s_key[i] & 0xffffffffull);
-    const float4 b = raw[r];
+  for (int w = 1; w < kPrepThreads / 32; ++w) maxc = fmaxf(maxc, s_max[w]);
+  const float unit = __fadd_rn(maxc, 1.0f);   // boxes.max() + 1
+  for (int r = threadIdx.x; r < K; r += kPrepThreads) {   // each thread re-reads what it wrote
+    const float4 b = boxes[r];
     const float off = __fmul_rn((float)cls[r], unit);
-    sorted[i] = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
-    order[i] = r;
-    for (int w = 0; w < NZ; ++w) nz[(size_t)i * NZ + w] = 0ull;
+    boxes[r] = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
   }
 }
 
-// Predecessor bit matrix over score-ordered boxes: bit i of pred[j][rb] is set when box
-// rb*64+i, ranked before j, overlaps box j above the threshold.  A word is stored only when
-// it is non-zero, and then flagged in the per-box map nz[j] so the resolve pass touches nothing
-// else.  256 threads per 64x64 tile: four threads share a column, 16 rows each.
+// Predecessor bit matrix in list order: bit i of pred[j][i / 64] is set when box i is visited
+// before box j by the greedy pass and overlaps it above the threshold.  Overlaps are rare, so
+// bits are set with atomics and the per-box map nz[j] records which words are non-zero.
+// 256 threads per 64x64 tile (rb <= cb): four threads share a column, 16 rows each.
 constexpr int kMaskThreads = 256;
 
 __device__ __forceinline__ bool nms_overlaps(const float4& a, float area_a, const float4& b, float area_b,
@@ -120,9 +102,11 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace
   const int Wcap = nms_words(g.sel_cap);
   const int NZ = nms_nz_words(g.sel_cap);
   const float4* boxes = ws.nms_box + (size_t)n * g.sel_cap;
+  const float* score = ws.nms_score + (size_t)n * g.sel_cap;
   unsigned long long* pred = ws.nms_mask + (size_t)n * g.sel_cap * Wcap;
   unsigned long long* nz = ws.nms_nz + (size_t)n * g.sel_cap * NZ;
   __shared__ float4 s_row[2][64];
+  __shared__ float s_rscore[2][64];
   const int col = threadIdx.x >> 2, part = threadIdx.x & 3;
   const int ntile = W * (W + 1) / 2;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -132,36 +116,43 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace
   if (t >= ntile) return;
   int rb, cb;
   nms_tile_of(t, W, rb, cb);
-  float4 next_row = (threadIdx.x < 64 && rb * 64 + threadIdx.x < K) ? boxes[rb * 64 + threadIdx.x] : zero4;
+  const bool rthread = threadIdx.x < 64;
+  float4 next_row = (rthread && rb * 64 + threadIdx.x < K) ? boxes[rb * 64 + threadIdx.x] : zero4;
+  float next_rs = (rthread && rb * 64 + threadIdx.x < K) ? score[rb * 64 + threadIdx.x] : 0.f;
   float4 next_col = cb * 64 + col < K ? boxes[cb * 64 + col] : zero4;
+  float next_cs = cb * 64 + col < K ? score[cb * 64 + col] : 0.f;
   int buf = 0;
   while (t < ntile) {
-    if (threadIdx.x < 64) s_row[buf][threadIdx.x] = next_row;
+    if (rthread) { s_row[buf][threadIdx.x] = next_row; s_rscore[buf][threadIdx.x] = next_rs; }
     const float4 a = next_col;
+    const float sa = next_cs;
     const int crb = rb, ccb = cb;
     const int tn = t + gridDim.x;
     if (tn < ntile) {
       nms_tile_of(tn, W, rb, cb);
-      next_row = (threadIdx.x < 64 && rb * 64 + threadIdx.x < K) ? boxes[rb * 64 + threadIdx.x] : zero4;
+      next_row = (rthread && rb * 64 + threadIdx.x < K) ? boxes[rb * 64 + threadIdx.x] : zero4;
+      next_rs = (rthread && rb * 64 + threadIdx.x < K) ? score[rb * 64 + threadIdx.x] : 0.f;
       next_col = cb * 64 + col < K ? boxes[cb * 64 + col] : zero4;
+      next_cs = cb * 64 + col < K ? score[cb * 64 + col] : 0.f;
     }
     __syncthreads();
     const int j = ccb * 64 + col;
-    unsigned long long bits = 0ull;
     if (j < K) {
       const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
-      const int rmax = (crb == ccb) ? col : min(64, K - crb * 64);   // only boxes ranked before j
+      const int rmax = (crb == ccb) ? col : min(64, K - crb * 64);   // pairs i < j, once each
       for (int r = part * 16; r < part * 16 + 16 && r < rmax; ++r) {
         const float4 b = s_row[buf][r];
-        if (nms_overlaps(b, __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)), a, area_a, iou_thr))
-          bits |= 1ull << r;
+        if (!nms_overlaps(b, __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)), a, area_a, iou_thr)) continue;
+        const int i = crb * 64 + r;
+        const float si = s_rscore[buf][r];
+        if (si >= sa) {   // i < j in the list: i is visited first on equal scores too
+          atomicOr(pred + (size_t)j * Wcap + crb, 1ull << r);
+          atomicOr(nz + (size_t)j * NZ + (crb >> 6), 1ull << (crb & 63));
+        } else {
+          atomicOr(pred + (size_t)i * Wcap + ccb, 1ull << col);
+          atomicOr(nz + (size_t)i * NZ + (ccb >> 6), 1ull << (ccb & 63));
+        }
       }
-    }
-    bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
-    bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-    if (part == 0 && bits) {
-      pred[(size_t)j * Wcap + crb] = bits;
-      atomicOr(nz + (size_t)j * NZ + (crb >> 6), 1ull << (crb & 63));
     }
     buf ^= 1;
     t = tn;
@@ -227,7 +218,8 @@ __global__ void __launch_bounds__(kResThreads) nms_resolve_kernel(Geo g, Workspa
     for (int w = threadIdx.x; w < W; w += kResThreads) { kept[w] = kept_n[w]; dec[w] = dec_n[w]; }
     __syncthreads();
   }
-  // survivors in score order: exclusive prefix of the per-word popcounts
+  // survivors: count, unordered compact list (ordered by score later, off the critical path),
+  // and the marks the box sweep needs: flag bit 2 and the row of the distillation gradient
   if (threadIdx.x == 0) {
     int run = 0;
     for (int w = 0; w < W; ++w) {
@@ -238,42 +230,87 @@ __global__ void __launch_bounds__(kResThreads) nms_resolve_kernel(Geo g, Workspa
     keep_count[n] = run;
   }
   __syncthreads();
-  const int* order = ws.nms_order + (size_t)n * g.sel_cap;
   int32_t* out = keep + (size_t)n * g.sel_cap;
   const int32_t* list = box_inds + (size_t)n * g.sel_cap;
   for (int j = threadIdx.x; j < K; j += kResThreads) {
     const int wj = j >> 6;
     const unsigned long long kw = kept[wj];
     if (!(kw & (1ull << (j & 63)))) continue;
-    const int pos = order[j];
-    out[(int)dec[wj] + __popcll(kw & ((1ull << (j & 63)) - 1ull))] = pos;
-    // mark the survivor for the box sweep: flag bit 2 and the row of its distillation gradient
-    const int a = list[pos];
-    ws.kd_slot[(size_t)n * g.A + a] = pos;
+    out[(int)dec[wj] + __popcll(kw & ((1ull << (j & 63)) - 1ull))] = j;
+    const int a = list[j];
+    ws.kd_slot[(size_t)n * g.A + a] = j;
     sel_flags[(size_t)n * g.A + a] |= 4;
   }
 }
 
+// keep list in descending-score order (ties: earlier list position first), what batched_nms
+// returns.  One CTA per image, bitonic sort of the survivors in shared memory.
+constexpr int kSortThreads = 1024;
+
+__global__ void __launch_bounds__(kSortThreads) nms_order_kernel(Geo g, Workspace ws, int32_t* __restrict__ keep,
+                                                                 const int32_t* __restrict__ keep_count) {
+  extern __shared__ unsigned long long s_key[];
+  const int n = blockIdx.x;
+  const int M = keep_count[n];
+  if (M < 2) return;
+  int P = 1;
+  while (P < M) P <<= 1;
+  int32_t* out = keep + (size_t)n * g.sel_cap;
+  const float* score = ws.nms_score + (size_t)n * g.sel_cap;
+  for (int r = threadIdx.x; r < P; r += kSortThreads) {
+    unsigned long long key = ~0ull;
+    if (r < M) {
+      const int pos = out[r];
+      key = ((unsigned long long)(~__float_as_uint(score[pos])) << 32) | (unsigned int)pos;
+    }
+    s_key[r] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += kSortThreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s_key[i], b = s_key[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { s_key[i] = b; s_key[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = threadIdx.x; r < M; r += kSortThreads) out[r] = (int)(unsigned int)(s_key[r] & 0xffffffffull);
+}
+
 cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_inds, const int32_t* box_count,
                        const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count, uint8_t* sel_flags,
-                       cudaStream_t st) {
-  int P = 1;
-  while (P < g.sel_cap) P <<= 1;
-  const size_t sort_smem = sizeof(unsigned long long) * (size_t)P;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
+                       cudaStream_t st, cudaEvent_t prepped, cudaEvent_t resolved) {
+  ERD_LAUNCH(kKNmsSort, st, (nms_prep_kernel<<<g.n_img, kPrepThreads, 0, st>>>(g, ws, box_inds, box_count, pad_hw)));
+  if (prepped) {   // lets the caller start DRAM-heavy work only after the latency-bound gathers
+    cudaError_t e = cudaEventRecord(prepped, st);
+    if (e != cudaSuccess) return e;
   }
-  if (sort_smem > 200 * 1024) return cudaErrorInvalidValue;
-  ERD_LAUNCH(kKNmsSort, st,
-             (nms_sort_kernel<<<g.n_img, kSortThreads, sort_smem, st>>>(g, ws, box_inds, box_count, pad_hw)));
   ERD_LAUNCH(kKNmsMask, st,
              (nms_mask_kernel<<<dim3(48, g.n_img), kMaskThreads, 0, st>>>(g, ws, box_count, iou_thr)));
   const size_t res_smem = sizeof(unsigned long long) * 4 * (size_t)nms_words(g.sel_cap);
   ERD_LAUNCH(kKNmsScan, st,
              (nms_resolve_kernel<<<g.n_img, kResThreads, res_smem, st>>>(g, ws, box_inds, box_count, keep,
                                                                          keep_count, sel_flags)));
+  // everything the loss needs exists now; the ordering of the keep list is only an output
+  if (resolved) {
+    cudaError_t e = cudaEventRecord(resolved, st);
+    if (e != cudaSuccess) return e;
+  }
+  int P = 1;
+  while (P < g.sel_cap) P <<= 1;
+  const size_t sort_smem = sizeof(unsigned long long) * (size_t)P;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(nms_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  if (sort_smem > 200 * 1024) return cudaErrorInvalidValue;
+  ERD_LAUNCH(kKNmsOrder, st, (nms_order_kernel<<<g.n_img, kSortThreads, sort_smem, st>>>(g, ws, keep, keep_count)));
   return cudaGetLastError();
 }
 

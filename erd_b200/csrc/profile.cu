@@ -8,7 +8,7 @@
 namespace erd {
 
 static const char* kKernelNames[kNumKernels] = {"ers_scan", "ers_select", "atss_candidates", "atss_finalize",
-                                                "pos_prepass", "nms_sort", "nms_mask", "nms_resolve", "kd_rows", "upstream_check",
+                                                "pos_prepass", "nms_prep", "nms_mask", "nms_resolve", "nms_order", "kd_rows", "upstream_check",
                                                 "cls_sweep", "pos_grad", "box_early", "box_sweep", "finalize"};
 
 struct ProfState {
@@ -17,6 +17,7 @@ struct ProfState {
   unsigned long long launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[kNumKernels];
   std::vector<cudaEvent_t> pool;
+  cudaEvent_t ref = nullptr;   // erd_profile_mark
 };
 static ProfState g_prof;
 
@@ -61,6 +62,28 @@ int erd_profile_enable(unsigned int kernel_mask) {
 unsigned long long erd_launch_count(void) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
   return g_prof.launches;
+}
+
+// Timeline support: mark a reference point on `stream`; erd_profile_timeline then reports, for the
+// most recent profiled launch of each kernel, its start and end relative to that mark (ms).
+int erd_profile_mark(void* stream) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  if (!g_prof.ref) cudaEventCreate(&g_prof.ref);
+  return cudaEventRecord(g_prof.ref, (cudaStream_t)stream) == cudaSuccess ? ERD_OK : ERD_ERR_CUDA;
+}
+
+int erd_profile_timeline(float* start_ms, float* end_ms) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  if (!g_prof.ref) return ERD_ERR_NULL;
+  for (int k = 0; k < kNumKernels; ++k) {
+    start_ms[k] = end_ms[k] = -1.f;
+    if (g_prof.pending[k].empty()) continue;
+    auto& pr = g_prof.pending[k].back();
+    if (cudaEventSynchronize(pr.second) != cudaSuccess) continue;
+    cudaEventElapsedTime(&start_ms[k], g_prof.ref, pr.first);
+    cudaEventElapsedTime(&end_ms[k], g_prof.ref, pr.second);
+  }
+  return ERD_OK;
 }
 
 int erd_profile_num_kernels(void) { return kNumKernels; }

@@ -221,7 +221,8 @@ class ErdPath:
         N.check(self.lib.erd_loss_fwd_bwd(
             self._context(p.device), C.byref(p.shape), _ptrs(s_cls), _ptrs(s_box), _ptrs(t_cls), _ptrs(t_box), p.gt_boxes.data_ptr(),
             p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(), p.gt_inds.data_ptr(),
-            p.num_pos.data_ptr(), p.cls_count.data_ptr(), p.sel_flags.data_ptr(), p.box_inds.data_ptr(), p.keep.data_ptr(),
+            p.num_pos.data_ptr(), p.cls_count.data_ptr(), p.sel_flags.data_ptr(), p.box_inds.data_ptr(), p.box_count.data_ptr(),
+            p.keep.data_ptr(),
             p.keep_count.data_ptr(), p.avg.data_ptr(), float(dist_loss_weight),
             upstream.data_ptr() if upstream is not None else None, 1 if skip_if_unit else 0,
             losses.data_ptr(), _ptrs(g_cls), _ptrs(g_box), p.ws.data_ptr(), _stream()), 'erd_loss_fwd_bwd')

@@ -166,7 +166,7 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
                      const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
                      const int32_t* gt_inds, const int32_t* num_pos, const int32_t* cls_count,
                      const uint8_t* sel_flags,
-                     const int32_t* box_inds, const int32_t* keep, const int32_t* keep_count,
+                     const int32_t* box_inds, const int32_t* box_count, const int32_t* keep, const int32_t* keep_count,
                      const float* avg, float dist_loss_weight, const float* upstream,
                      int32_t skip_if_unit_upstream, float* losses, float* const* g_cls, float* const* g_box, void* ws,
                      void* stream);
@@ -208,6 +208,8 @@ unsigned long long erd_launch_count(void);   /* kernels launched by this library
 int erd_profile_num_kernels(void);
 const char* erd_profile_kernel_name(int id);
 int erd_profile_collect(float* total_ms, int* count);
+int erd_profile_mark(void* stream);                          /* reference point for the timeline */
+int erd_profile_timeline(float* start_ms, float* end_ms);    /* last launch of each kernel vs the mark */
 
 #ifdef __cplusplus
 }
