@@ -132,7 +132,7 @@ static MPtr5 mptr5(float* const* p) {
 
 struct ErdContext {
   cudaStream_t side[3];          // [0] assignment + positives prepass, [1] teacher NMS, [2] KD rows
-  cudaEvent_t fork, join[3], sel, early_done, nms_all;
+  cudaEvent_t fork, join[3], sel, sel_done, early_done, nms_all;
   bool nms_pending;              // join[1] recorded by erd_step_prepare, not yet waited on
 };
 
@@ -171,6 +171,7 @@ int erd_create(ErdContext** ctx) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sel, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->early_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->nms_all, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sel_done, cudaEventDisableTiming);
   c->nms_pending = false;
   if (e != cudaSuccess) {
     delete c;
@@ -190,6 +191,7 @@ int erd_destroy(ErdContext* c) {
   cudaEventDestroy(c->sel);
   cudaEventDestroy(c->early_done);
   cudaEventDestroy(c->nms_all);
+  cudaEventDestroy(c->sel_done);
   delete c;
   return ERD_OK;
 }
@@ -338,6 +340,7 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
     ls.early = ctx->side[0];
     ls.fork = ctx->fork;
     ls.early_done = ctx->early_done;
+    ls.sel_ready = ctx->nms_pending ? ctx->sel_done : nullptr;
     ls.nms_done = ctx->nms_pending ? ctx->join[1] : nullptr;
     ls.kd_done = ctx->nms_pending ? ctx->join[2] : nullptr;
     const bool had_nms = ctx->nms_pending;
@@ -358,43 +361,43 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   if (!ctx || !b) return fail(ERD_ERR_NULL, "erd_step_prepare: NULL ctx/buffers");
   cudaStream_t main = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-  if (ctx->nms_pending) {   // a previous prepare whose NMS nobody consumed: do not race its teacher cache
+  if (ctx->nms_pending) {   // a previous prepare nobody consumed: do not race its teacher cache
     e = cudaStreamWaitEvent(main, ctx->nms_all, 0);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ctx->join[2], 0);
     ctx->nms_pending = false;
   }
-  // stream layout: main = teacher pass (ERS scan + select); side[0] = ATSS + positives prepass
-  // (joined back before returning, the caller all-reduces avg next); side[1] = teacher NMS and
-  // side[2] = distillation rows of every box candidate, both forked after the selection and
-  // joined inside erd_loss_fwd_bwd in front of the late box sweep.
+  // Stream layout.  The caller's stream only carries what the avg-factor all-reduce needs
+  // (ATSS + positives prepass), so the caller can all-reduce and start the QFL sweep at once.
+  // The teacher side runs beside it: side[1] = ERS scan + select (sel_done) -> NMS (join[1] when
+  // the survivors are marked, nms_all when the keep list is ordered); side[2] = distillation
+  // rows of every box candidate, started behind the NMS's own gathers (join[2]).
+  // erd_loss_fwd_bwd(ctx, ...) joins them exactly where their results are consumed.
   if (e == cudaSuccess) e = cudaEventRecord(ctx->fork, main);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[0], ctx->fork, 0);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[1], ctx->fork, 0);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[2], ctx->fork, 0);
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork");
-  int rc = erd_atss_assign(shape, gt_boxes, gt_labels, gt_offsets, pad_hw, b->gt_inds, b->num_pos, wsp, ctx->side[0]);
-  if (!rc)
-    rc = erd_avg_factors(shape, s_cls, s_box, gt_boxes, gt_labels, gt_offsets, b->gt_inds, b->num_pos, b->avg, wsp,
-                         ctx->side[0]);
-  if (!rc && !(flags & ERD_PREPARE_ERS_DONE))
+  int rc = 0;
+  if (!(flags & ERD_PREPARE_ERS_DONE))
     rc = erd_ers_select(shape, t_cls, t_box, b->cls_inds, b->cls_count, b->box_inds, b->box_count, b->thr,
-                        b->sel_flags, wsp, main);
+                        b->sel_flags, wsp, ctx->side[1]);
   if (rc) return rc;
-  e = cudaEventRecord(ctx->sel, main);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[1], ctx->sel, 0);
-  if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork nms");
-  if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork kd");
+  e = cudaEventRecord(ctx->sel_done, ctx->side[1]);
+  if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare sel");
   if (!b->box_inds || !b->box_count || !pad_hw || !b->keep || !b->keep_count || !b->sel_flags || !wsp)
     return fail(ERD_ERR_NULL, "erd_step_prepare: NULL NMS buffer");
   rc = nms_on_side_stream(ctx, shape, b, pad_hw, iou_thr, wsp);
   // the distillation rows (random DRAM gathers) start once the NMS has finished its own gathers
-  // (ctx->sel is re-recorded behind nms_prep), so they do not stretch the latency-bound chain
+  // (ctx->sel is recorded behind nms_prep), so they do not stretch the latency-bound chain
   if (!rc && cudaStreamWaitEvent(ctx->side[2], ctx->sel, 0) != cudaSuccess) rc = fail(ERD_ERR_CUDA, "fork kd");
   if (!rc) rc = erd_kd_rows(shape, s_cls, s_box, t_box, b->box_inds, b->box_count, wsp, ctx->side[2]);
   if (rc) return rc;
   e = cudaEventRecord(ctx->join[2], ctx->side[2]);
   if (e == cudaSuccess) ctx->nms_pending = true;
-  if (e == cudaSuccess) e = cudaEventRecord(ctx->join[0], ctx->side[0]);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ctx->join[0], 0);
-  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_step_prepare join");
+  if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare join");
+  rc = erd_atss_assign(shape, gt_boxes, gt_labels, gt_offsets, pad_hw, b->gt_inds, b->num_pos, wsp, main);
+  if (!rc)
+    rc = erd_avg_factors(shape, s_cls, s_box, gt_boxes, gt_labels, gt_offsets, b->gt_inds, b->num_pos, b->avg, wsp, main);
+  return rc;
 }
 
 }  // extern "C"

@@ -146,7 +146,7 @@ struct Quad {
 
 // ---------------------------------------------------------------- launch accounting (profile.cu)
 enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan, kKNmsOrder,
-                kKKdRows, kKUpCheck, kKLossMain, kKPosGrad, kKBoxEarly, kKBoxSweep, kKFinalize, kNumKernels };
+                kKKdRows, kKUpCheck, kKLossMain, kKClsOld, kKPosGrad, kKBoxEarly, kKBoxSweep, kKFinalize, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 // ERD_LAUNCH(id, stream, kernel<<<...>>>(...)) counts the launch and, when profiling is on,
@@ -199,6 +199,7 @@ cudaError_t launch_kd_rows(const Geo& g, const Workspace& ws, const Ptr5& s_cls,
 struct LossStreams {
   cudaStream_t early;                 // helper stream for the NMS-independent box sectors
   cudaEvent_t fork, early_done;
+  cudaEvent_t sel_ready;              // may be null: ERS selection already ordered before the caller's stream
   cudaEvent_t nms_done;               // may be null: NMS already ordered before the caller's stream
   cudaEvent_t kd_done;                // may be null: likewise for the distillation rows
 };

@@ -329,11 +329,11 @@ __device__ __forceinline__ void cls_tile(const Geo& g, const Workspace& ws, cons
   out_loss += loss_cls;
 }
 
-__global__ void __launch_bounds__(kTileThreads) cls_sweep_kernel(Geo g, Workspace ws, LossArgs A) {
+__global__ void __launch_bounds__(kTileThreads) cls_sweep_kernel(Geo g, Workspace ws, LossArgs A, int part_offset) {
   if (A.skip_flag && *A.skip_flag == 0u) return;
   const int n = blockIdx.y;
   const int tile = blockIdx.x;
-  const int part = blockIdx.z;
+  const int part = blockIdx.z + part_offset;
   const int l = level_of_tile(g, tile);
   const int hw0 = (tile - g.tile_start[l]) * kTile;
   float out = 0.f;
@@ -631,9 +631,12 @@ cudaError_t launch_kd_rows(const Geo& g, const Workspace& ws, const Ptr5& s_cls,
   return cudaGetLastError();
 }
 
-// Sequence on the caller's stream `st`; with helper streams (erd_step_prepare's context) the
-// box gradients of every sector that cannot depend on the NMS are written on `early` while the
-// NMS is still running on its own stream, and `st` joins both before the late box launch.
+// Sequence on the caller's stream `st`.  With helper streams (erd_step_prepare's context):
+//   st    : QFL sweep (needs only assignment + avg factors) -> wait selection -> class-response
+//           sweep -> wait early/NMS/KD -> late box kernel -> finalize
+//   early : wait selection -> positives' rows -> box sectors that cannot depend on the NMS
+// so the bandwidth-bound sweeps overlap the latency-bound ERS / NMS chain instead of queueing
+// behind it.
 cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, const LossStreams* ls) {
   const int total = 3 * kLevels + 2 * g.n_img;
   cudaError_t e = cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * total, st);
@@ -652,21 +655,25 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
   p.upstream = a.upstream;
   p.skip_flag = a.skip_flag;
   const dim3 box_grid(g.tile_start[kLevels], g.n_img, 4);
-  if (ls) {   // fork: early box sectors beside the class sweep
+  const int parts_old = (g.ori + kSweepCh - 1) / kSweepCh, parts_new = (g.cn + kSweepCh - 1) / kSweepCh;
+  const dim3 tile_grid_new(g.tile_start[kLevels], g.n_img, parts_new), tile_grid_old(g.tile_start[kLevels], g.n_img, parts_old);
+  if (ls) {
     e = cudaEventRecord(ls->fork, st);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ls->early, ls->fork, 0);
+    if (e == cudaSuccess && ls->sel_ready) e = cudaStreamWaitEvent(ls->early, ls->sel_ready, 0);
     if (e != cudaSuccess) return e;
-    // the positives' gradient rows are consumed by the box kernels only: keep them off the
-    // class sweep's stream
     ERD_LAUNCH(kKPosGrad, ls->early,
                (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, ls->early>>>(g, ws, p)));
     ERD_LAUNCH(kKBoxEarly, ls->early, (box_sweep_kernel<1><<<box_grid, kTileThreads, 0, ls->early>>>(g, ws, a)));
     e = cudaEventRecord(ls->early_done, ls->early);
     if (e != cudaSuccess) return e;
   }
-  const int parts = (g.ori + kSweepCh - 1) / kSweepCh + (g.cn + kSweepCh - 1) / kSweepCh;
-  ERD_LAUNCH(kKLossMain, st,
-             (cls_sweep_kernel<<<dim3(g.tile_start[kLevels], g.n_img, parts), kTileThreads, 0, st>>>(g, ws, a)));
+  ERD_LAUNCH(kKLossMain, st, (cls_sweep_kernel<<<tile_grid_new, kTileThreads, 0, st>>>(g, ws, a, parts_old)));
+  if (ls && ls->sel_ready) {
+    e = cudaStreamWaitEvent(st, ls->sel_ready, 0);
+    if (e != cudaSuccess) return e;
+  }
+  ERD_LAUNCH(kKClsOld, st, (cls_sweep_kernel<<<tile_grid_old, kTileThreads, 0, st>>>(g, ws, a, 0)));
   if (ls) {
     e = cudaStreamWaitEvent(st, ls->early_done, 0);
     if (e == cudaSuccess && ls->nms_done) e = cudaStreamWaitEvent(st, ls->nms_done, 0);

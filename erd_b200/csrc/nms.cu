@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace
   unsigned long long* pred = ws.nms_mask + (size_t)n * g.sel_cap * Wcap;
   unsigned long long* nz = ws.nms_nz + (size_t)n * g.sel_cap * NZ;
   __shared__ float4 s_row[2][64];
+  __shared__ float2 s_rx[2][64];   // (x1, x2) of the row boxes: most pairs are rejected on x alone
+  __shared__ float s_rarea[2][64];
   __shared__ float s_rscore[2][64];
   const int col = threadIdx.x >> 2, part = threadIdx.x & 3;
   const int ntile = W * (W + 1) / 2;
@@ -123,7 +125,12 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace
   float next_cs = cb * 64 + col < K ? score[cb * 64 + col] : 0.f;
   int buf = 0;
   while (t < ntile) {
-    if (rthread) { s_row[buf][threadIdx.x] = next_row; s_rscore[buf][threadIdx.x] = next_rs; }
+    if (rthread) {
+      s_row[buf][threadIdx.x] = next_row;
+      s_rx[buf][threadIdx.x] = make_float2(next_row.x, next_row.z);
+      s_rarea[buf][threadIdx.x] = __fmul_rn(__fsub_rn(next_row.z, next_row.x), __fsub_rn(next_row.w, next_row.y));
+      s_rscore[buf][threadIdx.x] = next_rs;
+    }
     const float4 a = next_col;
     const float sa = next_cs;
     const int crb = rb, ccb = cb;
@@ -140,9 +147,14 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace
     if (j < K) {
       const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
       const int rmax = (crb == ccb) ? col : min(64, K - crb * 64);   // pairs i < j, once each
-      for (int r = part * 16; r < part * 16 + 16 && r < rmax; ++r) {
+      const bool neg_thr = 0.f > iou_thr;   // then even disjoint boxes "overlap": no shortcut
+#pragma unroll 4
+      for (int r = part * 16; r < part * 16 + 16; ++r) {
+        if (r >= rmax) break;
+        const float2 bx = s_rx[buf][r];
+        if (!neg_thr && !(fminf(a.z, bx.y) > fmaxf(a.x, bx.x))) continue;   // w <= 0: ovr is 0 (or NaN)
         const float4 b = s_row[buf][r];
-        if (!nms_overlaps(b, __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)), a, area_a, iou_thr)) continue;
+        if (!nms_overlaps(b, s_rarea[buf][r], a, area_a, iou_thr)) continue;
         const int i = crb * 64 + r;
         const float si = s_rscore[buf][r];
         if (si >= sa) {   // i < j in the list: i is visited first on equal scores too
@@ -187,10 +199,72 @@ __global__ void __launch_bounds__(kResThreads) nms_resolve_kernel(Geo g, Workspa
   const unsigned long long* nz = ws.nms_nz + (size_t)n * g.sel_cap * NZ;
   for (int w = threadIdx.x; w < 4 * Wcap; w += kResThreads) s_state[w] = 0ull;
   __syncthreads();
+  // Each thread owns boxes j = tid, tid + 512, ...; the (few) non-zero predecessor words of its
+  // first kOwn boxes are fetched once into registers, so a round costs shared-memory traffic
+  // only.  Boxes beyond kOwn per thread or with more than kCache non-zero words re-read global.
+  constexpr int kOwn = 3, kCache = 4;
+  unsigned long long cbits[kOwn][kCache];
+  int cword[kOwn][kCache];
+  int cnum[kOwn];
+#pragma unroll
+  for (int o = 0; o < kOwn; ++o) {
+    cnum[o] = 0;
+    const int j = threadIdx.x + o * kResThreads;
+    if (j >= K) continue;
+    int cnt = 0;
+    for (int zw = 0; zw < NZ; ++zw) {
+      unsigned long long m = nz[(size_t)j * NZ + zw];
+      while (m) {
+        const int w = (zw << 6) + __ffsll((long long)m) - 1;
+        m &= m - 1ull;
+        if (cnt < kCache) {
+          cword[o][cnt] = w;
+          cbits[o][cnt] = pred[(size_t)j * Wcap + w];
+        }
+        ++cnt;
+      }
+    }
+    cnum[o] = cnt;   // > kCache: not fully cached
+  }
   int pending = K > 0;
   while (pending) {
     int undecided = 0;
-    for (int j = threadIdx.x; j < K; j += kResThreads) {
+    bool now_dec[kOwn], now_kept[kOwn];
+#pragma unroll
+    for (int o = 0; o < kOwn; ++o) {
+      now_dec[o] = now_kept[o] = false;
+      const int j = threadIdx.x + o * kResThreads;
+      if (j >= K || cnum[o] > kCache) continue;
+      const int wj = j >> 6;
+      const unsigned long long bit = 1ull << (j & 63);
+      if (dec[wj] & bit) continue;
+      bool sup = false, wait = false;
+#pragma unroll
+      for (int c = 0; c < kCache; ++c) {
+        if (c >= cnum[o]) break;
+        const unsigned long long pr = cbits[o][c];
+        if (pr & kept[cword[o][c]]) sup = true;
+        if (pr & ~dec[cword[o][c]]) wait = true;
+      }
+      now_dec[o] = sup || !wait;
+      now_kept[o] = !sup && !wait;
+      if (wait && !sup) undecided = 1;
+    }
+    // a warp owns the 32 consecutive boxes of each of its slots = one 32-bit half of a state
+    // word: publish the round's decisions with a ballot and a plain store, no atomics
+#pragma unroll
+    for (int o = 0; o < kOwn; ++o) {
+      const unsigned kd_bits = __ballot_sync(0xffffffffu, now_dec[o]);
+      const unsigned kk_bits = __ballot_sync(0xffffffffu, now_kept[o]);
+      const int half = (threadIdx.x + o * kResThreads) >> 5;   // warp-uniform
+      if ((threadIdx.x & 31) == 0 && kd_bits) {
+        reinterpret_cast<unsigned*>(dec_n)[half] |= kd_bits;
+        reinterpret_cast<unsigned*>(kept_n)[half] |= kk_bits;
+      }
+    }
+    for (int j = threadIdx.x; j < K; j += kResThreads) {   // uncached boxes
+      const int o = j / kResThreads;
+      if (o < kOwn && cnum[o < kOwn ? o : 0] <= kCache) continue;
       const int wj = j >> 6;
       const unsigned long long bit = 1ull << (j & 63);
       if (dec[wj] & bit) continue;
@@ -205,11 +279,12 @@ __global__ void __launch_bounds__(kResThreads) nms_resolve_kernel(Geo g, Workspa
           if (pr & ~dec[w]) wait = true;
         }
       }
+      const unsigned b32 = 1u << (j & 31);
       if (sup) {
-        atomicOr(dec_n + wj, bit);
+        atomicOr(reinterpret_cast<unsigned*>(dec_n) + (j >> 5), b32);
       } else if (!wait) {
-        atomicOr(kept_n + wj, bit);
-        atomicOr(dec_n + wj, bit);
+        atomicOr(reinterpret_cast<unsigned*>(kept_n) + (j >> 5), b32);
+        atomicOr(reinterpret_cast<unsigned*>(dec_n) + (j >> 5), b32);
       } else {
         undecided = 1;
       }
@@ -291,7 +366,7 @@ cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_ind
     if (e != cudaSuccess) return e;
   }
   ERD_LAUNCH(kKNmsMask, st,
-             (nms_mask_kernel<<<dim3(48, g.n_img), kMaskThreads, 0, st>>>(g, ws, box_count, iou_thr)));
+             (nms_mask_kernel<<<dim3(256, g.n_img), kMaskThreads, 0, st>>>(g, ws, box_count, iou_thr)));
   const size_t res_smem = sizeof(unsigned long long) * 4 * (size_t)nms_words(g.sel_cap);
   ERD_LAUNCH(kKNmsScan, st,
              (nms_resolve_kernel<<<g.n_img, kResThreads, res_smem, st>>>(g, ws, box_inds, box_count, keep,

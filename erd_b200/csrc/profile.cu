@@ -9,7 +9,7 @@ namespace erd {
 
 static const char* kKernelNames[kNumKernels] = {"ers_scan", "ers_select", "atss_candidates", "atss_finalize",
                                                 "pos_prepass", "nms_prep", "nms_mask", "nms_resolve", "nms_order", "kd_rows", "upstream_check",
-                                                "cls_sweep", "pos_grad", "box_early", "box_sweep", "finalize"};
+                                                "qfl_sweep", "cls_old_sweep", "pos_grad", "box_early", "box_sweep", "finalize"};
 
 struct ProfState {
   std::mutex mu;

@@ -173,11 +173,13 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
 
 /* One training-step worth of the path in two calls around the caller's all-reduce:
  * erd_step_prepare = erd_ers_select + erd_atss_assign + erd_avg_factors + erd_teacher_nms +
- * erd_kd_rows
- * (forked over the context's helper streams; assignment and avg factors are joined back into
- * `stream`, the NMS is joined by erd_loss_fwd_bwd(ctx, ...));
- * erd_step_loss = erd_loss_fwd_bwd.  Replaces GFLIncrementERD.loss
- * (detectors/gfl_increment_erd.py:202-220) minus the conv stacks. */
+ * erd_kd_rows, erd_step_loss = erd_loss_fwd_bwd(ctx, ...).  Replaces GFLIncrementERD.loss
+ * (detectors/gfl_increment_erd.py:202-220) minus the conv stacks.
+ * Only assignment and avg factors are ordered on `stream` when erd_step_prepare returns (that is
+ * what the all-reduce needs); the teacher side (selection, NMS, distillation rows) keeps running
+ * on the context's helper streams and is joined by erd_loss_fwd_bwd(ctx, ...) where its results
+ * are consumed.  A caller that reads ERS / NMS outputs itself must synchronise the device (or
+ * call erd_loss_fwd_bwd first). */
 typedef struct ErdStepBuffers {
   int32_t* cls_inds;
   int32_t* cls_count;
