@@ -147,6 +147,11 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
+    if os.environ.get('ERD_BENCH_DEBUG'):
+        import faulthandler
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        _fh = open(os.path.join(ROOT, 'gpurun_out', f"hang_rank{os.environ.get('RANK', 0)}.txt"), 'w')
+        faulthandler.dump_traceback_later(int(os.environ['ERD_BENCH_DEBUG']), exit=True, file=_fh)
     rank = int(os.environ.get('RANK', 0))
     local = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -341,7 +346,14 @@ def run_ours(args):
                                                               'torch-CPU oracle port of the reference'}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL teardown with a captured graph alive can block; everything is printed, so leave
+        # through a barrier and a hard exit instead of destroy_process_group()
+        sys.stdout.flush()
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os._exit(0)
 
 
 if __name__ == '__main__':
