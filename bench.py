@@ -32,10 +32,13 @@ IMG_HW = (800, 1333)
 IMGS_PER_GPU = 16
 ORI, NUM_CLASSES, REG_MAX = 40, 80, 16
 # compulsory fp32 traffic per anchor, fwd+bwd, 40+40 split
-# per dense kernel: ers_scan reads teacher cls+box; cls_sweep reads student cls + teacher cls and
-# writes grad cls; box_sweep writes grad box (student box is only touched at positives / NMS rows)
-BYTES_PER_ANCHOR = {'path': 1616, 'ers_scan': 4 * (ORI + 68), 'cls_sweep': 4 * (NUM_CLASSES + ORI + NUM_CLASSES),
-                    'box_sweep': 4 * 68}
+# per dense kernel: ers_scan reads teacher cls + box; qfl_sweep reads the student's
+# new-class logits and writes their gradients; cls_old_sweep reads student + teacher old-class logits and
+# writes the old-class gradients; box_early writes the box gradients (student box logits are only touched
+# at positives / ERS rows, by the small gather kernels)
+CN = NUM_CLASSES - ORI
+BYTES_PER_ANCHOR = {'path': 1616, 'ers_scan': 4 * (ORI + 68), 'qfl_sweep': 4 * (CN + CN),
+                    'cls_old_sweep': 4 * (ORI + ORI + ORI), 'box_early': 4 * 68}
 
 
 def parse():
@@ -194,7 +197,7 @@ def run_ours(args):
 
     nk = lib.erd_profile_num_kernels()
     names = [lib.erd_profile_kernel_name(i).decode() for i in range(nk)]
-    dense = [k for k in ('ers_scan', 'cls_sweep', 'box_sweep') if k in names]
+    dense = [k for k in ('ers_scan', 'qfl_sweep', 'cls_old_sweep', 'box_early') if k in names]
 
     def collect():
         tot, cnt = (C.c_float * nk)(), (C.c_int * nk)()
