@@ -22,6 +22,12 @@ namespace erd {
 // independent of register pressure (a register-staged version of this pass sat at 2.7 TB/s,
 // latency-bound).  Bulk copies need 16 B aligned rows (hw % 4 == 0); tiles of the other levels
 // (a few % of the anchors) are filled with ordinary loads.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
@@ -145,6 +151,214 @@ __global__ void __launch_bounds__(T) ers_scan_kernel(Geo g, Workspace ws, Ptr5 t
     for (int w = 0; w < T / 32; ++w) sm += s_red[w][threadIdx.x];
     ws.ers_part[((size_t)n * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = sm;
   }
+}
+
+// ----------------------------------------------------------------------------- pass 1, pipelined
+// Persistent, warp-specialised form of the same pass: one CTA per SM; warp 0 is the producer
+// (bulk copies of 17-row x 256-anchor stages into a ring of shared-memory slots, full/empty
+// mbarriers per slot), warps 1..8 are consumers (one anchor per thread).  The producer runs
+// ahead by the whole ring (~200 KB of requests in flight per SM) no matter what the consumers
+// are doing, so the pass is bound by HBM, not by load latency.
+constexpr int kPipeT = 256;                 // anchors per tile = consumer threads
+constexpr int kPipeRows = kBins;            // rows per stage
+constexpr int kPipeThreads = kPipeT + 32;
+constexpr int kPipeStageFloats = kPipeRows * kPipeT;
+
+struct PipeTile {
+  int n, l, hw0, cnt, part;
+};
+
+__device__ __forceinline__ PipeTile pipe_tile(const Geo& g, int t, int tiles_per_img) {
+  PipeTile p;
+  p.n = t / tiles_per_img;
+  int tile = t - p.n * tiles_per_img;
+  p.part = tile;
+  p.l = 0;
+#pragma unroll
+  for (int i = 0; i < kLevels - 1; ++i) {
+    const int tl = (g.hw[i] + kPipeT - 1) / kPipeT;
+    if (p.l == i && tile >= tl) { tile -= tl; ++p.l; }
+  }
+  p.hw0 = tile * kPipeT;
+  p.cnt = min(kPipeT, g.hw[p.l] - p.hw0);
+  return p;
+}
+
+__global__ void __launch_bounds__(kPipeThreads, 2) ers_scan_pipe_kernel(Geo g, Workspace ws, Ptr5 t_cls, Ptr5 t_box,
+                                                                        int tiles_per_img, int total_tiles, int stages) {
+  extern __shared__ __align__(128) float s_ring[];   // [stages][kPipeRows][kPipeT]
+  __shared__ __align__(8) unsigned long long s_full[16], s_empty[16];
+  __shared__ double s_red[kPipeT / 32][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ori = g.ori;
+  const int cls_chunks = (ori + kPipeRows - 1) / kPipeRows;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < stages; ++b) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_full[b])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_empty[b])), "r"(kPipeT / 32));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int slot = 0;
+  uint32_t phase = 0;   // parity of the current pass over the ring
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const PipeTile p = pipe_tile(g, t, tiles_per_img);
+      const int HW = g.hw[p.l];
+      if (!g.vec[p.l]) continue;   // rows not 16 B aligned: the consumers load those tiles themselves
+      const uint32_t row_bytes = (uint32_t)p.cnt * 4u;
+      for (int ch = 0; ch < cls_chunks + 4; ++ch) {
+        const bool is_cls = ch < cls_chunks;
+        const int r0 = is_cls ? ch * kPipeRows : 0;
+        const int rows = is_cls ? min(kPipeRows, ori - r0) : kPipeRows;
+        const float* src = is_cls ? t_cls.p[p.l] + ((size_t)p.n * ori + r0) * HW + p.hw0
+                                  : t_box.p[p.l] + ((size_t)p.n * kBoxCh + (ch - cls_chunks) * kBins) * HW + p.hw0;
+        float* dst = s_ring + (size_t)slot * kPipeStageFloats;
+        mbar_wait(&s_empty[slot], phase ^ 1u);   // slot free (first pass: passes immediately)
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_full[slot])),
+                       "r"(row_bytes * (uint32_t)rows) : "memory");
+        __syncwarp();
+        if (lane < rows)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(dst + (size_t)lane * kPipeT)), "l"(src + (size_t)lane * HW), "r"(row_bytes),
+                         "r"(smem_u32(&s_full[slot])) : "memory");
+        if (++slot == stages) { slot = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- consumers
+  const int tid = threadIdx.x - 32;     // 0 .. kPipeT-1: anchor within the tile
+  const int cwarp = tid >> 5;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const PipeTile p = pipe_tile(g, t, tiles_per_img);
+    const bool on = tid < p.cnt;
+    float best = -INFINITY, u = -INFINITY;
+    int arg = 0;
+    float dist[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!g.vec[p.l]) {
+      // unaligned level (a few % of the anchors): every consumer fetches its own column
+      if (on) {
+        const int HW = g.hw[p.l];
+        const float* cb = t_cls.p[p.l] + (size_t)p.n * ori * HW + p.hw0 + tid;
+#pragma unroll 8
+        for (int c = 0; c < ori; ++c) {
+          const float v = __ldg(cb + (size_t)c * HW);
+          if (v > best) { best = v; arg = c; }
+        }
+        const float* bb = t_box.p[p.l] + (size_t)p.n * kBoxCh * HW + p.hw0 + tid;
+#pragma unroll
+        for (int sd = 0; sd < 4; ++sd) {
+          float z[kBins];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < kBins; ++j) {
+            z[j] = __ldg(bb + (size_t)(sd * kBins + j) * HW);
+            mx = fmaxf(mx, z[j]);
+          }
+          float sum = 0.f, num = 0.f;
+#pragma unroll
+          for (int j = 0; j < kBins; ++j) {
+            const float e = __expf(z[j] - mx);
+            sum += e;
+            num = fmaf((float)j, e, num);
+          }
+          dist[sd] = __fdiv_rn(num, sum);
+          u = fmaxf(u, mx);
+        }
+      }
+    }
+    for (int ch = 0; g.vec[p.l] && ch < cls_chunks + 4; ++ch) {
+      const float* col = s_ring + (size_t)slot * kPipeStageFloats + tid;
+      mbar_wait(&s_full[slot], phase);
+      // rows of threads beyond the tile's last anchor hold stale but finite data: computing on
+      // them unconditionally keeps the loops free of predicates (their results are discarded)
+      if (ch < cls_chunks) {
+        const int r0 = ch * kPipeRows;
+        if (r0 + kPipeRows <= ori) {
+#pragma unroll
+          for (int r = 0; r < kPipeRows; ++r) {
+            const float v = col[r * kPipeT];
+            if (v > best) { best = v; arg = r0 + r; }
+          }
+        } else {
+          for (int r = 0; r < ori - r0; ++r) {
+            const float v = col[r * kPipeT];
+            if (v > best) { best = v; arg = r0 + r; }
+          }
+        }
+      } else {
+        float z[kBins];
+#pragma unroll
+        for (int j = 0; j < kBins; ++j) z[j] = col[j * kPipeT];
+        float mx = z[0];
+#pragma unroll
+        for (int j = 1; j < kBins; ++j) mx = fmaxf(mx, z[j]);
+        const float kL2e = 1.4426950408889634f;
+        const float bias = -mx * kL2e;
+        float sum = 0.f, num = 0.f;
+#pragma unroll
+        for (int j = 0; j < kBins; ++j) {
+          const float e = ex2_approx(fmaf(z[j], kL2e, bias));   // exp(z - mx), 2 ulp
+          sum += e;
+          num = fmaf((float)j, e, num);
+        }
+        dist[ch - cls_chunks] = __fdiv_rn(num, sum);
+        u = fmaxf(u, mx);
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[slot])) : "memory");
+      if (++slot == stages) { slot = 0; phase ^= 1u; }
+    }
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (on) {
+      const float m = sigmoid_ref(best);
+      const size_t a = (size_t)p.n * g.A + g.start[p.l] + p.hw0 + tid;
+      ws.t_m[a] = m;
+      ws.t_arg[a] = arg;
+      ws.t_u[a] = u;
+      ws.t_dist[a] = make_float4(dist[0], dist[1], dist[2], dist[3]);
+      acc[0] = (double)m;
+      acc[1] = (double)m * (double)m;
+      acc[2] = (double)u;
+      acc[3] = (double)u * (double)u;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = warp_sum(acc[i]);
+    asm volatile("bar.sync 1, %0;" ::"n"(kPipeT));   // consumers only: s_red free again
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_red[cwarp][i] = acc[i];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kPipeT));
+    if (tid < 4) {
+      double sm = 0.0;
+      for (int w = 0; w < kPipeT / 32; ++w) sm += s_red[w][tid];
+      ws.ers_part[((size_t)p.n * tiles_per_img + p.part) * 4 + tid] = sm;
+    }
+  }
+}
+
+static int launch_scan_pipe(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box, cudaStream_t st) {
+  int tiles = 0;
+  for (int l = 0; l < kLevels; ++l) tiles += (g.hw[l] + kPipeT - 1) / kPipeT;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(ers_scan_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * kPipeStageFloats * 4);
+  }
+  const int stages = 6;    // 2 CTAs/SM x 6 x 17 KB = 204 KB of copies in flight per SM
+  const int total = tiles * g.n_img;
+  const int grid = total < 2 * sms ? total : 2 * sms;
+  ERD_LAUNCH(kKErsScan, st,
+             (ers_scan_pipe_kernel<<<grid, kPipeThreads, (size_t)stages * kPipeStageFloats * 4, st>>>(
+                 g, ws, t_cls, t_box, tiles, total, stages)));
+  return tiles;
 }
 
 template <int T>
@@ -289,19 +503,25 @@ __global__ void __launch_bounds__(kSelThreads) ers_select_kernel(Geo g, Workspac
 cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box, int32_t* cls_inds,
                        int32_t* cls_count, int32_t* box_inds, int32_t* box_count, float* thr, uint8_t* sel_flags,
                        cudaStream_t st) {
-  // anchors per CTA: the largest tile that still lets two CTAs share an SM's shared memory
-  const size_t row = (size_t)(g.ori + kBoxCh) * sizeof(float);
-  static int forced = -1;   // ERD_SCAN_TILE=64|128|256 overrides (tuning)
-  if (forced < 0) {
+  // ERD_SCAN_MODE=staged selects the non-persistent kernel (ERD_SCAN_TILE=64|128|256); default: pipelined
+  static int mode = -1, forced = 0;
+  if (mode < 0) {
+    const char* m = getenv("ERD_SCAN_MODE");
+    mode = (m && m[0] == 's') ? 1 : 0;
     const char* e = getenv("ERD_SCAN_TILE");
     forced = e ? atoi(e) : 0;
   }
-  int T = forced ? forced : (row * 256 <= 110 * 1024 ? 256 : row * 128 <= 110 * 1024 ? 128 : 64);
-  if (row * T > 220 * 1024) return cudaErrorInvalidValue;
   int tiles;
-  if (T == 256) tiles = launch_scan<256>(g, ws, t_cls, t_box, st);
-  else if (T == 128) tiles = launch_scan<128>(g, ws, t_cls, t_box, st);
-  else tiles = launch_scan<64>(g, ws, t_cls, t_box, st);
+  if (mode == 0) {
+    tiles = launch_scan_pipe(g, ws, t_cls, t_box, st);
+  } else {
+    const size_t row = (size_t)(g.ori + kBoxCh) * sizeof(float);
+    const int T = forced ? forced : (row * 256 <= 110 * 1024 ? 256 : row * 128 <= 110 * 1024 ? 128 : 64);
+    if (row * T > 220 * 1024) return cudaErrorInvalidValue;
+    if (T == 256) tiles = launch_scan<256>(g, ws, t_cls, t_box, st);
+    else if (T == 128) tiles = launch_scan<128>(g, ws, t_cls, t_box, st);
+    else tiles = launch_scan<64>(g, ws, t_cls, t_box, st);
+  }
   ERD_LAUNCH(kKErsSelect, st,
              (ers_select_kernel<<<dim3((g.A + kSelChunk - 1) / kSelChunk, g.n_img), kSelThreads, 0, st>>>(
                  g, ws, tiles, cls_inds, cls_count, box_inds,
