@@ -44,6 +44,7 @@ SIGNATURES = {
     'erd_abi_version': [],
     'erd_last_error': [],
     'erd_sizes': [_SH, C.POINTER(ErdSizes)],
+    'erd_workspace_init': [_SH, _P, _P],
     'erd_create': [C.POINTER(_P)],
     'erd_destroy': [_P],
     'erd_ers_select': [_SH, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -80,9 +80,11 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->t_dist = (float4*)take(NA * 16);
   ws->ers_part = (double*)take((size_t)g.n_img * (g.A / 64 + kLevels) * 4 * 8);
   ws->atss_key = (unsigned long long*)take(NA * 8);
-  ws->pos_list = (int*)take(NA * 4);
+  ws->pos_list = (int2*)take(NA * 8);
+  ws->pos_counter = (int*)take((size_t)g.n_img * 4);
   ws->pos_score = (float*)take(NA * 4);
   ws->pre_acc = (double*)take((size_t)(2 * kLevels + 1) * 8);
+  ws->pre_pub = (double*)take((size_t)(2 * kLevels + 1) * 8);
   ws->pos_slot = (int*)take(NA * 4);
   ws->kd_slot = (int*)take(NA * 4);
   ws->kd_rows = (float*)take(NS * kBoxCh * 4);
@@ -153,6 +155,17 @@ int erd_sizes(const ErdShape* shape, ErdSizes* out) {
   out->num_losses = 3 * kLevels + 2 * g.n_img;
   out->workspace_bytes = ws.bytes;
   return ERD_OK;
+}
+
+int erd_workspace_init(const ErdShape* shape, void* wsp, void* stream) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (!wsp) return fail(ERD_ERR_NULL, "erd_workspace_init: NULL workspace");
+  Workspace ws;
+  carve(g, wsp, &ws);
+  cudaError_t e = cudaMemsetAsync(wsp, 0, ws.bytes, (cudaStream_t)stream);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_workspace_init");
 }
 
 int erd_create(ErdContext** ctx) {

@@ -45,6 +45,12 @@ __device__ __forceinline__ float anchor_gt_iou(float ax1, float ay1, float ax2, 
   return __fdiv_rn(inter, uni);
 }
 
+// (distance bits, index in level): ascending order = nearest first, lowest index on ties
+__device__ __forceinline__ unsigned long long distance_key(const LevelView& v, int x, int y, float gcx, float gcy) {
+  const float d = center_distance((float)(x * v.stride), (float)(y * v.stride), gcx, gcy);
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)(y * v.W + x);
+}
+
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -68,26 +74,30 @@ __global__ void __launch_bounds__(kCandThreads) atss_candidates_kernel(Geo g, Wo
                                                                         const int32_t* __restrict__ pad_hw) {
   const int gid = blockIdx.x;
   const int lane = threadIdx.x & 31, l = threadIdx.x >> 5;
-  __shared__ int s_img;
+  __shared__ int s_img, s_first, s_pad[2];
   __shared__ int s_idx[kLevels * kTopK];
   __shared__ float s_iou[kLevels * kTopK];
   __shared__ float s_cx[kLevels * kTopK], s_cy[kLevels * kTopK];
-  if (threadIdx.x == 0) {
-    int lo = 0, hi = g.n_img;   // last image with gt_offsets[img] <= gid
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (gt_offsets[mid] <= gid) lo = mid; else hi = mid;
+  // every load of the prologue is independent, so the CTA pays one memory round trip: each
+  // thread tests one image's GT range (the image owning gid publishes itself and its padding)
+  const float gx1 = gt_boxes[gid * 4 + 0], gy1 = gt_boxes[gid * 4 + 1];
+  const float gx2 = gt_boxes[gid * 4 + 2], gy2 = gt_boxes[gid * 4 + 3];
+  for (int i = threadIdx.x; i < g.n_img; i += kCandThreads) {
+    const int lo = gt_offsets[i], hi = gt_offsets[i + 1];
+    const int ph = pad_hw[i * 2], pw = pad_hw[i * 2 + 1];
+    if (lo <= gid && gid < hi) {
+      s_img = i;
+      s_first = lo;
+      s_pad[0] = ph;
+      s_pad[1] = pw;
     }
-    s_img = lo;
   }
   if (threadIdx.x < kLevels * kTopK) s_idx[threadIdx.x] = -1;
   __syncthreads();
   const int n = s_img;
-  const float gx1 = gt_boxes[gid * 4 + 0], gy1 = gt_boxes[gid * 4 + 1];
-  const float gx2 = gt_boxes[gid * 4 + 2], gy2 = gt_boxes[gid * 4 + 3];
   const float gcx = __fmul_rn(__fadd_rn(gx1, gx2), 0.5f);   // (x1 + x2) / 2.0, atss_assigner.py:25-26
   const float gcy = __fmul_rn(__fadd_rn(gy1, gy2), 0.5f);
-  const LevelView v = level_view(g, l, pad_hw[n * 2], pad_hw[n * 2 + 1]);
+  const LevelView v = level_view(g, l, s_pad[0], s_pad[1]);
   const int nvalid = v.vw * v.vh;
   const int ksel = min(kTopK, nvalid);                      // atss_assigner.py:198
   if (ksel > 0) {
@@ -110,18 +120,28 @@ __global__ void __launch_bounds__(kCandThreads) atss_candidates_kernel(Geo g, Wo
     for (int pass = 0; pass < 2; ++pass) {
       const int npts = wx * wy;
       unsigned long long prev = 0ull;
-      for (int r = 0; r < ksel; ++r) {
-        unsigned long long best = ~0ull;
-        for (int p = lane; p < npts; p += 32) {
-          const int x = x0 + p % wx, y = y0 + p / wx;
-          const float d = center_distance((float)(x * v.stride), (float)(y * v.stride), gcx, gcy);
-          const unsigned long long key =
-              ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)(y * v.W + x);
-          if ((r == 0 || key > prev) && key < best) best = key;
+      if (npts <= 64) {   // the usual case (7x7 window): two keys per lane, computed once
+        unsigned long long k0 = ~0ull, k1 = ~0ull;
+        if (lane < npts) k0 = distance_key(v, x0 + lane % wx, y0 + lane / wx, gcx, gcy);
+        if (lane + 32 < npts) k1 = distance_key(v, x0 + (lane + 32) % wx, y0 + (lane + 32) / wx, gcx, gcy);
+        if (k1 < k0) { const unsigned long long t = k0; k0 = k1; k1 = t; }
+        for (int r = 0; r < ksel; ++r) {
+          const unsigned long long best = warp_min_u64(k0);
+          if (k0 == best) { k0 = k1; k1 = ~0ull; }   // keys are unique (they embed the index)
+          prev = best;
+          if (lane == 0) s_idx[l * kTopK + r] = (int)(unsigned int)(best & 0xffffffffull);
         }
-        best = warp_min_u64(best);
-        prev = best;
-        if (lane == 0) s_idx[l * kTopK + r] = (int)(unsigned int)(best & 0xffffffffull);
+      } else {
+        for (int r = 0; r < ksel; ++r) {
+          unsigned long long best = ~0ull;
+          for (int p = lane; p < npts; p += 32) {
+            const unsigned long long key = distance_key(v, x0 + p % wx, y0 + p / wx, gcx, gcy);
+            if ((r == 0 || key > prev) && key < best) best = key;
+          }
+          best = warp_min_u64(best);
+          prev = best;
+          if (lane == 0) s_idx[l * kTopK + r] = (int)(unsigned int)(best & 0xffffffffull);
+        }
       }
       // the window is sufficient when the k-th distance is safely below every outside anchor
       const float dk = __uint_as_float((unsigned int)(prev >> 32));
@@ -150,7 +170,7 @@ __global__ void __launch_bounds__(kCandThreads) atss_candidates_kernel(Geo g, Wo
   const double d0 = h0 ? v0 - mean : 0.0, d1 = h1 ? v1 - mean : 0.0;
   const double var = warp_sum(d0 * d0 + d1 * d1) / (cnt - 1.0);   // one candidate -> NaN, as torch.std
   const float thr = __fadd_rn((float)mean, (float)sqrt(var));
-  const int glocal = gid - gt_offsets[n];
+  const int glocal = gid - s_first;
 #pragma unroll
   for (int rep = 0; rep < 2; ++rep) {
     const int t = rep ? t1 : t0;
@@ -169,25 +189,54 @@ __global__ void __launch_bounds__(kCandThreads) atss_candidates_kernel(Geo g, Wo
 }
 
 // Per anchor: decode the argmax table into gt_inds and append positives to the image's list.
+__device__ __forceinline__ void atss_decode_anchor(const Geo& g, const Workspace& ws, const int32_t* __restrict__ pad_hw,
+                                                   const int32_t* __restrict__ gt_offsets,
+                                                   int32_t* __restrict__ gt_inds, int n, int a);
+
 __global__ void __launch_bounds__(256) atss_finalize_kernel(Geo g, Workspace ws, const int32_t* __restrict__ pad_hw,
+                                                            const int32_t* __restrict__ gt_offsets,
                                                             int32_t* __restrict__ gt_inds,
                                                             int32_t* __restrict__ num_pos) {
   const int n = blockIdx.y;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= g.A) return;
+  if (a < g.A) atss_decode_anchor(g, ws, pad_hw, gt_offsets, gt_inds, n, a);
+  // The last block to finish publishes the per-image positive counts and re-zeroes the state
+  // the step accumulates into, so no memset sits on the step's critical path (the workspace is
+  // zero-initialised once, erd_workspace_init).
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(ws.counters + 3, 1u) == gridDim.x * gridDim.y - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < g.n_img; i += blockDim.x) {
+    num_pos[i] = ((volatile int*)ws.pos_counter)[i];
+    ws.pos_counter[i] = 0;
+  }
+  if (threadIdx.x == 0) ws.counters[3] = 0u;
+}
+
+__device__ __forceinline__ void atss_decode_anchor(const Geo& g, const Workspace& ws, const int32_t* __restrict__ pad_hw,
+                                                   const int32_t* __restrict__ gt_offsets,
+                                                   int32_t* __restrict__ gt_inds, int n, int a) {
+  // candidates are valid anchors only, so the key of an invalid one is always 0
+  const unsigned long long key = ws.atss_key[(size_t)n * g.A + a];
+  const int first_gt = gt_offsets[n];
   const int l = level_of_anchor(g, a);
   const LevelView v = level_view(g, l, pad_hw[n * 2], pad_hw[n * 2 + 1]);
   const int r = a - v.start;
   const int x = r % v.W, y = r / v.W;
   int out = -1;
-  if (x < v.vw && y < v.vh) {
-    const unsigned long long key = ws.atss_key[(size_t)n * g.A + a];
-    out = key ? (int)(0xffffffffu - (unsigned int)(key & 0xffffffffull)) + 1 : 0;
-  }
+  if (x < v.vw && y < v.vh) out = key ? (int)(0xffffffffu - (unsigned int)(key & 0xffffffffull)) + 1 : 0;
   gt_inds[(size_t)n * g.A + a] = out;
+  if (key) ws.atss_key[(size_t)n * g.A + a] = 0ull;   // leave the table clean for the next step
   if (out > 0) {
-    const int slot = atomicAdd(num_pos + n, 1);
-    ws.pos_list[(size_t)n * g.A + slot] = a;
+    const int slot = atomicAdd(ws.pos_counter + n, 1);
+    ws.pos_list[(size_t)n * g.A + slot] = make_int2(a, first_gt + out - 1);
+    ws.pos_slot[(size_t)n * g.A + a] = slot;
   }
 }
 
@@ -195,15 +244,11 @@ cudaError_t launch_atss(const Geo& g, const Workspace& ws, const float* gt_boxes
                         const int32_t* gt_offsets, const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos,
                         cudaStream_t st) {
   (void)gt_labels;
-  cudaError_t e = cudaMemsetAsync(ws.atss_key, 0, sizeof(unsigned long long) * (size_t)g.n_img * g.A, st);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(num_pos, 0, sizeof(int32_t) * g.n_img, st);
-  if (e != cudaSuccess) return e;
   if (g.total_gt > 0)
     ERD_LAUNCH(kKAtssCand, st,
                (atss_candidates_kernel<<<g.total_gt, kCandThreads, 0, st>>>(g, ws, gt_boxes, gt_offsets, pad_hw)));
   ERD_LAUNCH(kKAtssFin, st,
-             (atss_finalize_kernel<<<dim3((g.A + 255) / 256, g.n_img), 256, 0, st>>>(g, ws, pad_hw, gt_inds, num_pos)));
+             (atss_finalize_kernel<<<dim3((g.A + 255) / 256, g.n_img), 256, 0, st>>>(g, ws, pad_hw, gt_offsets, gt_inds, num_pos)));
   return cudaGetLastError();
 }
 

@@ -44,10 +44,12 @@ struct Workspace {
   float4* t_dist;                 // [N][A] teacher softmax-integral distances (l,t,r,b), bin units
   double* ers_part;               // [N][tiles][4] per-CTA sums: m, m^2, u, u^2
   unsigned long long* atss_key;   // [N][A] packed (iou bits << 32 | ~gt) argmax table
-  int* pos_list;                  // [N][A] anchors with an assigned GT (unordered)
+  int2* pos_list;                 // [N][A] (anchor, global GT row) of the assigned anchors (unordered)
+  int* pos_counter;               // [N] running length of pos_list (zero between steps)
   float* pos_score;               // [N][A] IoU quality score, defined at positives only
+  double* pre_pub;                // [2L+1] pre_acc of the last avg-factor pass, read by finalize
   double* pre_acc;                // [2L+1] sum w(1-giou) per level, sum w*dfl per level, sum w
-  int* pos_slot;                  // [N][A] row of pos_rows, defined at positives only
+  int* pos_slot;                  // [N][A] index into pos_list / pos_rows, defined at positives only
   int* kd_slot;                   // [N][A] list position of an NMS survivor (row of kd_rows)
   float* kd_rows;                 // [N][sel_cap][68] w * (p_s - p_t) of every ERS box candidate
   float* kd_loss;                 // [N][sel_cap] weighted KL of every ERS box candidate

@@ -116,28 +116,44 @@ __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, P
   // whole warps stay together (8 positives per warp) so the quad shuffles are convergent
   for (int p = (blockIdx.x * kPosThreads + threadIdx.x) >> 2; p < ((np + 7) & ~7) && p < g.pos_cap;
        p += (gridDim.x * kPosThreads) >> 2) {
+    // Dependent memory round trips are what this kernel costs (it runs beside DRAM-saturating
+    // sweeps), so everything past the list entry is issued as one independent batch of loads.
     const bool live = p < np;
-    const int a = live ? ws.pos_list[(size_t)n * g.A + p] : 0;
-    const int gi = live ? A.gt_inds[(size_t)n * g.A + a] : 0;
-    const int gidx = A.gt_offsets[n] + max(gi, 1) - 1;
-    const long long lab = live ? A.gt_labels[gidx] : -1;
-    const bool on = live && lab >= 0 && lab < g.cn;                     // gfl_head_increment_erd.py:273-274
+    const int2 ent = live ? ws.pos_list[(size_t)n * g.A + p] : make_int2(0, 0);
+    const int a = ent.x, gidx = ent.y;
     const int l = level_of_anchor(g, a);
     const int HW = g.hw[l];
     const int hw = a - g.start[l];
-    // weight_targets: max_c sigmoid(new-class logits), detached (:283-284)
-    float mx = -INFINITY;
-    if (on) {
-      const float* cplane = A.s_cls.p[l] + ((size_t)n * g.C + g.ori) * HW + hw;
-      for (int c = side; c < g.cn; c += 4) mx = fmaxf(mx, __ldg(cplane + (size_t)c * HW));
-    }
-    mx = quad_max(mx);
-    const float w = on ? sigmoid_ref(mx) : 0.f;
-    // Integral of this thread's side: softmax expectation (:40-54,285)
     const float* bplane = A.s_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW + hw;
     float z[kBins];
 #pragma unroll
-    for (int j = 0; j < kBins; ++j) z[j] = on ? __ldg(bplane + (size_t)j * HW) : 0.f;
+    for (int j = 0; j < kBins; ++j) z[j] = live ? __ldg(bplane + (size_t)j * HW) : 0.f;
+    // weight_targets: max_c sigmoid(new-class logits), detached (:283-284)
+    float mx = -INFINITY;
+    if (live) {
+      const float* cplane = A.s_cls.p[l] + ((size_t)n * g.C + g.ori) * HW + hw;
+      for (int c = side; c < g.cn; c += 4) mx = fmaxf(mx, __ldg(cplane + (size_t)c * HW));
+    }
+    const long long lab = live ? A.gt_labels[gidx] : -1;
+    const float4 gb = live ? *reinterpret_cast<const float4*>(A.gt_boxes + (size_t)gidx * 4) : make_float4(0, 0, 1, 1);
+    const bool on = live && lab >= 0 && lab < g.cn;                     // gfl_head_increment_erd.py:273-274
+    mx = quad_max(mx);
+    const float w = on ? sigmoid_ref(mx) : 0.f;
+    // DFL target of this side: bbox2distance clamped to [0, reg_max - 0.1] (transforms.py:221-230)
+    const float fs = (float)g.stride[l];
+    const float cx = (float)(hw % g.w[l]), cy = (float)(hw / g.w[l]);
+    const float tx1 = gb.x / fs, ty1 = gb.y / fs, tx2 = gb.z / fs, ty2 = gb.w / fs;   // :288
+    const float tgt = side == 0 ? cx - tx1 : side == 1 ? cy - ty1 : side == 2 ? tx2 - cx : ty2 - cy;
+    const float y = fminf(fmaxf(tgt, 0.f), (float)(kBins - 1) - 0.1f);
+    const int yl = (int)y;
+    const float wl = (float)(yl + 1) - y, wr = y - (float)yl;
+    float zl = 0.f, zr = 0.f;   // the two logits the DFL cross-entropy reads
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) {
+      zl = j == yl ? z[j] : zl;
+      zr = j == yl + 1 ? z[j] : zr;
+    }
+    // Integral of this thread's side: softmax expectation (:40-54,285)
     float zm = z[0];
 #pragma unroll
     for (int j = 1; j < kBins; ++j) zm = fmaxf(zm, z[j]);
@@ -154,11 +170,7 @@ __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, P
 #pragma unroll
     for (int s = 0; s < 4; ++s) d[s] = __shfl_sync(0xffffffffu, dmine, (threadIdx.x & 28) | s, 32);
     // anchor centre / stride is the grid coordinate itself (gfl_head.py:232-243, :281)
-    const float fs = (float)g.stride[l];
-    const float cx = (float)(hw % g.w[l]), cy = (float)(hw / g.w[l]);
-    const float4 gb = on ? *reinterpret_cast<const float4*>(A.gt_boxes + (size_t)gidx * 4) : make_float4(0, 0, 1, 1);
     const float px1 = cx - d[0], py1 = cy - d[1], px2 = cx + d[2], py2 = cy + d[3];   // distance2bbox
-    const float tx1 = gb.x / fs, ty1 = gb.y / fs, tx2 = gb.z / fs, ty2 = gb.w / fs;   // :288
     // aligned IoU / GIoU (bbox_overlaps.py:151-169,189-199), eps 1e-6
     const float area_p = (px2 - px1) * (py2 - py1);
     const float area_t = (tx2 - tx1) * (ty2 - ty1);
@@ -172,16 +184,10 @@ __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, P
     const float ew = fmaxf(ew_raw, 0.f), eh = fmaxf(eh_raw, 0.f);
     const float enc_raw = ew * eh;
     const float enc = fmaxf(enc_raw, 1e-6f);
-    // DFL target of this side: bbox2distance clamped to [0, reg_max - 0.1] (transforms.py:221-230)
-    const float tgt = side == 0 ? cx - tx1 : side == 1 ? cy - ty1 : side == 2 ? tx2 - cx : ty2 - cy;
-    const float y = fminf(fmaxf(tgt, 0.f), (float)(kBins - 1) - 0.1f);
-    const int yl = (int)y;
-    const float wl = (float)(yl + 1) - y, wr = y - (float)yl;
     if (!GRAD) {
       if (on) {
         const float giou = iou - (enc - uni) / enc;
         const float lse = zm + logf(sum);
-        const float zl = __ldg(bplane + (size_t)yl * HW), zr = __ldg(bplane + (size_t)(yl + 1) * HW);
         atomicAdd(&s_acc[kLevels + l], (double)(w * ((lse - zl) * wl + (lse - zr) * wr)));   // gfocal_loss.py:159-165
         if (side == 0) {
           ws.pos_score[(size_t)n * g.A + a] = iou;                                              // :289-292
@@ -214,12 +220,10 @@ __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, P
         gr += cd * (wl * (pj - (j == yl ? 1.f : 0.f)) + wr * (pj - (j == yl + 1 ? 1.f : 0.f)));
         row[j] = gr;
       }
-      if (side == 0) ws.pos_slot[(size_t)n * g.A + a] = p;
     } else if (GRAD && live) {   // assigned to a GT whose label lies outside the new-class range: no box loss
       float* row = ws.pos_rows + ((size_t)n * g.pos_cap + p) * kBoxCh + side * kBins;
 #pragma unroll
       for (int j = 0; j < kBins; ++j) row[j] = 0.f;
-      if (side == 0) ws.pos_slot[(size_t)n * g.A + a] = p;
     }
   }
   if (GRAD) return;
@@ -234,12 +238,20 @@ __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, P
     last = atomicAdd(ws.counters, 1u) == gridDim.x * gridDim.y - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
+  if (!last) return;
+  __threadfence();
+  // publish the sums for finalize and leave the accumulators / ticket clean for the next call
+  if (threadIdx.x < 2 * kLevels + 1) {
+    const double v = ((volatile double*)ws.pre_acc)[threadIdx.x];
+    ws.pre_pub[threadIdx.x] = v;
+    ws.pre_acc[threadIdx.x] = 0.0;
+    if (threadIdx.x == 2 * kLevels) A.avg[1] = (float)v;
+  }
+  if (threadIdx.x == 32) {
     long long cnt = 0;
     for (int i = 0; i < g.n_img; ++i) cnt += max(A.num_pos[i], 1);
     A.avg[0] = (float)cnt;
-    A.avg[1] = (float)((volatile double*)ws.pre_acc)[2 * kLevels];
+    ws.counters[0] = 0u;
   }
 }
 
@@ -510,6 +522,8 @@ __global__ void __launch_bounds__(kTileThreads) box_sweep_kernel(Geo g, Workspac
 // by the warp of its first candidate only.
 constexpr int kLateThreads = 256;
 
+__device__ __forceinline__ void finalize_one(const Geo& g, const Workspace& ws, const LossArgs& A, int i);
+
 __global__ void __launch_bounds__(kLateThreads) box_late_kernel(Geo g, Workspace ws, LossArgs A,
                                                                 const int32_t* __restrict__ box_count) {
   if (A.skip_flag && *A.skip_flag == 0u) return;
@@ -559,10 +573,21 @@ __global__ void __launch_bounds__(kLateThreads) box_late_kernel(Geo g, Workspace
   kd = warp_sum(kd);
   if (lane == 0) red[warp] = kd;
   __syncthreads();
+  __shared__ bool last;
   if (threadIdx.x == 0) {
     double s2 = 0.0;
     for (int w = 0; w < kLateThreads / 32; ++w) s2 += (double)red[w];
     if (s2 != 0.0) atomicAdd(ws.loss_acc + acc_dbox(g, n), s2);
+    // the last block to finish turns the accumulators into the loss vector (saves a launch at
+    // the very end of the step's critical path)
+    __threadfence();
+    last = atomicAdd(ws.counters + 2, 1u) == gridDim.x * gridDim.y - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    finalize_one(g, ws, A, threadIdx.x);
+    if (threadIdx.x == 0) ws.counters[2] = 0u;
   }
 }
 
@@ -575,26 +600,30 @@ __global__ void upstream_check_kernel(Workspace ws, const float* __restrict__ up
 }
 
 // Accumulators -> the reference's loss values, with its division order.
-__global__ void finalize_kernel(Geo g, Workspace ws, LossArgs A) {
-  if (A.skip_flag && *A.skip_flag == 0u) return;
-  const int i = threadIdx.x;
+__device__ __forceinline__ void finalize_one(const Geo& g, const Workspace& ws, const LossArgs& A, int i) {
   const int total = 3 * kLevels + 2 * g.n_img;
   if (i >= total) return;
   const float avg2 = fmaxf(A.avg[1], 1.0f);                                        // :407 clamp_(min=1)
   float out;
   if (i < kLevels) {
-    out = g.w_cls * ((float)ws.loss_acc[i] / (float)((double)A.avg[0] + (double)kEps32));
+    out = g.w_cls * ((float)((volatile double*)ws.loss_acc)[i] / (float)((double)A.avg[0] + (double)kEps32));
   } else if (i < 2 * kLevels) {
-    out = g.w_bbox * ((float)ws.pre_acc[i - kLevels] / (1.0f + kEps32)) / avg2;   // :299-303,408
+    out = g.w_bbox * ((float)ws.pre_pub[i - kLevels] / (1.0f + kEps32)) / avg2;   // :299-303,408
   } else if (i < 3 * kLevels) {
-    out = g.w_dfl * ((float)ws.pre_acc[i - kLevels] / 4.0f) / avg2;               // :306-310,409
+    out = g.w_dfl * ((float)ws.pre_pub[i - kLevels] / 4.0f) / avg2;               // :306-310,409
   } else if (i < 3 * kLevels + g.n_img) {
     const int n = i - 3 * kLevels;
-    out = A.dlw * (float)(ws.loss_acc[i] / ((double)A.cls_count[n] * (double)g.ori));   // mean over K*ori; 0/0 -> NaN
+    out = A.dlw * (float)(((volatile double*)ws.loss_acc)[i] / ((double)A.cls_count[n] * (double)g.ori));   // mean over K*ori; 0/0 -> NaN
   } else {
-    out = A.dlw * (g.w_ld * ((float)ws.loss_acc[i] / 4.0f));
+    out = A.dlw * (g.w_ld * ((float)((volatile double*)ws.loss_acc)[i] / 4.0f));
   }
   A.losses[i] = out;
+  ws.loss_acc[i] = 0.0;   // clean for the next step
+}
+
+__global__ void finalize_kernel(Geo g, Workspace ws, LossArgs A) {
+  if (A.skip_flag && *A.skip_flag == 0u) return;
+  finalize_one(g, ws, A, threadIdx.x);
 }
 
 static int pos_grid_x(const Geo& g) {
@@ -605,9 +634,6 @@ static int pos_grid_x(const Geo& g) {
 cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
                        const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
                        const int32_t* gt_inds, const int32_t* num_pos, float* avg, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(ws.pre_acc, 0, sizeof(double) * (2 * kLevels + 1), st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(ws.counters, 0, sizeof(unsigned int), st);
-  if (e != cudaSuccess) return e;
   PosArgs a;
   a.s_cls = s_cls;
   a.s_box = s_box;
@@ -639,8 +665,7 @@ cudaError_t launch_kd_rows(const Geo& g, const Workspace& ws, const Ptr5& s_cls,
 // behind it.
 cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, const LossStreams* ls) {
   const int total = 3 * kLevels + 2 * g.n_img;
-  cudaError_t e = cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * total, st);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;   // accumulators are left clean by the previous finalize (erd_workspace_init once)
   if (a.skip_flag) ERD_LAUNCH(kKUpCheck, st, (upstream_check_kernel<<<1, 128, 0, st>>>(ws, a.upstream, total)));
   PosArgs p;
   p.s_cls = a.s_cls;
@@ -679,7 +704,8 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
     if (e == cudaSuccess && ls->nms_done) e = cudaStreamWaitEvent(st, ls->nms_done, 0);
     if (e == cudaSuccess && ls->kd_done) e = cudaStreamWaitEvent(st, ls->kd_done, 0);
     if (e != cudaSuccess) return e;
-    ERD_LAUNCH(kKBoxSweep, st, (box_late_kernel<<<dim3(32, g.n_img), kLateThreads, 0, st>>>(g, ws, a, a.box_count)));
+    ERD_LAUNCH(kKBoxSweep, st, (box_late_kernel<<<dim3(128, g.n_img), kLateThreads, 0, st>>>(g, ws, a, a.box_count)));
+    return cudaGetLastError();   // box_late's last block wrote the loss vector
   } else {
     ERD_LAUNCH(kKPosGrad, st, (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, st>>>(g, ws, p)));
     ERD_LAUNCH(kKBoxSweep, st, (box_sweep_kernel<0><<<box_grid, kTileThreads, 0, st>>>(g, ws, a)));

@@ -21,6 +21,15 @@ struct ProfState {
 };
 static ProfState g_prof;
 
+// Inside a stream capture an event record must be an external event-record node to be timed
+// after the graph has run.
+static cudaError_t record(cudaEvent_t e, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+    return cudaEventRecordWithFlags(e, st, cudaEventRecordExternal);
+  return cudaEventRecord(e, st);
+}
+
 static cudaEvent_t take_event() {
   if (!g_prof.pool.empty()) {
     cudaEvent_t e = g_prof.pool.back();
@@ -37,14 +46,14 @@ void prof_begin(int id, cudaStream_t st) {
   ++g_prof.launches;
   if (!(g_prof.mask >> id & 1u)) return;
   cudaEvent_t a = take_event(), b = take_event();
-  cudaEventRecord(a, st);
+  record(a, st);
   g_prof.pending[id].push_back({a, b});
 }
 
 void prof_end(int id, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
   if (!(g_prof.mask >> id & 1u)) return;
-  if (!g_prof.pending[id].empty()) cudaEventRecord(g_prof.pending[id].back().second, st);
+  if (!g_prof.pending[id].empty()) record(g_prof.pending[id].back().second, st);
 }
 
 }  // namespace erd
@@ -69,7 +78,7 @@ unsigned long long erd_launch_count(void) {
 int erd_profile_mark(void* stream) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
   if (!g_prof.ref) cudaEventCreate(&g_prof.ref);
-  return cudaEventRecord(g_prof.ref, (cudaStream_t)stream) == cudaSuccess ? ERD_OK : ERD_ERR_CUDA;
+  return record(g_prof.ref, (cudaStream_t)stream) == cudaSuccess ? ERD_OK : ERD_ERR_CUDA;
 }
 
 int erd_profile_timeline(float* start_ms, float* end_ms) {

@@ -59,6 +59,9 @@ class Plan:
         self.num_losses = int(sizes.num_losses)
         i32 = dict(dtype=torch.int32, device=device)
         self.ws = torch.empty(int(sizes.workspace_bytes), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):   # zero once; the kernels keep it clean afterwards
+            N.check(N.load().erd_workspace_init(C.byref(self.shape), self.ws.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), 'erd_workspace_init')
         self.cls_inds = torch.empty(n, self.sel_cap, **i32)
         self.box_inds = torch.empty(n, self.sel_cap, **i32)
         self.keep = torch.empty(n, self.sel_cap, **i32)

@@ -80,6 +80,11 @@ const char* erd_last_error(void);
 /* Sizes and workspace requirement for a shape. */
 int erd_sizes(const ErdShape* shape, ErdSizes* out);
 
+/* Zero the workspace.  Required once after allocation (and after a failed call): the kernels
+ * leave every accumulator / counter / table clean for the next step themselves, so no memset
+ * sits on a step's critical path. */
+int erd_workspace_init(const ErdShape* shape, void* ws, void* stream);
+
 int erd_create(ErdContext** ctx);
 int erd_destroy(ErdContext* ctx);
 

@@ -37,3 +37,28 @@ print(f'{"kernel":16s} {"start us":>9s} {"end us":>9s} {"dur":>7s}   (median of 
 for k, v in sorted(rows.items(), key=lambda kv: sorted(x[0] for x in kv[1])[len(kv[1]) // 2]):
     st = sorted(x[0] for x in v)[len(v) // 2]; en = sorted(x[1] for x in v)[len(v) // 2]
     print(f'{k:16s} {st:9.1f} {en:9.1f} {en - st:7.1f}  ' + ' ' * int(st / 4) + '#' * max(1, int((en - st) / 4)))
+
+print()
+print('--- same step replayed from a CUDA graph (external event nodes), median of 5 replays')
+lib.erd_profile_collect(None, None)
+side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side): step()
+torch.cuda.current_stream().wait_stream(side)
+gmask = int(os.environ.get('ERD_TL_MASK', '0'), 0) or (1 << nk) - 1
+lib.erd_profile_enable(gmask)
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    lib.erd_profile_mark(torch.cuda.current_stream().cuda_stream)
+    step()
+lib.erd_profile_enable(0)
+rows = {}
+for it in range(6):
+    graph.replay(); torch.cuda.synchronize()
+    s, e = (C.c_float * nk)(), (C.c_float * nk)()
+    lib.erd_profile_timeline(s, e)
+    if it == 0: continue
+    for i in range(nk):
+        if s[i] >= 0: rows.setdefault(names[i], []).append((s[i] * 1e3, e[i] * 1e3))
+for k, v in sorted(rows.items(), key=lambda kv: sorted(x[0] for x in kv[1])[len(kv[1]) // 2]):
+    st = sorted(x[0] for x in v)[len(v) // 2]; en = sorted(x[1] for x in v)[len(v) // 2]
+    print(f'{k:16s} {st:9.1f} {en:9.1f} {en - st:7.1f}  ' + ' ' * int(st / 4) + '#' * max(1, int((en - st) / 4)))
