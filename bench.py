@@ -34,11 +34,11 @@ ORI, NUM_CLASSES, REG_MAX = 40, 80, 16
 # compulsory fp32 traffic per anchor, fwd+bwd, 40+40 split
 # per dense kernel: ers_scan reads teacher cls + box; qfl_sweep reads the student's
 # new-class logits and writes their gradients; cls_old_sweep reads student + teacher old-class logits and
-# writes the old-class gradients; box_early writes the box gradients (student box logits are only touched
+# writes the old-class gradients; box_sweep writes the box gradients (student box logits are only touched
 # at positives / ERS rows, by the small gather kernels)
 CN = NUM_CLASSES - ORI
 BYTES_PER_ANCHOR = {'path': 1616, 'ers_scan': 4 * (ORI + 68), 'qfl_sweep': 4 * (CN + CN),
-                    'cls_old_sweep': 4 * (ORI + ORI + ORI), 'box_early': 4 * 68}
+                    'cls_old_sweep': 4 * (ORI + ORI + ORI), 'box_sweep': 4 * 68}
 
 
 def parse():
@@ -197,7 +197,7 @@ def run_ours(args):
 
     nk = lib.erd_profile_num_kernels()
     names = [lib.erd_profile_kernel_name(i).decode() for i in range(nk)]
-    dense = [k for k in ('ers_scan', 'qfl_sweep', 'cls_old_sweep', 'box_early') if k in names]
+    dense = [k for k in ('ers_scan', 'qfl_sweep', 'cls_old_sweep', 'box_sweep') if k in names]
 
     def collect():
         tot, cnt = (C.c_float * nk)(), (C.c_int * nk)()

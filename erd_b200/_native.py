@@ -51,7 +51,6 @@ SIGNATURES = {
     'erd_atss_assign': [_SH, _P, _P, _P, _P, _P, _P, _P, _P],
     'erd_avg_factors': [_SH, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P],
     'erd_teacher_nms': [_SH, _P, _P, _P, _F, _P, _P, _P, _P, _P],
-    'erd_kd_rows': [_SH, PtrArray, PtrArray, PtrArray, _P, _P, _P, _P],
     'erd_loss_fwd_bwd': [_P, _SH, PtrArray, PtrArray, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                          _P, _P, _P, _F, _P, _I, _P, PtrArray, PtrArray, _P, _P],
     'erd_step_prepare': [_P, _SH, PtrArray, PtrArray, PtrArray, PtrArray, _P, _P, _P, _P, _F,

@@ -86,8 +86,7 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->pre_acc = (double*)take((size_t)(2 * kLevels + 1) * 8);
   ws->pre_pub = (double*)take((size_t)(2 * kLevels + 1) * 8);
   ws->pos_slot = (int*)take(NA * 4);
-  ws->kd_slot = (int*)take(NA * 4);
-  ws->kd_rows = (float*)take(NS * kBoxCh * 4);
+  ws->keep_raw = (int*)take(NS * 4);
   ws->kd_loss = (float*)take(NS * 4);
   ws->pos_rows = (float*)take((size_t)g.n_img * g.pos_cap * kBoxCh * 4);
   ws->nms_nz = (unsigned long long*)take(NS * nms_nz_words(g.sel_cap) * 8);
@@ -133,8 +132,8 @@ static MPtr5 mptr5(float* const* p) {
 }
 
 struct ErdContext {
-  cudaStream_t side[3];          // [0] assignment + positives prepass, [1] teacher NMS, [2] KD rows
-  cudaEvent_t fork, join[3], sel, sel_done, early_done, nms_all;
+  cudaStream_t side[3];          // [0] early box sectors, [1] teacher chain, [2] positives' rows + late box groups
+  cudaEvent_t fork, join[3], pos_done, sel_done, early_done, nms_all;
   bool nms_pending;              // join[1] recorded by erd_step_prepare, not yet waited on
 };
 
@@ -177,11 +176,11 @@ int erd_create(ErdContext** ctx) {
   int prio_least = 0, prio_greatest = 0;
   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
-    e = cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, i == 1 ? prio_greatest : prio_least);
+    e = cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, i == 0 ? prio_least : prio_greatest);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sel, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->pos_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->early_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->nms_all, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sel_done, cudaEventDisableTiming);
@@ -201,7 +200,7 @@ int erd_destroy(ErdContext* c) {
     cudaEventDestroy(c->join[i]);
   }
   cudaEventDestroy(c->fork);
-  cudaEventDestroy(c->sel);
+  cudaEventDestroy(c->pos_done);
   cudaEventDestroy(c->early_done);
   cudaEventDestroy(c->nms_all);
   cudaEventDestroy(c->sel_done);
@@ -280,23 +279,9 @@ static int nms_on_side_stream(ErdContext* ctx, const ErdShape* shape, const ErdS
   Workspace ws;
   carve(g, wsp, &ws);
   cudaError_t e = launch_nms(g, ws, b->box_inds, b->box_count, pad_hw, iou_thr, b->keep, b->keep_count, b->sel_flags,
-                             ctx->side[1], ctx->sel, ctx->join[1]);
+                             ctx->side[1], nullptr, ctx->join[1]);
   if (e == cudaSuccess) e = cudaEventRecord(ctx->nms_all, ctx->side[1]);
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_step_prepare nms");
-}
-
-int erd_kd_rows(const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
-                const float* const* t_box, const int32_t* box_inds, const int32_t* box_count, void* wsp,
-                void* stream) {
-  Geo g;
-  int rc = make_geo(shape, &g);
-  if (rc) return rc;
-  if (NULLS(s_cls) || NULLS(s_box) || NULLS(t_box) || !box_inds || !box_count || !wsp)
-    return fail(ERD_ERR_NULL, "erd_kd_rows: NULL argument");
-  Workspace ws;
-  carve(g, wsp, &ws);
-  cudaError_t e = launch_kd_rows(g, ws, ptr5(s_cls), ptr5(s_box), ptr5(t_box), box_inds, box_count, (cudaStream_t)stream);
-  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_kd_rows");
 }
 
 int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
@@ -351,11 +336,13 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
   if (ctx) {
     LossStreams ls;
     ls.early = ctx->side[0];
+    ls.late = ctx->side[2];
+    ls.pos_done = ctx->pos_done;
+    ls.late_done = ctx->join[2];
     ls.fork = ctx->fork;
     ls.early_done = ctx->early_done;
     ls.sel_ready = ctx->nms_pending ? ctx->sel_done : nullptr;
     ls.nms_done = ctx->nms_pending ? ctx->join[1] : nullptr;
-    ls.kd_done = ctx->nms_pending ? ctx->join[2] : nullptr;
     const bool had_nms = ctx->nms_pending;
     e = launch_loss(g, ws, a, (cudaStream_t)stream, &ls);
     // the score-ordered keep list is an output only: join it last
@@ -376,18 +363,15 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   cudaError_t e = cudaSuccess;
   if (ctx->nms_pending) {   // a previous prepare nobody consumed: do not race its teacher cache
     e = cudaStreamWaitEvent(main, ctx->nms_all, 0);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ctx->join[2], 0);
     ctx->nms_pending = false;
   }
   // Stream layout.  The caller's stream only carries what the avg-factor all-reduce needs
   // (ATSS + positives prepass), so the caller can all-reduce and start the QFL sweep at once.
   // The teacher side runs beside it: side[1] = ERS scan + select (sel_done) -> NMS (join[1] when
-  // the survivors are marked, nms_all when the keep list is ordered); side[2] = distillation
-  // rows of every box candidate, started behind the NMS's own gathers (join[2]).
+  // the survivors are marked, nms_all when the keep list is ordered).
   // erd_loss_fwd_bwd(ctx, ...) joins them exactly where their results are consumed.
   if (e == cudaSuccess) e = cudaEventRecord(ctx->fork, main);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[1], ctx->fork, 0);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[2], ctx->fork, 0);
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork");
   int rc = 0;
   if (!(flags & ERD_PREPARE_ERS_DONE))
@@ -399,18 +383,21 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   if (!b->box_inds || !b->box_count || !pad_hw || !b->keep || !b->keep_count || !b->sel_flags || !wsp)
     return fail(ERD_ERR_NULL, "erd_step_prepare: NULL NMS buffer");
   rc = nms_on_side_stream(ctx, shape, b, pad_hw, iou_thr, wsp);
-  // the distillation rows (random DRAM gathers) start once the NMS has finished its own gathers
-  // (ctx->sel is recorded behind nms_prep), so they do not stretch the latency-bound chain
-  if (!rc && cudaStreamWaitEvent(ctx->side[2], ctx->sel, 0) != cudaSuccess) rc = fail(ERD_ERR_CUDA, "fork kd");
-  if (!rc) rc = erd_kd_rows(shape, s_cls, s_box, t_box, b->box_inds, b->box_count, wsp, ctx->side[2]);
   if (rc) return rc;
-  e = cudaEventRecord(ctx->join[2], ctx->side[2]);
-  if (e == cudaSuccess) ctx->nms_pending = true;
-  if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare join");
-  rc = erd_atss_assign(shape, gt_boxes, gt_labels, gt_offsets, pad_hw, b->gt_inds, b->num_pos, wsp, main);
-  if (!rc)
-    rc = erd_avg_factors(shape, s_cls, s_box, gt_boxes, gt_labels, gt_offsets, b->gt_inds, b->num_pos, b->avg, wsp, main);
-  return rc;
+  ctx->nms_pending = true;
+  // erd_atss_assign + erd_avg_factors, with the decode and the positives prepass in one launch
+  Geo g;
+  rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (NULLS(s_cls) || NULLS(s_box) || !gt_offsets || !b->gt_inds || !b->num_pos || !b->avg ||
+      (g.total_gt > 0 && (!gt_labels || !gt_boxes)))
+    return fail(ERD_ERR_NULL, "erd_step_prepare: NULL assignment argument");
+  if (g.total_gt > 0 && ((uintptr_t)gt_boxes & 15)) return fail(ERD_ERR_BAD_SHAPE, "gt_boxes must be 16 B aligned");
+  Workspace ws;
+  carve(g, wsp, &ws);
+  e = launch_assign_avg(g, ws, ptr5(s_cls), ptr5(s_box), gt_boxes, gt_labels, gt_offsets, pad_hw, b->gt_inds,
+                        b->num_pos, b->avg, main);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_step_prepare assignment");
 }
 
 }  // extern "C"

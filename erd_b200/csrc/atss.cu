@@ -12,23 +12,6 @@
 
 namespace erd {
 
-struct LevelView {
-  int W, vw, vh, stride, start;
-  float half;
-};
-
-__device__ __forceinline__ LevelView level_view(const Geo& g, int l, int pad_h, int pad_w) {
-  LevelView v;
-  v.W = g.w[l];
-  v.stride = g.stride[l];
-  v.start = g.start[l];
-  v.half = g.half[l];
-  // valid_flags: x < min(ceil(pad_w / s), W), y < min(ceil(pad_h / s), H)  (anchor_generator.py:434-442)
-  v.vw = min((pad_w + v.stride - 1) / v.stride, g.w[l]);
-  v.vh = min((pad_h + v.stride - 1) / v.stride, g.h[l]);
-  return v;
-}
-
 __device__ __forceinline__ float center_distance(float pcx, float pcy, float gcx, float gcy) {
   const float dx = __fsub_rn(pcx, gcx), dy = __fsub_rn(pcy, gcy);
   return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));   // atss_assigner.py:33-34
@@ -188,11 +171,8 @@ __global__ void __launch_bounds__(kCandThreads) atss_candidates_kernel(Geo g, Wo
   }
 }
 
-// Per anchor: decode the argmax table into gt_inds and append positives to the image's list.
-__device__ __forceinline__ void atss_decode_anchor(const Geo& g, const Workspace& ws, const int32_t* __restrict__ pad_hw,
-                                                   const int32_t* __restrict__ gt_offsets,
-                                                   int32_t* __restrict__ gt_inds, int n, int a);
-
+// Per anchor: decode the argmax table into gt_inds and append positives to the image's list
+// (atss_decode_anchor, erd_common.cuh).
 __global__ void __launch_bounds__(256) atss_finalize_kernel(Geo g, Workspace ws, const int32_t* __restrict__ pad_hw,
                                                             const int32_t* __restrict__ gt_offsets,
                                                             int32_t* __restrict__ gt_inds,
@@ -219,34 +199,20 @@ __global__ void __launch_bounds__(256) atss_finalize_kernel(Geo g, Workspace ws,
   if (threadIdx.x == 0) ws.counters[3] = 0u;
 }
 
-__device__ __forceinline__ void atss_decode_anchor(const Geo& g, const Workspace& ws, const int32_t* __restrict__ pad_hw,
-                                                   const int32_t* __restrict__ gt_offsets,
-                                                   int32_t* __restrict__ gt_inds, int n, int a) {
-  // candidates are valid anchors only, so the key of an invalid one is always 0
-  const unsigned long long key = ws.atss_key[(size_t)n * g.A + a];
-  const int first_gt = gt_offsets[n];
-  const int l = level_of_anchor(g, a);
-  const LevelView v = level_view(g, l, pad_hw[n * 2], pad_hw[n * 2 + 1]);
-  const int r = a - v.start;
-  const int x = r % v.W, y = r / v.W;
-  int out = -1;
-  if (x < v.vw && y < v.vh) out = key ? (int)(0xffffffffu - (unsigned int)(key & 0xffffffffull)) + 1 : 0;
-  gt_inds[(size_t)n * g.A + a] = out;
-  if (key) ws.atss_key[(size_t)n * g.A + a] = 0ull;   // leave the table clean for the next step
-  if (out > 0) {
-    const int slot = atomicAdd(ws.pos_counter + n, 1);
-    ws.pos_list[(size_t)n * g.A + slot] = make_int2(a, first_gt + out - 1);
-    ws.pos_slot[(size_t)n * g.A + a] = slot;
-  }
+cudaError_t launch_atss_candidates(const Geo& g, const Workspace& ws, const float* gt_boxes, const int32_t* gt_offsets,
+                                   const int32_t* pad_hw, cudaStream_t st) {
+  if (g.total_gt > 0)
+    ERD_LAUNCH(kKAtssCand, st,
+               (atss_candidates_kernel<<<g.total_gt, kCandThreads, 0, st>>>(g, ws, gt_boxes, gt_offsets, pad_hw)));
+  return cudaGetLastError();
 }
 
 cudaError_t launch_atss(const Geo& g, const Workspace& ws, const float* gt_boxes, const int64_t* gt_labels,
                         const int32_t* gt_offsets, const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos,
                         cudaStream_t st) {
   (void)gt_labels;
-  if (g.total_gt > 0)
-    ERD_LAUNCH(kKAtssCand, st,
-               (atss_candidates_kernel<<<g.total_gt, kCandThreads, 0, st>>>(g, ws, gt_boxes, gt_offsets, pad_hw)));
+  cudaError_t e = launch_atss_candidates(g, ws, gt_boxes, gt_offsets, pad_hw, st);
+  if (e != cudaSuccess) return e;
   ERD_LAUNCH(kKAtssFin, st,
              (atss_finalize_kernel<<<dim3((g.A + 255) / 256, g.n_img), 256, 0, st>>>(g, ws, pad_hw, gt_offsets, gt_inds, num_pos)));
   return cudaGetLastError();

@@ -49,10 +49,9 @@ struct Workspace {
   float* pos_score;               // [N][A] IoU quality score, defined at positives only
   double* pre_pub;                // [2L+1] pre_acc of the last avg-factor pass, read by finalize
   double* pre_acc;                // [2L+1] sum w(1-giou) per level, sum w*dfl per level, sum w
-  int* pos_slot;                  // [N][A] index into pos_list / pos_rows, defined at positives only
-  int* kd_slot;                   // [N][A] list position of an NMS survivor (row of kd_rows)
-  float* kd_rows;                 // [N][sel_cap][68] w * (p_s - p_t) of every ERS box candidate
+  int* keep_raw;                  // [N][sel_cap] NMS survivors as list positions, unordered (resolve pass)
   float* kd_loss;                 // [N][sel_cap] weighted KL of every ERS box candidate
+  int* pos_slot;                  // [N][A] index into pos_list / pos_rows, defined at positives only
   float* pos_rows;                // [N][pos_cap][68] box-logit gradient rows of the positives
   unsigned long long* nms_nz;     // [N][sel_cap][nz_words] which words of a predecessor row are non-zero
   unsigned int* counters;         // [8] last-block tickets
@@ -121,14 +120,14 @@ struct Quad {
   __device__ __forceinline__ void load(const float* __restrict__ plane, float (&v)[4], float fill) const {
     if (VEC) {
       if (ok[0]) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(plane + hw[0]));
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(plane + hw[0]));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
       } else {
         v[0] = v[1] = v[2] = v[3] = fill;
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = ok[k] ? __ldg(plane + hw[k]) : fill;
+      for (int k = 0; k < 4; ++k) v[k] = ok[k] ? __ldcs(plane + hw[k]) : fill;
     }
   }
   __device__ __forceinline__ void store(float* __restrict__ plane, const float (&v)[4]) const {
@@ -148,7 +147,7 @@ struct Quad {
 
 // ---------------------------------------------------------------- launch accounting (profile.cu)
 enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan, kKNmsOrder,
-                kKKdRows, kKUpCheck, kKLossMain, kKClsOld, kKPosGrad, kKBoxEarly, kKBoxSweep, kKFinalize, kNumKernels };
+                kKUpCheck, kKLossMain, kKClsOld, kKPosGrad, kKBoxEarly, kKBoxKd, kKBoxSweep, kKFinalize, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 // ERD_LAUNCH(id, stream, kernel<<<...>>>(...)) counts the launch and, when profiling is on,
@@ -160,14 +159,67 @@ void prof_end(int id, cudaStream_t st);
     ::erd::prof_end(id, st);    \
   } while (0)
 
-// ---------------------------------------------------------------- host launchers (one per .cu)
+
+// ----------------------------------------------------------------------------- ATSS decode
+struct LevelView {
+  int W, vw, vh, stride, start;
+  float half;
+};
+
+__device__ __forceinline__ LevelView level_view(const Geo& g, int l, int pad_h, int pad_w) {
+  LevelView v;
+  v.W = g.w[l];
+  v.stride = g.stride[l];
+  v.start = g.start[l];
+  v.half = g.half[l];
+  // valid_flags: x < min(ceil(pad_w / s), W), y < min(ceil(pad_h / s), H)  (anchor_generator.py:434-442)
+  v.vw = min((pad_w + v.stride - 1) / v.stride, g.w[l]);
+  v.vh = min((pad_h + v.stride - 1) / v.stride, g.h[l]);
+  return v;
+}
+
+// Anchor a of image n: argmax table entry -> assigned_gt_inds (-1 invalid, 0 background, k > 0
+// = GT k-1 of the image; atss_assigner.py:236-246, gfl_head.py:613-640).  Positives are appended
+// to the image's list; returns the global GT row (>= 0) of a positive, -1 otherwise.
+__device__ __forceinline__ int atss_decode_key(const Geo& g, const Workspace& ws, int pad_h, int pad_w, int first_gt,
+                                               int32_t* __restrict__ gt_inds, int n, int a, unsigned long long key) {
+  const int l = level_of_anchor(g, a);
+  const LevelView v = level_view(g, l, pad_h, pad_w);
+  const int r = a - v.start;
+  const int x = r % v.W, y = r / v.W;
+  int out = -1;
+  if (x < v.vw && y < v.vh) out = key ? (int)(0xffffffffu - (unsigned int)(key & 0xffffffffull)) + 1 : 0;
+  gt_inds[(size_t)n * g.A + a] = out;
+  if (key) ws.atss_key[(size_t)n * g.A + a] = 0ull;   // leave the table clean for the next step
+  if (out <= 0) return -1;
+  const int slot = atomicAdd(ws.pos_counter + n, 1);
+  ws.pos_list[(size_t)n * g.A + slot] = make_int2(a, first_gt + out - 1);
+  ws.pos_slot[(size_t)n * g.A + a] = slot;
+  return first_gt + out - 1;
+}
+
+__device__ __forceinline__ int atss_decode_anchor(const Geo& g, const Workspace& ws, const int32_t* __restrict__ pad_hw,
+                                                  const int32_t* __restrict__ gt_offsets,
+                                                  int32_t* __restrict__ gt_inds, int n, int a) {
+  // candidates are valid anchors only, so the key of an invalid one is always 0
+  const unsigned long long key = ws.atss_key[(size_t)n * g.A + a];
+  return atss_decode_key(g, ws, pad_hw[n * 2], pad_hw[n * 2 + 1], gt_offsets[n], gt_inds, n, a, key);
+}
+
 
 cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box,
                        int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds, int32_t* box_count,
                        float* thr, uint8_t* sel_flags, cudaStream_t st);
+// ---------------------------------------------------------------- host launchers (one per .cu)
+cudaError_t launch_atss_candidates(const Geo& g, const Workspace& ws, const float* gt_boxes, const int32_t* gt_offsets,
+                                   const int32_t* pad_hw, cudaStream_t st);
 cudaError_t launch_atss(const Geo& g, const Workspace& ws, const float* gt_boxes, const int64_t* gt_labels,
                         const int32_t* gt_offsets, const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos,
                         cudaStream_t st);
+// atss_finalize + pos_prepass in one launch (the step's student-side chain is latency bound)
+cudaError_t launch_assign_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
+                              const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                              const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos, float* avg, cudaStream_t st);
 cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
                        const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
                        const int32_t* gt_inds, const int32_t* num_pos, float* avg, cudaStream_t st);
@@ -196,14 +248,12 @@ struct LossArgs {
   float* losses;
   float dlw;
 };
-cudaError_t launch_kd_rows(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box, const Ptr5& t_box,
-                           const int32_t* box_inds, const int32_t* box_count, cudaStream_t st);
 struct LossStreams {
-  cudaStream_t early;                 // helper stream for the NMS-independent box sectors
-  cudaEvent_t fork, early_done;
+  cudaStream_t early;                 // low-priority helper: the dense box sweep
+  cudaStream_t late;                  // high-priority helper: positives' rows, survivors' distillation rows
+  cudaEvent_t fork, pos_done, early_done, late_done;
   cudaEvent_t sel_ready;              // may be null: ERS selection already ordered before the caller's stream
   cudaEvent_t nms_done;               // may be null: NMS already ordered before the caller's stream
-  cudaEvent_t kd_done;                // may be null: likewise for the distillation rows
 };
 cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, const LossStreams* ls);
 

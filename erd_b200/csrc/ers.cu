@@ -5,6 +5,7 @@
 // pass is gfl_head_increment_erd.py:40-54,189-195.
 #include <stdlib.h>
 
+#include <cstdlib>
 #include "erd_common.cuh"
 
 namespace erd {
@@ -352,9 +353,20 @@ static int launch_scan_pipe(const Geo& g, const Workspace& ws, const Ptr5& t_cls
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(ers_scan_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * kPipeStageFloats * 4);
   }
-  const int stages = 6;    // 2 CTAs/SM x 6 x 17 KB = 204 KB of copies in flight per SM
+  static int stages = 0;   // 2 CTAs/SM x stages x 17 KB of copies in flight per SM
+  if (!stages) {
+    const char* e = getenv("ERD_SCAN_STAGES");
+    stages = e ? atoi(e) : 2;
+    if (stages < 2 || stages > 6) stages = 2;
+  }
   const int total = tiles * g.n_img;
-  const int grid = total < 2 * sms ? total : 2 * sms;
+  static int per_sm = 0;
+  if (!per_sm) {
+    const char* e = getenv("ERD_SCAN_CTAS");
+    per_sm = e ? atoi(e) : 2;
+    if (per_sm < 1 || per_sm > 4) per_sm = 2;
+  }
+  const int grid = total < per_sm * sms ? total : per_sm * sms;
   ERD_LAUNCH(kKErsScan, st,
              (ers_scan_pipe_kernel<<<grid, kPipeThreads, (size_t)stages * kPipeStageFloats * 4, st>>>(
                  g, ws, t_cls, t_box, tiles, total, stages)));

@@ -15,7 +15,7 @@
 //   cls_sweep_kernel   streaming sweep over the class logits: QFL on the new-class channels of
 //                      every anchor, class-response L2 on the old-class channels (zero off
 //                      the ERS rows), gradients written once, densely.
-//   kd_rows_kernel     (prepare phase, beside the NMS) DFL-distribution KL rows of every ERS
+//   (kd_side)          DFL-distribution KL of the NMS survivors, computed where box_late writes
 //                      box candidate.
 //   box_sweep_kernel   dense write of the box-logit gradients: zero, the compact rows of the
 //                      positives, and the distillation rows of the NMS survivors.
@@ -101,6 +101,119 @@ struct PosArgs {
   const unsigned int* skip_flag;
 };
 
+// One side of one positive anchor (a, assigned to GT row gidx); the four side threads are
+// adjacent lanes.  Dead lanes (live == false) run along so the quad shuffles stay convergent.
+template <bool GRAD>
+__device__ __forceinline__ void pos_item(const Geo& g, const Workspace& ws, const PosArgs& A, int n, bool live, int a,
+                                         int gidx, int p, int side, double* s_acc, float avg2) {
+  // Dependent memory round trips are what this kernel costs (it runs beside DRAM-saturating
+  // sweeps), so everything past the list entry is issued as one independent batch of loads.
+  const int l = level_of_anchor(g, a);
+  const int HW = g.hw[l];
+  const int hw = a - g.start[l];
+  const float* bplane = A.s_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW + hw;
+  float z[kBins];
+#pragma unroll
+  for (int j = 0; j < kBins; ++j) z[j] = live ? __ldg(bplane + (size_t)j * HW) : 0.f;
+  // weight_targets: max_c sigmoid(new-class logits), detached (:283-284)
+  float mx = -INFINITY;
+  if (live) {
+    const float* cplane = A.s_cls.p[l] + ((size_t)n * g.C + g.ori) * HW + hw;
+    for (int c = side; c < g.cn; c += 4) mx = fmaxf(mx, __ldg(cplane + (size_t)c * HW));
+  }
+  const long long lab = live ? A.gt_labels[gidx] : -1;
+  const float4 gb = live ? *reinterpret_cast<const float4*>(A.gt_boxes + (size_t)gidx * 4) : make_float4(0, 0, 1, 1);
+  const bool on = live && lab >= 0 && lab < g.cn;                     // gfl_head_increment_erd.py:273-274
+  mx = quad_max(mx);
+  const float w = on ? sigmoid_ref(mx) : 0.f;
+  // DFL target of this side: bbox2distance clamped to [0, reg_max - 0.1] (transforms.py:221-230)
+  const float fs = (float)g.stride[l];
+  const float cx = (float)(hw % g.w[l]), cy = (float)(hw / g.w[l]);
+  const float tx1 = gb.x / fs, ty1 = gb.y / fs, tx2 = gb.z / fs, ty2 = gb.w / fs;   // :288
+  const float tgt = side == 0 ? cx - tx1 : side == 1 ? cy - ty1 : side == 2 ? tx2 - cx : ty2 - cy;
+  const float y = fminf(fmaxf(tgt, 0.f), (float)(kBins - 1) - 0.1f);
+  const int yl = (int)y;
+  const float wl = (float)(yl + 1) - y, wr = y - (float)yl;
+  float zl = 0.f, zr = 0.f;   // the two logits the DFL cross-entropy reads
+#pragma unroll
+  for (int j = 0; j < kBins; ++j) {
+    zl = j == yl ? z[j] : zl;
+    zr = j == yl + 1 ? z[j] : zr;
+  }
+  // Integral of this thread's side: softmax expectation (:40-54,285)
+  float zm = z[0];
+#pragma unroll
+  for (int j = 1; j < kBins; ++j) zm = fmaxf(zm, z[j]);
+  float sum = 0.f, num = 0.f;
+#pragma unroll
+  for (int j = 0; j < kBins; ++j) {
+    z[j] = expf(z[j] - zm);
+    sum += z[j];
+    num = fmaf((float)j, z[j], num);
+  }
+  const float inv = 1.0f / sum;
+  const float dmine = num * inv;
+  float d[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) d[s] = __shfl_sync(0xffffffffu, dmine, (threadIdx.x & 28) | s, 32);
+  // anchor centre / stride is the grid coordinate itself (gfl_head.py:232-243, :281)
+  const float px1 = cx - d[0], py1 = cy - d[1], px2 = cx + d[2], py2 = cy + d[3];   // distance2bbox
+  // aligned IoU / GIoU (bbox_overlaps.py:151-169,189-199), eps 1e-6
+  const float area_p = (px2 - px1) * (py2 - py1);
+  const float area_t = (tx2 - tx1) * (ty2 - ty1);
+  const float iw_raw = fminf(px2, tx2) - fmaxf(px1, tx1), ih_raw = fminf(py2, ty2) - fmaxf(py1, ty1);
+  const float iw = fmaxf(iw_raw, 0.f), ih = fmaxf(ih_raw, 0.f);
+  const float inter = iw * ih;
+  const float uni_raw = area_p + area_t - inter;
+  const float uni = fmaxf(uni_raw, 1e-6f);
+  const float iou = inter / uni;
+  const float ew_raw = fmaxf(px2, tx2) - fminf(px1, tx1), eh_raw = fmaxf(py2, ty2) - fminf(py1, ty1);
+  const float ew = fmaxf(ew_raw, 0.f), eh = fmaxf(eh_raw, 0.f);
+  const float enc_raw = ew * eh;
+  const float enc = fmaxf(enc_raw, 1e-6f);
+  if (!GRAD) {
+    if (on) {
+      const float giou = iou - (enc - uni) / enc;
+      const float lse = zm + logf(sum);
+      atomicAdd(&s_acc[kLevels + l], (double)(w * ((lse - zl) * wl + (lse - zr) * wr)));   // gfocal_loss.py:159-165
+      if (side == 0) {
+        ws.pos_score[(size_t)n * g.A + a] = iou;                                              // :289-292
+        atomicAdd(&s_acc[l], (double)(w * (1.0f - giou)));                                   // iou_loss.py:124-126
+        atomicAdd(&s_acc[2 * kLevels], (double)w);
+      }
+    }
+  } else if (on) {
+    // d(1 - giou) / d(px1, py1, px2, py2), then through distance2bbox to this side's distance
+    const float g_uni = (inter / (uni * uni) - 1.0f / enc) * pick_gt(uni_raw, 1e-6f);
+    const float g_int = -1.0f / uni - g_uni;
+    const float g_enc = (uni / (enc * enc)) * pick_gt(enc_raw, 1e-6f);
+    const float g_iw = g_int * ih * (iw_raw >= 0.f ? 1.f : 0.f);
+    const float g_ih = g_int * iw * (ih_raw >= 0.f ? 1.f : 0.f);
+    const float g_ew = g_enc * eh * (ew_raw >= 0.f ? 1.f : 0.f);
+    const float g_eh = g_enc * ew * (eh_raw >= 0.f ? 1.f : 0.f);
+    const float hgt = py2 - py1, wid = px2 - px1;
+    float gd;
+    if (side == 0) gd = g_uni * hgt + g_iw * pick_gt(px1, tx1) + g_ew * pick_gt(tx1, px1);        // -d/dx1
+    else if (side == 1) gd = g_uni * wid + g_ih * pick_gt(py1, ty1) + g_eh * pick_gt(ty1, py1);  // -d/dy1
+    else if (side == 2) gd = g_uni * hgt + g_iw * pick_gt(tx2, px2) + g_ew * pick_gt(px2, tx2);  // d/dx2
+    else gd = g_uni * wid + g_ih * pick_gt(ty2, py2) + g_eh * pick_gt(py2, ty2);                  // d/dy2
+    const float cb = upstream_of(A.upstream, acc_bbox(l)) * g.w_bbox / (1.0f + kEps32) / avg2 * w * gd;
+    const float cd = upstream_of(A.upstream, acc_dfl(l)) * g.w_dfl / 4.0f / avg2 * w;
+    float* row = ws.pos_rows + ((size_t)n * g.pos_cap + p) * kBoxCh + side * kBins;
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) {
+      const float pj = z[j] * inv;
+      float gr = cb * pj * ((float)j - dmine);
+      gr += cd * (wl * (pj - (j == yl ? 1.f : 0.f)) + wr * (pj - (j == yl + 1 ? 1.f : 0.f)));
+      row[j] = gr;
+    }
+  } else if (GRAD && live) {   // assigned to a GT whose label lies outside the new-class range: no box loss
+    float* row = ws.pos_rows + ((size_t)n * g.pos_cap + p) * kBoxCh + side * kBins;
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) row[j] = 0.f;
+  }
+}
+
 template <bool GRAD>
 __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, PosArgs A) {
   if (GRAD && A.skip_flag && *A.skip_flag == 0u) return;
@@ -116,115 +229,9 @@ __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, P
   // whole warps stay together (8 positives per warp) so the quad shuffles are convergent
   for (int p = (blockIdx.x * kPosThreads + threadIdx.x) >> 2; p < ((np + 7) & ~7) && p < g.pos_cap;
        p += (gridDim.x * kPosThreads) >> 2) {
-    // Dependent memory round trips are what this kernel costs (it runs beside DRAM-saturating
-    // sweeps), so everything past the list entry is issued as one independent batch of loads.
     const bool live = p < np;
     const int2 ent = live ? ws.pos_list[(size_t)n * g.A + p] : make_int2(0, 0);
-    const int a = ent.x, gidx = ent.y;
-    const int l = level_of_anchor(g, a);
-    const int HW = g.hw[l];
-    const int hw = a - g.start[l];
-    const float* bplane = A.s_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW + hw;
-    float z[kBins];
-#pragma unroll
-    for (int j = 0; j < kBins; ++j) z[j] = live ? __ldg(bplane + (size_t)j * HW) : 0.f;
-    // weight_targets: max_c sigmoid(new-class logits), detached (:283-284)
-    float mx = -INFINITY;
-    if (live) {
-      const float* cplane = A.s_cls.p[l] + ((size_t)n * g.C + g.ori) * HW + hw;
-      for (int c = side; c < g.cn; c += 4) mx = fmaxf(mx, __ldg(cplane + (size_t)c * HW));
-    }
-    const long long lab = live ? A.gt_labels[gidx] : -1;
-    const float4 gb = live ? *reinterpret_cast<const float4*>(A.gt_boxes + (size_t)gidx * 4) : make_float4(0, 0, 1, 1);
-    const bool on = live && lab >= 0 && lab < g.cn;                     // gfl_head_increment_erd.py:273-274
-    mx = quad_max(mx);
-    const float w = on ? sigmoid_ref(mx) : 0.f;
-    // DFL target of this side: bbox2distance clamped to [0, reg_max - 0.1] (transforms.py:221-230)
-    const float fs = (float)g.stride[l];
-    const float cx = (float)(hw % g.w[l]), cy = (float)(hw / g.w[l]);
-    const float tx1 = gb.x / fs, ty1 = gb.y / fs, tx2 = gb.z / fs, ty2 = gb.w / fs;   // :288
-    const float tgt = side == 0 ? cx - tx1 : side == 1 ? cy - ty1 : side == 2 ? tx2 - cx : ty2 - cy;
-    const float y = fminf(fmaxf(tgt, 0.f), (float)(kBins - 1) - 0.1f);
-    const int yl = (int)y;
-    const float wl = (float)(yl + 1) - y, wr = y - (float)yl;
-    float zl = 0.f, zr = 0.f;   // the two logits the DFL cross-entropy reads
-#pragma unroll
-    for (int j = 0; j < kBins; ++j) {
-      zl = j == yl ? z[j] : zl;
-      zr = j == yl + 1 ? z[j] : zr;
-    }
-    // Integral of this thread's side: softmax expectation (:40-54,285)
-    float zm = z[0];
-#pragma unroll
-    for (int j = 1; j < kBins; ++j) zm = fmaxf(zm, z[j]);
-    float sum = 0.f, num = 0.f;
-#pragma unroll
-    for (int j = 0; j < kBins; ++j) {
-      z[j] = expf(z[j] - zm);
-      sum += z[j];
-      num = fmaf((float)j, z[j], num);
-    }
-    const float inv = 1.0f / sum;
-    const float dmine = num * inv;
-    float d[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) d[s] = __shfl_sync(0xffffffffu, dmine, (threadIdx.x & 28) | s, 32);
-    // anchor centre / stride is the grid coordinate itself (gfl_head.py:232-243, :281)
-    const float px1 = cx - d[0], py1 = cy - d[1], px2 = cx + d[2], py2 = cy + d[3];   // distance2bbox
-    // aligned IoU / GIoU (bbox_overlaps.py:151-169,189-199), eps 1e-6
-    const float area_p = (px2 - px1) * (py2 - py1);
-    const float area_t = (tx2 - tx1) * (ty2 - ty1);
-    const float iw_raw = fminf(px2, tx2) - fmaxf(px1, tx1), ih_raw = fminf(py2, ty2) - fmaxf(py1, ty1);
-    const float iw = fmaxf(iw_raw, 0.f), ih = fmaxf(ih_raw, 0.f);
-    const float inter = iw * ih;
-    const float uni_raw = area_p + area_t - inter;
-    const float uni = fmaxf(uni_raw, 1e-6f);
-    const float iou = inter / uni;
-    const float ew_raw = fmaxf(px2, tx2) - fminf(px1, tx1), eh_raw = fmaxf(py2, ty2) - fminf(py1, ty1);
-    const float ew = fmaxf(ew_raw, 0.f), eh = fmaxf(eh_raw, 0.f);
-    const float enc_raw = ew * eh;
-    const float enc = fmaxf(enc_raw, 1e-6f);
-    if (!GRAD) {
-      if (on) {
-        const float giou = iou - (enc - uni) / enc;
-        const float lse = zm + logf(sum);
-        atomicAdd(&s_acc[kLevels + l], (double)(w * ((lse - zl) * wl + (lse - zr) * wr)));   // gfocal_loss.py:159-165
-        if (side == 0) {
-          ws.pos_score[(size_t)n * g.A + a] = iou;                                              // :289-292
-          atomicAdd(&s_acc[l], (double)(w * (1.0f - giou)));                                   // iou_loss.py:124-126
-          atomicAdd(&s_acc[2 * kLevels], (double)w);
-        }
-      }
-    } else if (on) {
-      // d(1 - giou) / d(px1, py1, px2, py2), then through distance2bbox to this side's distance
-      const float g_uni = (inter / (uni * uni) - 1.0f / enc) * pick_gt(uni_raw, 1e-6f);
-      const float g_int = -1.0f / uni - g_uni;
-      const float g_enc = (uni / (enc * enc)) * pick_gt(enc_raw, 1e-6f);
-      const float g_iw = g_int * ih * (iw_raw >= 0.f ? 1.f : 0.f);
-      const float g_ih = g_int * iw * (ih_raw >= 0.f ? 1.f : 0.f);
-      const float g_ew = g_enc * eh * (ew_raw >= 0.f ? 1.f : 0.f);
-      const float g_eh = g_enc * ew * (eh_raw >= 0.f ? 1.f : 0.f);
-      const float hgt = py2 - py1, wid = px2 - px1;
-      float gd;
-      if (side == 0) gd = g_uni * hgt + g_iw * pick_gt(px1, tx1) + g_ew * pick_gt(tx1, px1);        // -d/dx1
-      else if (side == 1) gd = g_uni * wid + g_ih * pick_gt(py1, ty1) + g_eh * pick_gt(ty1, py1);  // -d/dy1
-      else if (side == 2) gd = g_uni * hgt + g_iw * pick_gt(tx2, px2) + g_ew * pick_gt(px2, tx2);  // d/dx2
-      else gd = g_uni * wid + g_ih * pick_gt(ty2, py2) + g_eh * pick_gt(py2, ty2);                  // d/dy2
-      const float cb = upstream_of(A.upstream, acc_bbox(l)) * g.w_bbox / (1.0f + kEps32) / avg2 * w * gd;
-      const float cd = upstream_of(A.upstream, acc_dfl(l)) * g.w_dfl / 4.0f / avg2 * w;
-      float* row = ws.pos_rows + ((size_t)n * g.pos_cap + p) * kBoxCh + side * kBins;
-#pragma unroll
-      for (int j = 0; j < kBins; ++j) {
-        const float pj = z[j] * inv;
-        float gr = cb * pj * ((float)j - dmine);
-        gr += cd * (wl * (pj - (j == yl ? 1.f : 0.f)) + wr * (pj - (j == yl + 1 ? 1.f : 0.f)));
-        row[j] = gr;
-      }
-    } else if (GRAD && live) {   // assigned to a GT whose label lies outside the new-class range: no box loss
-      float* row = ws.pos_rows + ((size_t)n * g.pos_cap + p) * kBoxCh + side * kBins;
-#pragma unroll
-      for (int j = 0; j < kBins; ++j) row[j] = 0.f;
-    }
+    pos_item<GRAD>(g, ws, A, n, live, ent.x, ent.y, p, side, s_acc, avg2);
   }
   if (GRAD) return;
   __syncthreads();
@@ -252,6 +259,83 @@ __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, P
     for (int i = 0; i < g.n_img; ++i) cnt += max(A.num_pos[i], 1);
     A.avg[0] = (float)cnt;
     ws.counters[0] = 0u;
+  }
+}
+
+// ATSS decode + positives prepass in ONE launch (erd_step_prepare): the student-side chain in
+// front of the sweeps is a sequence of short latency-bound kernels, so every launch boundary
+// and every list round trip removed from it moves the sweeps earlier.  Per anchor like
+// atss_finalize_kernel; a warp that found positives then works them off eight at a time
+// (lane = positive-in-batch x side) with the body of pos_kernel<false>.  The last block
+// publishes num_pos and both avg factors.
+constexpr int kAssignPer = 4;   // anchors per thread: the whole grid is one wave
+
+__global__ void __launch_bounds__(256) assign_prepass_kernel(Geo g, Workspace ws, PosArgs A,
+                                                             const int32_t* __restrict__ pad_hw,
+                                                             int32_t* __restrict__ gt_inds,
+                                                             int32_t* __restrict__ num_pos) {
+  const int n = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  __shared__ double s_acc[2 * kLevels + 1];
+  if (threadIdx.x < 2 * kLevels + 1) s_acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  // one batch of independent loads: the argmax-table entries of this thread's anchors
+  const int a0 = blockIdx.x * (256 * kAssignPer) + threadIdx.x;
+  unsigned long long key[kAssignPer];
+#pragma unroll
+  for (int i = 0; i < kAssignPer; ++i) {
+    const int a = a0 + i * 256;
+    key[i] = a < g.A ? ws.atss_key[(size_t)n * g.A + a] : 0ull;
+  }
+  const int pad_h = pad_hw[n * 2], pad_w = pad_hw[n * 2 + 1], first_gt = A.gt_offsets[n];
+#pragma unroll
+  for (int i = 0; i < kAssignPer; ++i) {
+    const int a = a0 + i * 256;
+    const int gidx = a < g.A ? atss_decode_key(g, ws, pad_h, pad_w, first_gt, gt_inds, n, a, key[i]) : -1;
+    unsigned todo = __ballot_sync(0xffffffffu, gidx >= 0);
+    while (todo) {   // warp-uniform
+      // the (lane >> 2)-th positive still to do, if there is one
+      unsigned m = todo;
+      for (int k = 0; k < (lane >> 2); ++k) m &= m - 1;
+      const bool live = m != 0;
+      const int src = live ? __ffs(m) - 1 : 0;
+      const int pa = __shfl_sync(0xffffffffu, a, src);
+      const int pg = __shfl_sync(0xffffffffu, gidx, src);
+      pos_item<false>(g, ws, A, n, live, live ? pa : 0, live ? pg : 0, 0, lane & 3, s_acc, 1.0f);
+      for (int k = 0; k < 8 && todo; ++k) todo &= todo - 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kLevels + 1 && s_acc[threadIdx.x] != 0.0)
+    atomicAdd(ws.pre_acc + threadIdx.x, s_acc[threadIdx.x]);
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(ws.counters + 3, 1u) == gridDim.x * gridDim.y - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 2 * kLevels + 1) {
+    const double v = ((volatile double*)ws.pre_acc)[threadIdx.x];
+    ws.pre_pub[threadIdx.x] = v;
+    ws.pre_acc[threadIdx.x] = 0.0;
+    if (threadIdx.x == 2 * kLevels) A.avg[1] = (float)v;
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 64) {   // avg[0] = sum_img max(num_pos, 1) (sampling_result.py:96-100)
+    long long cnt = 0;
+    for (int i = lane; i < g.n_img; i += 32) {
+      const int np = ((volatile int*)ws.pos_counter)[i];
+      num_pos[i] = np;
+      ws.pos_counter[i] = 0;
+      cnt += max(np, 1);
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) {
+      A.avg[0] = (float)cnt;
+      ws.counters[3] = 0u;
+    }
   }
 }
 
@@ -365,229 +449,198 @@ __global__ void __launch_bounds__(kTileThreads) cls_sweep_kernel(Geo g, Workspac
   }
 }
 
-// ----------------------------------------------------------------------------- box distillation rows
+// ----------------------------------------------------------------------------- box distillation
 // DFL-distribution distillation (KL at temperature T between student and teacher box
-// distributions, weighted by the student's max old-class score; :204-221, kd_loss.py:12-37)
-// for EVERY ERS box candidate, four threads per candidate (one per side), all loads in flight
-// at once.  It depends only on the selection, so it runs beside the NMS; the box sweep later
-// merges the rows of the candidates the NMS kept.  Rows hold w * (p_s - p_t); the constant
-// factor (upstream, dist_loss_weight, loss weight, T) is applied at merge time.
-constexpr int kKdThreads = 256;
-
-__global__ void __launch_bounds__(kKdThreads) kd_rows_kernel(Geo g, Workspace ws, Ptr5 s_cls, Ptr5 s_box, Ptr5 t_box,
-                                                             const int32_t* __restrict__ box_inds,
-                                                             const int32_t* __restrict__ box_count) {
-  const int n = blockIdx.y;
-  const int side = threadIdx.x & 3;
-  const int K = box_count[n];
+// distributions, weighted by the student's max old-class score; :204-221, kd_loss.py:12-37).
+// Only the NMS survivors carry it (a few dozen anchors per image at iou_threshold 0.005), so it
+// is computed where their gradient rows are written instead of for every ERS candidate.
+//
+// One side (17 bins) of one anchor: returns sum_j p_t (log p_t - log p_s) and fills
+// row[j] = w * (p_s - p_t); the constant factor (upstream, dist_loss_weight, loss weight, T) is
+// applied by the caller.
+__device__ __forceinline__ float kd_side(const Geo& g, const LossArgs& A, int n, int l, int hw, int side, float w,
+                                         float* row) {
+  const int HW = g.hw[l];
   const float inv_T = 1.0f / g.T;
-  for (int r = (blockIdx.x * kKdThreads + threadIdx.x) >> 2; r < ((K + 7) & ~7); r += (gridDim.x * kKdThreads) >> 2) {
-    const bool on = r < K;
-    const int a = on ? box_inds[(size_t)n * g.sel_cap + r] : 0;
-    const int l = level_of_anchor(g, a);
-    const int HW = g.hw[l];
-    const int hw = a - g.start[l];
-    float mx = -INFINITY;
-    if (on) {
-      const float* cplane = s_cls.p[l] + (size_t)n * g.C * HW + hw;
-      for (int c = side; c < g.ori; c += 4) mx = fmaxf(mx, __ldg(cplane + (size_t)c * HW));
-    }
-    mx = quad_max(mx);
-    const float w = sigmoid_ref(mx);                                               // :217-218
-    const size_t off = ((size_t)n * kBoxCh + side * kBins) * HW + hw;
-    const float* sp = s_box.p[l] + off;
-    const float* tp = t_box.p[l] + off;
-    float zs[kBins], zt[kBins];
+  const size_t off = ((size_t)n * kBoxCh + side * kBins) * HW + hw;
+  const float* sp = A.s_box.p[l] + off;
+  const float* tp = A.t_box.p[l] + off;
+  float zs[kBins], zt[kBins];
 #pragma unroll
-    for (int j = 0; j < kBins; ++j) {
-      zs[j] = on ? __ldg(sp + (size_t)j * HW) * inv_T : 0.f;
-      zt[j] = on ? __ldg(tp + (size_t)j * HW) * inv_T : 0.f;
-    }
-    float ms = zs[0], mt = zt[0];
-#pragma unroll
-    for (int j = 1; j < kBins; ++j) { ms = fmaxf(ms, zs[j]); mt = fmaxf(mt, zt[j]); }
-    float ss = 0.f, st = 0.f;
-#pragma unroll
-    for (int j = 0; j < kBins; ++j) {
-      zs[j] -= ms;
-      zt[j] -= mt;
-      ss += expf(zs[j]);
-      st += expf(zt[j]);
-    }
-    const float lss = logf(ss), lst = logf(st);
-    float kl = 0.f;
-    float* row = ws.kd_rows + ((size_t)n * g.sel_cap + r) * kBoxCh + side * kBins;
-#pragma unroll
-    for (int j = 0; j < kBins; ++j) {
-      const float lps = zs[j] - lss, lpt = zt[j] - lst;
-      const float ps = expf(lps), pt = expf(lpt);
-      if (pt > 0.f) kl += pt * (lpt - lps);
-      if (on) row[j] = w * (ps - pt);
-    }
-    kl += __shfl_xor_sync(0xffffffffu, kl, 1);
-    kl += __shfl_xor_sync(0xffffffffu, kl, 2);
-    if (on && side == 0) ws.kd_loss[(size_t)n * g.sel_cap + r] = w * (kl / (float)kBins * (g.T * g.T));   // .mean(1) * T*T
+  for (int j = 0; j < kBins; ++j) {
+    zs[j] = __ldg(sp + (size_t)j * HW) * inv_T;
+    zt[j] = __ldg(tp + (size_t)j * HW) * inv_T;
   }
+  float ms = zs[0], mt = zt[0];
+#pragma unroll
+  for (int j = 1; j < kBins; ++j) { ms = fmaxf(ms, zs[j]); mt = fmaxf(mt, zt[j]); }
+  float ss = 0.f, st = 0.f;
+#pragma unroll
+  for (int j = 0; j < kBins; ++j) {
+    zs[j] -= ms;
+    zt[j] -= mt;
+    ss += expf(zs[j]);
+    st += expf(zt[j]);
+  }
+  const float lss = logf(ss), lst = logf(st);
+  float kl = 0.f;
+#pragma unroll
+  for (int j = 0; j < kBins; ++j) {
+    const float lps = zs[j] - lss, lpt = zt[j] - lst;
+    const float ps = expf(lps), pt = expf(lpt);
+    if (pt > 0.f) kl += pt * (lpt - lps);
+    row[j] = w * (ps - pt);
+  }
+  return kl;
+}
+
+// this thread's share (channels first, first + step, ...) of max_c over the old-class logits
+__device__ __forceinline__ float kd_weight_part(const Geo& g, const LossArgs& A, int n, int l, int hw, int first,
+                                                int step) {
+  const int HW = g.hw[l];
+  const float* cplane = A.s_cls.p[l] + (size_t)n * g.C * HW + hw;
+  float mx = -INFINITY;
+  for (int c = first; c < g.ori; c += step) mx = fmaxf(mx, __ldg(cplane + (size_t)c * HW));
+  return mx;
 }
 
 // ----------------------------------------------------------------------------- box sweep
-// grid (tile, image, side).  Every box-logit gradient element is written exactly once, densely:
-// zero, plus the compact row of a positive (pos_kernel<true>), plus the distillation row of an
-// NMS survivor (kd_rows_kernel, marked by the NMS resolve pass).
-//
-// MODE 0: everything in one launch.  MODE 1 ("early", runs beside the NMS): only the groups
-// that hold no ERS box candidate, i.e. whose result cannot depend on the NMS; the remaining
-// groups are written after the NMS by box_late_kernel, one warp per candidate.  On 16 B aligned
-// levels a group is 8 consecutive anchors = one 32 B sector per channel, so the two launches
-// never share a sector; on the other levels (a few % of the anchors) a group is one anchor.
-template <bool VEC, int MODE>
+// grid (tile, image, side).  Every box-logit gradient element of an anchor that is NOT an ERS
+// box candidate is written here, once: zero, or the compact row of a positive
+// (pos_kernel<true>).  The candidates (a few % of the anchors) belong to box_kd_kernel, which
+// runs concurrently: the two kernels never write the same element.
+template <bool VEC>
 __device__ __forceinline__ void box_tile(const Geo& g, const Workspace& ws, const LossArgs& A, int n, int l,
-                                         int hw0, int side, float& kd_loss) {
+                                         int hw0, int side) {
   const int HW = g.hw[l];
   Quad<VEC> q(hw0, HW);
   const size_t abase = (size_t)n * g.A + g.start[l];
   const float* prow[4];
-  const float* krow[4];
   bool any = false, cand = false;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     prow[k] = nullptr;
-    krow[k] = nullptr;
     if (!q.ok[k]) continue;
     const size_t a = abase + q.hw[k];
-    const unsigned flags = A.sel_flags[a];
-    cand |= (flags & 2) != 0;
-    if (!VEC && MODE == 1 && (flags & 2)) { q.ok[k] = false; continue; }   // scalar levels: groups are single anchors
-    if (MODE != 1 && (flags & 4)) {
-      const size_t slot = (size_t)n * g.sel_cap + ws.kd_slot[a];
-      krow[k] = ws.kd_rows + slot * kBoxCh + side * kBins;
-      if (side == 0) kd_loss += ws.kd_loss[slot];
+    if (A.sel_flags[a] & 2) {   // candidate: not ours
+      cand = true;
+      q.ok[k] = false;
+      continue;
     }
     if (A.gt_inds[a] > 0)
       prow[k] = ws.pos_rows + ((size_t)n * g.pos_cap + ws.pos_slot[a]) * kBoxCh + side * kBins;
-    any |= prow[k] != nullptr || krow[k] != nullptr;
-  }
-  if (VEC && MODE != 0) {
-    const int neighbour = __shfl_xor_sync(0xffffffffu, cand ? 1 : 0, 1);   // every lane takes part
-    const bool group = cand || neighbour != 0;
-    if ((MODE == 1) == group) return;
+    any |= prow[k] != nullptr;
   }
   float* gbox = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW;
+  if (VEC && cand) {   // a 16 B group holding a candidate: element-wise stores around it
+    for (int j = 0; j < kBins; ++j) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (q.ok[k]) gbox[(size_t)j * HW + q.hw[k]] = prow[k] ? prow[k][j] : 0.f;
+    }
+    return;
+  }
   if (!any) {
 #pragma unroll
     for (int j = 0; j < kBins; ++j) q.store_zero(gbox + (size_t)j * HW);
     return;
   }
-  const float kT = g.T;
-  const float scale = upstream_of(A.upstream, acc_dbox(g, n)) * A.dlw * g.w_ld / 4.0f * (kT * kT / (float)kBins) / kT;
   for (int j = 0; j < kBins; ++j) {
     float v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = 0.f;
-      if (prow[k]) v[k] += prow[k][j];
-      if (krow[k]) v[k] = fmaf(scale, krow[k][j], v[k]);
-    }
+    for (int k = 0; k < 4; ++k) v[k] = prow[k] ? prow[k][j] : 0.f;
     q.store(gbox + (size_t)j * HW, v);
   }
 }
 
-template <int MODE>
 __global__ void __launch_bounds__(kTileThreads) box_sweep_kernel(Geo g, Workspace ws, LossArgs A) {
   if (A.skip_flag && *A.skip_flag == 0u) return;
   const int n = blockIdx.y;
   const int tile = blockIdx.x;
   const int l = level_of_tile(g, tile);
   const int hw0 = (tile - g.tile_start[l]) * kTile;
-  float kd = 0.f;
   if (g.vec[l])
-    box_tile<true, MODE>(g, ws, A, n, l, hw0, blockIdx.z, kd);
+    box_tile<true>(g, ws, A, n, l, hw0, blockIdx.z);
   else
-    box_tile<false, MODE>(g, ws, A, n, l, hw0, blockIdx.z, kd);
-  if (MODE == 1) return;
-  __shared__ float red[kTileThreads / 32];
+    box_tile<false>(g, ws, A, n, l, hw0, blockIdx.z);
+}
+
+// Box-logit gradients of the ERS box candidates, list driven: four threads per candidate, one
+// per box side, all loads in flight at once.  The distillation only counts for the candidates
+// the teacher NMS keeps, which is not known yet: this kernel runs BESIDE the NMS and writes
+// every candidate as if kept -- (positive's row, if it is one) + the KL gradient, and the
+// candidate's weighted KL into ws.kd_loss -- and box_fix_kernel takes the suppressed ones back
+// afterwards.  (Its ~64 B-per-element NCHW gathers are the expensive part and overlap the
+// latency-bound NMS chain this way, whatever fraction the NMS ends up keeping.)
+constexpr int kLateThreads = 256;
+
+__global__ void __launch_bounds__(kLateThreads) box_kd_kernel(Geo g, Workspace ws, LossArgs A) {
+  if (A.skip_flag && *A.skip_flag == 0u) return;
+  const int n = blockIdx.y;
+  const int side = threadIdx.x & 3;
+  const int K = A.box_count[n];
+  const float kT = g.T;
+  const float scale = upstream_of(A.upstream, acc_dbox(g, n)) * A.dlw * g.w_ld / 4.0f * (kT * kT / (float)kBins) / kT;
+  // whole warps stay together (8 candidates per warp) so the quad shuffles are convergent
+  for (int r = (blockIdx.x * kLateThreads + threadIdx.x) >> 2; r < ((K + 7) & ~7);
+       r += (gridDim.x * kLateThreads) >> 2) {
+    const bool on = r < K;
+    const int a = on ? A.box_inds[(size_t)n * g.sel_cap + r] : 0;
+    const int l = level_of_anchor(g, a);
+    const int HW = g.hw[l];
+    const int hw = a - g.start[l];
+    const size_t ga = (size_t)n * g.A + a;
+    const bool pos = on && A.gt_inds[ga] > 0;
+    const int slot = pos ? ws.pos_slot[ga] : 0;
+    float mx = on ? kd_weight_part(g, A, n, l, hw, side, 4) : 0.f;
+    mx = quad_max(mx);
+    const float w = sigmoid_ref(mx);                                               // :217-218
+    float row[kBins];
+    float kl = 0.f;
+    if (on) kl = kd_side(g, A, n, l, hw, side, w, row);
+    kl += __shfl_xor_sync(0xffffffffu, kl, 1);
+    kl += __shfl_xor_sync(0xffffffffu, kl, 2);
+    if (!on) continue;
+    if (side == 0) ws.kd_loss[(size_t)n * g.sel_cap + r] = w * (kl / (float)kBins * (kT * kT));   // .mean(1) * T*T
+    const float* prow = pos ? ws.pos_rows + ((size_t)n * g.pos_cap + slot) * kBoxCh + side * kBins : nullptr;
+    float* gp = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW + hw;
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) gp[(size_t)j * HW] = fmaf(scale, row[j], prow ? prow[j] : 0.f);
+  }
+}
+
+// After the NMS: sum the weighted KL of the survivors (flag bit 2 set by the resolve pass) and
+// rewrite the gradient of the suppressed candidates without the distillation term.
+__global__ void __launch_bounds__(kLateThreads) box_fix_kernel(Geo g, Workspace ws, LossArgs A) {
+  if (A.skip_flag && *A.skip_flag == 0u) return;
+  const int n = blockIdx.y;
+  const int side = threadIdx.x & 3;
+  const int K = A.box_count[n];
+  float kd = 0.f;
+  for (int r = (blockIdx.x * kLateThreads + threadIdx.x) >> 2; r < K; r += (gridDim.x * kLateThreads) >> 2) {
+    const int a = A.box_inds[(size_t)n * g.sel_cap + r];
+    const size_t ga = (size_t)n * g.A + a;
+    if (A.sel_flags[ga] & 4) {
+      if (side == 0) kd += ws.kd_loss[(size_t)n * g.sel_cap + r];
+      continue;
+    }
+    const int l = level_of_anchor(g, a);
+    const int HW = g.hw[l];
+    const int hw = a - g.start[l];
+    const float* prow = nullptr;
+    if (A.gt_inds[ga] > 0) prow = ws.pos_rows + ((size_t)n * g.pos_cap + ws.pos_slot[ga]) * kBoxCh + side * kBins;
+    float* gp = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW + hw;
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) gp[(size_t)j * HW] = prow ? prow[j] : 0.f;
+  }
+  __shared__ float red[kLateThreads / 32];
   kd = warp_sum(kd);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = kd;
   __syncthreads();
   if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < kTileThreads / 32; ++w) s += (double)red[w];
-    if (s != 0.0) atomicAdd(ws.loss_acc + acc_dbox(g, n), s);
-  }
-}
-
-// Late box gradients, list driven: one warp per ERS box candidate writes the whole group the
-// candidate lives in (lane = anchor-in-group x side), merging positives' rows and, where the
-// NMS kept the anchor, its distillation row.  A group shared by several candidates is written
-// by the warp of its first candidate only.
-constexpr int kLateThreads = 256;
-
-__device__ __forceinline__ void finalize_one(const Geo& g, const Workspace& ws, const LossArgs& A, int i);
-
-__global__ void __launch_bounds__(kLateThreads) box_late_kernel(Geo g, Workspace ws, LossArgs A,
-                                                                const int32_t* __restrict__ box_count) {
-  if (A.skip_flag && *A.skip_flag == 0u) return;
-  const int n = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int K = box_count[n];
-  const float kT = g.T;
-  const float scale = upstream_of(A.upstream, acc_dbox(g, n)) * A.dlw * g.w_ld / 4.0f * (kT * kT / (float)kBins) / kT;
-  float kd = 0.f;
-  for (int r = blockIdx.x * (kLateThreads / 32) + warp; r < K; r += gridDim.x * (kLateThreads / 32)) {
-    const int a = A.box_inds[(size_t)n * g.sel_cap + r];
-    const int l = level_of_anchor(g, a);
-    const int HW = g.hw[l];
-    const int hw = a - g.start[l];
-    const size_t abase = (size_t)n * g.A + g.start[l];
-    const bool vec = g.vec[l] != 0;
-    const int g0 = vec ? (hw & ~7) : hw;
-    const int k = vec ? (lane & 7) : 0;
-    const int side = vec ? (lane >> 3) : lane;
-    const int hwk = g0 + k;
-    const bool live = hwk < HW && side < 4;
-    const unsigned flags = live ? A.sel_flags[abase + hwk] : 0u;
-    if (vec) {   // the first candidate of the group owns it
-      const unsigned cands = __ballot_sync(0xffffffffu, (flags & 2) != 0) & 0xffu;
-      if (g0 + __ffs(cands) - 1 != hw) continue;
-    }
-    if (!live) continue;
-    const float* prow = nullptr;
-    const float* krow = nullptr;
-    if (A.gt_inds[abase + hwk] > 0)
-      prow = ws.pos_rows + ((size_t)n * g.pos_cap + ws.pos_slot[abase + hwk]) * kBoxCh + side * kBins;
-    if (flags & 4) {
-      const size_t slot = (size_t)n * g.sel_cap + ws.kd_slot[abase + hwk];
-      krow = ws.kd_rows + slot * kBoxCh + side * kBins;
-      if (side == 0) kd += ws.kd_loss[slot];
-    }
-    float* gp = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW + hwk;
-#pragma unroll
-    for (int j = 0; j < kBins; ++j) {
-      float v = 0.f;
-      if (prow) v = prow[j];
-      if (krow) v = fmaf(scale, krow[j], v);
-      gp[(size_t)j * HW] = v;
-    }
-  }
-  __shared__ float red[kLateThreads / 32];
-  kd = warp_sum(kd);
-  if (lane == 0) red[warp] = kd;
-  __syncthreads();
-  __shared__ bool last;
-  if (threadIdx.x == 0) {
     double s2 = 0.0;
     for (int w = 0; w < kLateThreads / 32; ++w) s2 += (double)red[w];
     if (s2 != 0.0) atomicAdd(ws.loss_acc + acc_dbox(g, n), s2);
-    // the last block to finish turns the accumulators into the loss vector (saves a launch at
-    // the very end of the step's critical path)
-    __threadfence();
-    last = atomicAdd(ws.counters + 2, 1u) == gridDim.x * gridDim.y - 1;
-  }
-  __syncthreads();
-  if (last) {
-    __threadfence();
-    finalize_one(g, ws, A, threadIdx.x);
-    if (threadIdx.x == 0) ws.counters[2] = 0u;
   }
 }
 
@@ -650,19 +703,28 @@ cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, con
   return cudaGetLastError();
 }
 
-cudaError_t launch_kd_rows(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box, const Ptr5& t_box,
-                           const int32_t* box_inds, const int32_t* box_count, cudaStream_t st) {
-  ERD_LAUNCH(kKKdRows, st,
-             (kd_rows_kernel<<<dim3(16, g.n_img), kKdThreads, 0, st>>>(g, ws, s_cls, s_box, t_box, box_inds, box_count)));
+cudaError_t launch_assign_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
+                              const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                              const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos, float* avg, cudaStream_t st) {
+  cudaError_t e = launch_atss_candidates(g, ws, gt_boxes, gt_offsets, pad_hw, st);
+  if (e != cudaSuccess) return e;
+  PosArgs a;
+  a.s_cls = s_cls;
+  a.s_box = s_box;
+  for (int l = 0; l < kLevels; ++l) a.g_box.p[l] = nullptr;
+  a.gt_boxes = gt_boxes;
+  a.gt_labels = gt_labels;
+  a.gt_offsets = gt_offsets;
+  a.gt_inds = gt_inds;
+  a.num_pos = num_pos;
+  a.avg = avg;
+  a.upstream = nullptr;
+  a.skip_flag = nullptr;
+  ERD_LAUNCH(kKAvg, st,
+             (assign_prepass_kernel<<<dim3((g.A + 256 * kAssignPer - 1) / (256 * kAssignPer), g.n_img), 256, 0, st>>>(g, ws, a, pad_hw, gt_inds, num_pos)));
   return cudaGetLastError();
 }
 
-// Sequence on the caller's stream `st`.  With helper streams (erd_step_prepare's context):
-//   st    : QFL sweep (needs only assignment + avg factors) -> wait selection -> class-response
-//           sweep -> wait early/NMS/KD -> late box kernel -> finalize
-//   early : wait selection -> positives' rows -> box sectors that cannot depend on the NMS
-// so the bandwidth-bound sweeps overlap the latency-bound ERS / NMS chain instead of queueing
-// behind it.
 cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, const LossStreams* ls) {
   const int total = 3 * kLevels + 2 * g.n_img;
   cudaError_t e = cudaSuccess;   // accumulators are left clean by the previous finalize (erd_workspace_init once)
@@ -680,17 +742,41 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
   p.upstream = a.upstream;
   p.skip_flag = a.skip_flag;
   const dim3 box_grid(g.tile_start[kLevels], g.n_img, 4);
+  const dim3 late_grid((g.sel_cap * 4 + kLateThreads - 1) / kLateThreads, g.n_img);
   const int parts_old = (g.ori + kSweepCh - 1) / kSweepCh, parts_new = (g.cn + kSweepCh - 1) / kSweepCh;
   const dim3 tile_grid_new(g.tile_start[kLevels], g.n_img, parts_new), tile_grid_old(g.tile_start[kLevels], g.n_img, parts_old);
+  // Box side: positives' rows -> { dense box sweep || candidates' rows with distillation } ->
+  // take-back of the candidates the NMS suppressed.  With helper streams it runs beside the
+  // class sweeps; the NMS is joined only in front of the last, list-driven launch.
+  // The two latency-bound launches go to a high-priority stream (their few CTAs must not queue
+  // behind the sweeps' thousands), the dense sweep to a low-priority one.
+  cudaStream_t hi = ls ? ls->late : st, lo = ls ? ls->early : st;
   if (ls) {
     e = cudaEventRecord(ls->fork, st);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(ls->early, ls->fork, 0);
-    if (e == cudaSuccess && ls->sel_ready) e = cudaStreamWaitEvent(ls->early, ls->sel_ready, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(hi, ls->fork, 0);
     if (e != cudaSuccess) return e;
-    ERD_LAUNCH(kKPosGrad, ls->early,
-               (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, ls->early>>>(g, ws, p)));
-    ERD_LAUNCH(kKBoxEarly, ls->early, (box_sweep_kernel<1><<<box_grid, kTileThreads, 0, ls->early>>>(g, ws, a)));
-    e = cudaEventRecord(ls->early_done, ls->early);
+  }
+  ERD_LAUNCH(kKPosGrad, hi, (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, hi>>>(g, ws, p)));
+  if (ls) {
+    e = cudaEventRecord(ls->pos_done, hi);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(lo, ls->pos_done, 0);
+    if (e != cudaSuccess) return e;
+  }
+  if (ls && ls->sel_ready) {
+    e = cudaStreamWaitEvent(lo, ls->sel_ready, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(hi, ls->sel_ready, 0);
+    if (e != cudaSuccess) return e;
+  }
+  ERD_LAUNCH(kKBoxEarly, lo, (box_sweep_kernel<<<box_grid, kTileThreads, 0, lo>>>(g, ws, a)));
+  ERD_LAUNCH(kKBoxKd, hi, (box_kd_kernel<<<late_grid, kLateThreads, 0, hi>>>(g, ws, a)));
+  if (ls) {
+    e = cudaEventRecord(ls->early_done, lo);
+    if (e == cudaSuccess && ls->nms_done) e = cudaStreamWaitEvent(hi, ls->nms_done, 0);
+    if (e != cudaSuccess) return e;
+  }
+  ERD_LAUNCH(kKBoxSweep, hi, (box_fix_kernel<<<late_grid, kLateThreads, 0, hi>>>(g, ws, a)));
+  if (ls) {
+    e = cudaEventRecord(ls->late_done, hi);
     if (e != cudaSuccess) return e;
   }
   ERD_LAUNCH(kKLossMain, st, (cls_sweep_kernel<<<tile_grid_new, kTileThreads, 0, st>>>(g, ws, a, parts_old)));
@@ -701,14 +787,8 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
   ERD_LAUNCH(kKClsOld, st, (cls_sweep_kernel<<<tile_grid_old, kTileThreads, 0, st>>>(g, ws, a, 0)));
   if (ls) {
     e = cudaStreamWaitEvent(st, ls->early_done, 0);
-    if (e == cudaSuccess && ls->nms_done) e = cudaStreamWaitEvent(st, ls->nms_done, 0);
-    if (e == cudaSuccess && ls->kd_done) e = cudaStreamWaitEvent(st, ls->kd_done, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ls->late_done, 0);
     if (e != cudaSuccess) return e;
-    ERD_LAUNCH(kKBoxSweep, st, (box_late_kernel<<<dim3(128, g.n_img), kLateThreads, 0, st>>>(g, ws, a, a.box_count)));
-    return cudaGetLastError();   // box_late's last block wrote the loss vector
-  } else {
-    ERD_LAUNCH(kKPosGrad, st, (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, st>>>(g, ws, p)));
-    ERD_LAUNCH(kKBoxSweep, st, (box_sweep_kernel<0><<<box_grid, kTileThreads, 0, st>>>(g, ws, a)));
   }
   ERD_LAUNCH(kKFinalize, st, (finalize_kernel<<<1, ((total + 31) / 32) * 32, 0, st>>>(g, ws, a)));
   return cudaGetLastError();

@@ -305,16 +305,14 @@ __global__ void __launch_bounds__(kResThreads) nms_resolve_kernel(Geo g, Workspa
     keep_count[n] = run;
   }
   __syncthreads();
-  int32_t* out = keep + (size_t)n * g.sel_cap;
+  int* out = ws.keep_raw + (size_t)n * g.sel_cap;   // score order comes later (nms_order_kernel)
   const int32_t* list = box_inds + (size_t)n * g.sel_cap;
   for (int j = threadIdx.x; j < K; j += kResThreads) {
     const int wj = j >> 6;
     const unsigned long long kw = kept[wj];
     if (!(kw & (1ull << (j & 63)))) continue;
     out[(int)dec[wj] + __popcll(kw & ((1ull << (j & 63)) - 1ull))] = j;
-    const int a = list[j];
-    ws.kd_slot[(size_t)n * g.A + a] = j;
-    sel_flags[(size_t)n * g.A + a] |= 4;
+    sel_flags[(size_t)n * g.A + list[j]] |= 4;
   }
 }
 
@@ -327,15 +325,19 @@ __global__ void __launch_bounds__(kSortThreads) nms_order_kernel(Geo g, Workspac
   extern __shared__ unsigned long long s_key[];
   const int n = blockIdx.x;
   const int M = keep_count[n];
-  if (M < 2) return;
+  int32_t* out = keep + (size_t)n * g.sel_cap;
+  const int* raw = ws.keep_raw + (size_t)n * g.sel_cap;
+  if (M < 2) {
+    if (M == 1 && threadIdx.x == 0) out[0] = raw[0];
+    return;
+  }
   int P = 1;
   while (P < M) P <<= 1;
-  int32_t* out = keep + (size_t)n * g.sel_cap;
   const float* score = ws.nms_score + (size_t)n * g.sel_cap;
   for (int r = threadIdx.x; r < P; r += kSortThreads) {
     unsigned long long key = ~0ull;
     if (r < M) {
-      const int pos = out[r];
+      const int pos = raw[r];
       key = ((unsigned long long)(~__float_as_uint(score[pos])) << 32) | (unsigned int)pos;
     }
     s_key[r] = key;

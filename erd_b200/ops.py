@@ -210,11 +210,6 @@ class ErdPath:
                                          p.keep_count.data_ptr(), p.sel_flags.data_ptr(), p.ws.data_ptr(),
                                          _stream()), 'erd_teacher_nms')
 
-    def kd_rows(self, p: Plan, s_cls, s_box, t_box):
-        N.check(self.lib.erd_kd_rows(C.byref(p.shape), _ptrs(s_cls), _ptrs(s_box), _ptrs(t_box),
-                                     p.box_inds.data_ptr(), p.box_count.data_ptr(), p.ws.data_ptr(), _stream()),
-                'erd_kd_rows')
-
     def reduce_avg(self, p: Plan):
         """reduce_mean of both normalisers in one 8-byte all-reduce (dist_utils.py:59-65)."""
         reduce_mean_(p.avg)

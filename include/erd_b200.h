@@ -138,15 +138,6 @@ int erd_teacher_nms(const ErdShape* shape, const int32_t* box_inds, const int32_
                     const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count,
                     uint8_t* sel_flags, void* ws, void* stream);
 
-/* DFL-distribution distillation rows (KL at temperature T, weighted by the student's max
- * old-class score) of every ERS box candidate; erd_loss_fwd_bwd merges the rows of the NMS
- * survivors.  Replaces the gathers, weight and loss_ld call of distill_loss_by_image_single
- * (dense_heads/gfl_head_increment_erd.py:204-221; losses/kd_loss.py:12-37).  Independent of
- * erd_teacher_nms (may run concurrently with it); both must precede erd_loss_fwd_bwd. */
-int erd_kd_rows(const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
-                const float* const* t_box, const int32_t* box_inds, const int32_t* box_count,
-                void* ws, void* stream);
-
 /* Fused forward + backward of QFL / GIoU / DFL and both distillation losses.
  * Replaces GFLHeadIncrementERD.loss_by_feat_single, distill_loss_by_image_single and the
  * glue of loss_by_feat (dense_heads/gfl_head_increment_erd.py:142-454) together with
@@ -177,11 +168,11 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
                      void* stream);
 
 /* One training-step worth of the path in two calls around the caller's all-reduce:
- * erd_step_prepare = erd_ers_select + erd_atss_assign + erd_avg_factors + erd_teacher_nms +
- * erd_kd_rows, erd_step_loss = erd_loss_fwd_bwd(ctx, ...).  Replaces GFLIncrementERD.loss
+ * erd_step_prepare = erd_ers_select + erd_atss_assign + erd_avg_factors + erd_teacher_nms,
+ * erd_step_loss = erd_loss_fwd_bwd(ctx, ...).  Replaces GFLIncrementERD.loss
  * (detectors/gfl_increment_erd.py:202-220) minus the conv stacks.
  * Only assignment and avg factors are ordered on `stream` when erd_step_prepare returns (that is
- * what the all-reduce needs); the teacher side (selection, NMS, distillation rows) keeps running
+ * what the all-reduce needs); the teacher side (selection, NMS) keeps running
  * on the context's helper streams and is joined by erd_loss_fwd_bwd(ctx, ...) where its results
  * are consumed.  A caller that reads ERS / NMS outputs itself must synchronise the device (or
  * call erd_loss_fwd_bwd first). */

@@ -14,7 +14,7 @@ losses = torch.empty(p.num_losses, device='cuda')
 nk = lib.erd_profile_num_kernels(); names = [lib.erd_profile_kernel_name(i).decode() for i in range(nk)]
 stages = [('ers_select', lambda: path.ers_select(p, b.t_cls, b.t_box)), ('atss', lambda: path.atss_assign(p)),
           ('avg', lambda: path.avg_factors(p, b.s_cls, b.s_box)), ('nms', lambda: path.teacher_nms(p)),
-          ('kd_rows', lambda: path.kd_rows(p, b.s_cls, b.s_box, b.t_box))]
+          ]
 for _, fn in stages: fn()
 torch.cuda.synchronize()
 print('counts', p.box_count.tolist()[:4], p.keep_count.tolist()[:4], p.num_pos.tolist()[:4])

@@ -63,5 +63,4 @@ def test_null_pointers_are_rejected_before_any_launch():
     assert lib.erd_ers_select(C.byref(s), nul, nul, None, None, None, None, None, None, None, None) == -2
     assert lib.erd_atss_assign(C.byref(s), None, None, None, None, None, None, None, None) == -2
     assert lib.erd_teacher_nms(C.byref(s), None, None, None, 0.005, None, None, None, None, None) == -2
-    assert lib.erd_kd_rows(C.byref(s), nul, nul, nul, None, None, None, None) == -2
     assert lib.erd_launch_count() == 0
