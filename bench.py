@@ -33,12 +33,12 @@ IMGS_PER_GPU = 16
 ORI, NUM_CLASSES, REG_MAX = 40, 80, 16
 # compulsory fp32 traffic per anchor, fwd+bwd, 40+40 split
 # per dense kernel: ers_scan reads teacher cls + box; qfl_sweep reads the student's
-# new-class logits and writes their gradients; cls_old_sweep reads student + teacher old-class logits and
-# writes the old-class gradients; box_sweep writes the box gradients (student box logits are only touched
-# at positives / ERS rows, by the small gather kernels)
+# new-class logits and writes their gradients; zero_fill writes the old-class and the box gradients (their
+# non-zero rows -- ERS rows, positives, box candidates -- are written over it by small list-driven kernels,
+# which are also the only readers of the student's old-class and box logits)
 CN = NUM_CLASSES - ORI
 BYTES_PER_ANCHOR = {'path': 1616, 'ers_scan': 4 * (ORI + 68), 'qfl_sweep': 4 * (CN + CN),
-                    'cls_old_sweep': 4 * (ORI + ORI + ORI), 'box_sweep': 4 * 68}
+                    'zero_fill': 4 * (ORI + 68)}
 
 
 def parse():
@@ -186,7 +186,7 @@ def run_ours(args):
 
     def step():
         # the two C-ABI calls around the 8-byte all-reduce; grads written into fixed buffers
-        path.prepare(plan, b.t_cls, b.t_box, b.s_cls, b.s_box)
+        path.prepare(plan, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls=g_cls, g_box=g_box)
         path.reduce_avg(plan)
         path.loss_fwd_bwd(plan, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls, g_box, losses, 1.0)
 
@@ -197,7 +197,7 @@ def run_ours(args):
 
     nk = lib.erd_profile_num_kernels()
     names = [lib.erd_profile_kernel_name(i).decode() for i in range(nk)]
-    dense = [k for k in ('ers_scan', 'qfl_sweep', 'cls_old_sweep', 'box_sweep') if k in names]
+    dense = [k for k in ('ers_scan', 'qfl_sweep', 'zero_fill') if k in names]
 
     def collect():
         tot, cnt = (C.c_float * nk)(), (C.c_int * nk)()

@@ -133,7 +133,10 @@ static MPtr5 mptr5(float* const* p) {
 
 struct ErdContext {
   cudaStream_t side[3];          // [0] early box sectors, [1] teacher chain, [2] positives' rows + late box groups
-  cudaEvent_t fork, join[3], pos_done, sel_done, early_done, nms_all;
+  cudaEvent_t fork, join[3], pos_done, sel_done, early_done, nms_all, clear_done;
+  bool clear_pending;            // gradient tensors below were zero-filled by erd_step_prepare
+  float* cleared_cls[kLevels];
+  float* cleared_box[kLevels];
   bool nms_pending;              // join[1] recorded by erd_step_prepare, not yet waited on
 };
 
@@ -181,10 +184,12 @@ int erd_create(ErdContext** ctx) {
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->pos_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->clear_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->early_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->nms_all, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sel_done, cudaEventDisableTiming);
   c->nms_pending = false;
+  c->clear_pending = false;
   if (e != cudaSuccess) {
     delete c;
     return fail_cuda(e, "erd_create");
@@ -201,6 +206,7 @@ int erd_destroy(ErdContext* c) {
   }
   cudaEventDestroy(c->fork);
   cudaEventDestroy(c->pos_done);
+  cudaEventDestroy(c->clear_done);
   cudaEventDestroy(c->early_done);
   cudaEventDestroy(c->nms_all);
   cudaEventDestroy(c->sel_done);
@@ -287,8 +293,8 @@ static int nms_on_side_stream(ErdContext* ctx, const ErdShape* shape, const ErdS
 int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const* s_cls, const float* const* s_box,
                      const float* const* t_cls, const float* const* t_box, const float* gt_boxes,
                      const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
-                     const int32_t* gt_inds, const int32_t* num_pos, const int32_t* cls_count,
-                     const uint8_t* sel_flags, const int32_t* box_inds, const int32_t* box_count,
+                     const int32_t* gt_inds, const int32_t* num_pos, const int32_t* cls_inds,
+                     const int32_t* cls_count, const uint8_t* sel_flags, const int32_t* box_inds, const int32_t* box_count,
                      const int32_t* keep,
                      const int32_t* keep_count, const float* avg, float dist_loss_weight, const float* upstream,
                      int32_t skip_if_unit_upstream, float* losses, float* const* g_cls, float* const* g_box,
@@ -297,7 +303,7 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
   int rc = make_geo(shape, &g);
   if (rc) return rc;
   if (NULLS(s_cls) || NULLS(s_box) || NULLS(t_cls) || NULLS(t_box) || NULLS(g_cls) || NULLS(g_box) || !gt_offsets ||
-      !pad_hw || !gt_inds || !num_pos || !cls_count || !sel_flags || !box_inds || !box_count || !keep || !keep_count ||
+      !pad_hw || !gt_inds || !num_pos || !cls_inds || !cls_count || !sel_flags || !box_inds || !box_count || !keep || !keep_count ||
       !avg ||
       !losses || !wsp || (g.total_gt > 0 && (!gt_boxes || !gt_labels)))
     return fail(ERD_ERR_NULL, "erd_loss_fwd_bwd: NULL argument");
@@ -318,6 +324,7 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
   a.pad_hw = pad_hw;
   a.gt_inds = gt_inds;
   a.num_pos = num_pos;
+  a.cls_inds = cls_inds;
   a.cls_count = cls_count;
   a.sel_flags = sel_flags;
   a.box_inds = box_inds;
@@ -341,6 +348,12 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
     ls.late_done = ctx->join[2];
     ls.fork = ctx->fork;
     ls.early_done = ctx->early_done;
+    // pre-cleared by erd_step_prepare only if these are the very tensors it was given
+    bool cleared = ctx->clear_pending;
+    for (int l = 0; l < kLevels && cleared; ++l)
+      cleared = ctx->cleared_cls[l] == g_cls[l] && ctx->cleared_box[l] == g_box[l];
+    ls.cleared = cleared ? ctx->clear_done : nullptr;
+    ctx->clear_pending = false;
     ls.sel_ready = ctx->nms_pending ? ctx->sel_done : nullptr;
     ls.nms_done = ctx->nms_pending ? ctx->join[1] : nullptr;
     const bool had_nms = ctx->nms_pending;
@@ -374,6 +387,25 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[1], ctx->fork, 0);
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork");
   int rc = 0;
+  // optional: zero fill of the gradient tensors now, beside the scan (low priority)
+  ctx->clear_pending = false;
+  if (b->g_cls[0] || b->g_box[0]) {
+    Geo gz;
+    rc = make_geo(shape, &gz);
+    if (rc) return rc;
+    MPtr5 zc, zb;
+    for (int l = 0; l < kLevels; ++l) {
+      if (!b->g_cls[l] || !b->g_box[l]) return fail(ERD_ERR_NULL, "erd_step_prepare: g_cls / g_box must be all set or all NULL");
+      zc.p[l] = ctx->cleared_cls[l] = b->g_cls[l];
+      zb.p[l] = ctx->cleared_box[l] = b->g_box[l];
+    }
+    set_vec(&gz, nullptr, nullptr, b->g_cls, b->g_box);
+    e = cudaStreamWaitEvent(ctx->side[0], ctx->fork, 0);
+    if (e == cudaSuccess) e = launch_zero_fill(gz, zc, zb, nullptr, ctx->side[0]);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->clear_done, ctx->side[0]);
+    if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare zero fill");
+    ctx->clear_pending = true;
+  }
   if (!(flags & ERD_PREPARE_ERS_DONE))
     rc = erd_ers_select(shape, t_cls, t_box, b->cls_inds, b->cls_count, b->box_inds, b->box_count, b->thr,
                         b->sel_flags, wsp, ctx->side[1]);

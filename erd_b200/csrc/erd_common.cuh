@@ -147,7 +147,7 @@ struct Quad {
 
 // ---------------------------------------------------------------- launch accounting (profile.cu)
 enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan, kKNmsOrder,
-                kKUpCheck, kKLossMain, kKClsOld, kKPosGrad, kKBoxEarly, kKBoxKd, kKBoxSweep, kKFinalize, kNumKernels };
+                kKUpCheck, kKZero, kKLossMain, kKClsOld, kKPosGrad, kKBoxKd, kKBoxSweep, kKFinalize, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 // ERD_LAUNCH(id, stream, kernel<<<...>>>(...)) counts the launch and, when profiling is on,
@@ -236,6 +236,7 @@ struct LossArgs {
   const int32_t* pad_hw;
   const int32_t* gt_inds;
   const int32_t* num_pos;
+  const int32_t* cls_inds;
   const int32_t* cls_count;
   const uint8_t* sel_flags;
   const int32_t* box_inds;
@@ -249,12 +250,15 @@ struct LossArgs {
   float dlw;
 };
 struct LossStreams {
-  cudaStream_t early;                 // low-priority helper: the dense box sweep
-  cudaStream_t late;                  // high-priority helper: positives' rows, survivors' distillation rows
+  cudaStream_t early;                 // low-priority helper: zero fill, class-response rows
+  cudaStream_t late;                  // high-priority helper: positives' rows, candidates' rows, take-back
   cudaEvent_t fork, pos_done, early_done, late_done;
+  cudaEvent_t cleared;                // may be null: gradient tensors not pre-cleared by erd_step_prepare
   cudaEvent_t sel_ready;              // may be null: ERS selection already ordered before the caller's stream
   cudaEvent_t nms_done;               // may be null: NMS already ordered before the caller's stream
 };
+cudaError_t launch_zero_fill(const Geo& g, const MPtr5& g_cls, const MPtr5& g_box, const unsigned int* skip_flag,
+                             cudaStream_t st);
 cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, const LossStreams* ls);
 
 }  // namespace erd

@@ -356,8 +356,8 @@ static int launch_scan_pipe(const Geo& g, const Workspace& ws, const Ptr5& t_cls
   static int stages = 0;   // 2 CTAs/SM x stages x 17 KB of copies in flight per SM
   if (!stages) {
     const char* e = getenv("ERD_SCAN_STAGES");
-    stages = e ? atoi(e) : 2;
-    if (stages < 2 || stages > 6) stages = 2;
+    stages = e ? atoi(e) : 4;
+    if (stages < 2 || stages > 6) stages = 4;
   }
   const int total = tiles * g.n_img;
   static int per_sm = 0;

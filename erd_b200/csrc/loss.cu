@@ -20,6 +20,7 @@
 //   box_sweep_kernel   dense write of the box-logit gradients: zero, the compact rows of the
 //                      positives, and the distillation rows of the NMS survivors.
 //   finalize_kernel    accumulators -> the reference's loss values.
+#include <cstdlib>
 #include "erd_common.cuh"
 
 namespace erd {
@@ -199,13 +200,16 @@ __device__ __forceinline__ void pos_item(const Geo& g, const Workspace& ws, cons
     else gd = g_uni * wid + g_ih * pick_gt(ty2, py2) + g_eh * pick_gt(py2, ty2);                  // d/dy2
     const float cb = upstream_of(A.upstream, acc_bbox(l)) * g.w_bbox / (1.0f + kEps32) / avg2 * w * gd;
     const float cd = upstream_of(A.upstream, acc_dfl(l)) * g.w_dfl / 4.0f / avg2 * w;
+    // compact copy (the candidates' kernels merge it) + the gradient tensor itself
     float* row = ws.pos_rows + ((size_t)n * g.pos_cap + p) * kBoxCh + side * kBins;
+    float* gp = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW + hw;
 #pragma unroll
     for (int j = 0; j < kBins; ++j) {
       const float pj = z[j] * inv;
       float gr = cb * pj * ((float)j - dmine);
       gr += cd * (wl * (pj - (j == yl ? 1.f : 0.f)) + wr * (pj - (j == yl + 1 ? 1.f : 0.f)));
       row[j] = gr;
+      gp[(size_t)j * HW] = gr;
     }
   } else if (GRAD && live) {   // assigned to a GT whose label lies outside the new-class range: no box loss
     float* row = ws.pos_rows + ((size_t)n * g.pos_cap + p) * kBoxCh + side * kBins;
@@ -340,8 +344,8 @@ __global__ void __launch_bounds__(256) assign_prepass_kernel(Geo g, Workspace ws
 }
 
 // ----------------------------------------------------------------------------- class sweep
-// grid (tile, image, part): a part is a group of kSweepCh class channels that lies entirely
-// in the old-class range [0, ori) or in the new-class range [ori, C).
+// QFL over the new-class channels.  grid (tile, image, part): a part is a group of kSweepCh
+// channels; part numbers start behind the (ori + kSweepCh - 1) / kSweepCh old-class groups.
 constexpr int kSweepCh = 8;
 
 template <bool VEC>
@@ -353,42 +357,6 @@ __device__ __forceinline__ void cls_tile(const Geo& g, const Workspace& ws, cons
   const int parts_old = (g.ori + kSweepCh - 1) / kSweepCh;
   const float* scls = A.s_cls.p[l] + (size_t)n * g.C * HW;
   float* gcls = A.g_cls.p[l] + (size_t)n * g.C * HW;
-  if (part < parts_old) {
-    // classification-response distillation: 2 (x_s - x_t) / (K ori) on the ERS rows, zero elsewhere
-    // (gfl_head_increment_erd.py:181-186,324-332).  A thread whose four anchors are all
-    // unselected issues no loads at all.
-    const int c0 = part * kSweepCh, c1 = min(c0 + kSweepCh, g.ori);
-    float sel[4];
-    bool any = false;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      sel[k] = (q.ok[k] && (A.sel_flags[abase + q.hw[k]] & 1)) ? 1.0f : 0.0f;   // gfl_increment_erd.py:149-151
-      any |= sel[k] != 0.f;
-    }
-    if (!any) {
-      for (int c = c0; c < c1; ++c) q.store_zero(gcls + (size_t)c * HW);
-      return;
-    }
-    const float kc = (float)A.cls_count[n] * (float)g.ori;
-    const float scale_dc = upstream_of(A.upstream, acc_dcls(n)) * A.dlw * 2.0f / kc;
-    const float* tcls = A.t_cls.p[l] + (size_t)n * g.ori * HW;
-    float sq = 0.f;
-#pragma unroll 4
-    for (int c = c0; c < c1; ++c) {
-      float xs[4], xt[4], gr[4];
-      q.load(scls + (size_t)c * HW, xs, 0.f);
-      q.load(tcls + (size_t)c * HW, xt, 0.f);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float df = sel[k] * (xs[k] - xt[k]);
-        sq = fmaf(df, df, sq);
-        gr[k] = scale_dc * df;
-      }
-      q.store(gcls + (size_t)c * HW, gr);
-    }
-    out_loss += sq;
-    return;
-  }
   // QFL over new-class channels of every anchor (:260-261,317-320)
   const int c0 = (part - parts_old) * kSweepCh, c1 = min(c0 + kSweepCh, g.cn);
   int label[4];
@@ -444,8 +412,7 @@ __global__ void __launch_bounds__(kTileThreads) cls_sweep_kernel(Geo g, Workspac
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int w = 0; w < kTileThreads / 32; ++w) s += (double)red[w];
-    const bool old_part = part < (g.ori + kSweepCh - 1) / kSweepCh;
-    if (s != 0.0) atomicAdd(ws.loss_acc + (old_part ? acc_dcls(n) : acc_cls(l)), s);
+    if (s != 0.0) atomicAdd(ws.loss_acc + acc_cls(l), s);
   }
 }
 
@@ -504,65 +471,121 @@ __device__ __forceinline__ float kd_weight_part(const Geo& g, const LossArgs& A,
   return mx;
 }
 
-// ----------------------------------------------------------------------------- box sweep
-// grid (tile, image, side).  Every box-logit gradient element of an anchor that is NOT an ERS
-// box candidate is written here, once: zero, or the compact row of a positive
-// (pos_kernel<true>).  The candidates (a few % of the anchors) belong to box_kd_kernel, which
-// runs concurrently: the two kernels never write the same element.
-template <bool VEC>
-__device__ __forceinline__ void box_tile(const Geo& g, const Workspace& ws, const LossArgs& A, int n, int l,
-                                         int hw0, int side) {
-  const int HW = g.hw[l];
-  Quad<VEC> q(hw0, HW);
-  const size_t abase = (size_t)n * g.A + g.start[l];
-  const float* prow[4];
-  bool any = false, cand = false;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    prow[k] = nullptr;
-    if (!q.ok[k]) continue;
-    const size_t a = abase + q.hw[k];
-    if (A.sel_flags[a] & 2) {   // candidate: not ours
-      cand = true;
-      q.ok[k] = false;
-      continue;
+// ----------------------------------------------------------------------------- zero fill
+// Most of the gradient is structurally zero: the old-class channels off the ERS rows and the
+// box channels of every anchor that is neither a positive nor an ERS box candidate.  One
+// launch clears both families (10 strided regions), with streaming 16 B stores; it depends on
+// nothing, so erd_step_prepare runs it at the very start of the step beside the ERS scan.
+// The sparse non-zero rows are written over it afterwards (cls_kd / pos_kernel<true> / box_kd).
+struct ZeroArgs {
+  float* base[2 * kLevels];
+  long long pitch[2 * kLevels];    // floats between consecutive rows
+  long long width[2 * kLevels];    // floats to clear per row
+  int rows[2 * kLevels];
+  int chunk0[2 * kLevels + 1];     // prefix of kZeroChunk-sized chunks
+  int vec[2 * kLevels];
+  const unsigned int* skip_flag;   // non-NULL: no-op when *skip_flag == 0 (see LossArgs)
+};
+constexpr int kZeroThreads = 256;
+constexpr int kZeroChunk = kZeroThreads * 16;   // floats per chunk
+
+__global__ void __launch_bounds__(kZeroThreads) zero_fill_kernel(ZeroArgs z) {
+  if (z.skip_flag && *z.skip_flag == 0u) return;
+  const int total = z.chunk0[2 * kLevels];
+  for (int c = blockIdx.x; c < total; c += gridDim.x) {
+    int reg = 0;
+    while (c >= z.chunk0[reg + 1]) ++reg;
+    const long long per_row = (z.width[reg] + kZeroChunk - 1) / kZeroChunk;
+    const long long local = c - z.chunk0[reg];
+    const long long row = local / per_row;
+    const long long off = (local - row * per_row) * kZeroChunk;
+    float* p = z.base[reg] + row * z.pitch[reg] + off;
+    const long long len = min((long long)kZeroChunk, z.width[reg] - off);
+    if (z.vec[reg]) {
+      for (long long i = (long long)threadIdx.x * 4; i < len; i += kZeroThreads * 4)
+        __stcs(reinterpret_cast<float4*>(p + i), make_float4(0.f, 0.f, 0.f, 0.f));
+    } else {
+      for (long long i = threadIdx.x; i < len; i += kZeroThreads) __stcs(p + i, 0.f);
     }
-    if (A.gt_inds[a] > 0)
-      prow[k] = ws.pos_rows + ((size_t)n * g.pos_cap + ws.pos_slot[a]) * kBoxCh + side * kBins;
-    any |= prow[k] != nullptr;
-  }
-  float* gbox = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW;
-  if (VEC && cand) {   // a 16 B group holding a candidate: element-wise stores around it
-    for (int j = 0; j < kBins; ++j) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (q.ok[k]) gbox[(size_t)j * HW + q.hw[k]] = prow[k] ? prow[k][j] : 0.f;
-    }
-    return;
-  }
-  if (!any) {
-#pragma unroll
-    for (int j = 0; j < kBins; ++j) q.store_zero(gbox + (size_t)j * HW);
-    return;
-  }
-  for (int j = 0; j < kBins; ++j) {
-    float v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = prow[k] ? prow[k][j] : 0.f;
-    q.store(gbox + (size_t)j * HW, v);
   }
 }
 
-__global__ void __launch_bounds__(kTileThreads) box_sweep_kernel(Geo g, Workspace ws, LossArgs A) {
+cudaError_t launch_zero_fill(const Geo& g, const MPtr5& g_cls, const MPtr5& g_box, const unsigned int* skip_flag,
+                             cudaStream_t st) {
+  ZeroArgs z;
+  z.skip_flag = skip_flag;
+  int chunks = 0;
+  for (int i = 0; i < 2 * kLevels; ++i) {
+    const int l = i % kLevels;
+    const bool cls = i < kLevels;
+    z.base[i] = cls ? g_cls.p[l] : g_box.p[l];
+    z.pitch[i] = (long long)(cls ? g.C : kBoxCh) * g.hw[l];
+    z.width[i] = (long long)(cls ? g.ori : kBoxCh) * g.hw[l];
+    z.rows[i] = g.n_img;
+    z.vec[i] = g.vec[l];
+    if (!cls) {   // contiguous over the images: one long row
+      z.width[i] *= g.n_img;
+      z.rows[i] = 1;
+    }
+    z.chunk0[i] = chunks;
+    chunks += (int)((z.width[i] + kZeroChunk - 1) / kZeroChunk) * z.rows[i];
+  }
+  z.chunk0[2 * kLevels] = chunks;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static int per_sm = 0;
+  if (!per_sm) {
+    const char* v = getenv("ERD_ZERO_CTAS");
+    per_sm = v ? atoi(v) : 1;
+    if (per_sm < 1 || per_sm > 8) per_sm = 1;
+  }
+  const int grid = chunks < per_sm * sms ? chunks : per_sm * sms;
+  if (grid > 0) ERD_LAUNCH(kKZero, st, (zero_fill_kernel<<<grid, kZeroThreads, 0, st>>>(z)));
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------- class-response distillation
+// 2 (x_s - x_t) / (K ori) on the old-class channels of the ERS rows (gfl_head_increment_erd.py:
+// 181-186,324-332), list driven: eight threads per selected anchor, each a strided eighth of
+// the channels, all gathers in flight at once.  Overwrites the zero fill on those rows.
+constexpr int kClsKdThreads = 256;
+
+__global__ void __launch_bounds__(kClsKdThreads) cls_kd_kernel(Geo g, Workspace ws, LossArgs A) {
   if (A.skip_flag && *A.skip_flag == 0u) return;
   const int n = blockIdx.y;
-  const int tile = blockIdx.x;
-  const int l = level_of_tile(g, tile);
-  const int hw0 = (tile - g.tile_start[l]) * kTile;
-  if (g.vec[l])
-    box_tile<true>(g, ws, A, n, l, hw0, blockIdx.z);
-  else
-    box_tile<false>(g, ws, A, n, l, hw0, blockIdx.z);
+  const int sub = threadIdx.x & 7;
+  const int K = A.cls_count[n];
+  const float kc = (float)K * (float)g.ori;
+  const float scale_dc = upstream_of(A.upstream, acc_dcls(n)) * A.dlw * 2.0f / kc;
+  float sq = 0.f;
+  for (int r = (blockIdx.x * kClsKdThreads + threadIdx.x) >> 3; r < K; r += (gridDim.x * kClsKdThreads) >> 3) {
+    const int a = A.cls_inds[(size_t)n * g.sel_cap + r];
+    const int l = level_of_anchor(g, a);
+    const int HW = g.hw[l];
+    const int hw = a - g.start[l];
+    const float* sp = A.s_cls.p[l] + (size_t)n * g.C * HW + hw;
+    const float* tp = A.t_cls.p[l] + (size_t)n * g.ori * HW + hw;
+    float* gp = A.g_cls.p[l] + (size_t)n * g.C * HW + hw;
+#pragma unroll 4
+    for (int c = sub; c < g.ori; c += 8) {
+      const float df = __ldg(sp + (size_t)c * HW) - __ldg(tp + (size_t)c * HW);
+      sq = fmaf(df, df, sq);
+      gp[(size_t)c * HW] = scale_dc * df;
+    }
+  }
+  __shared__ float red[kClsKdThreads / 32];
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s2 = 0.0;
+    for (int w = 0; w < kClsKdThreads / 32; ++w) s2 += (double)red[w];
+    if (s2 != 0.0) atomicAdd(ws.loss_acc + acc_dcls(n), s2);
+  }
 }
 
 // Box-logit gradients of the ERS box candidates, list driven: four threads per candidate, one
@@ -741,33 +764,44 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
   p.avg = const_cast<float*>(a.avg);
   p.upstream = a.upstream;
   p.skip_flag = a.skip_flag;
-  const dim3 box_grid(g.tile_start[kLevels], g.n_img, 4);
   const dim3 late_grid((g.sel_cap * 4 + kLateThreads - 1) / kLateThreads, g.n_img);
+  const dim3 cls_kd_grid((g.sel_cap * 8 + kClsKdThreads - 1) / kClsKdThreads, g.n_img);
   const int parts_old = (g.ori + kSweepCh - 1) / kSweepCh, parts_new = (g.cn + kSweepCh - 1) / kSweepCh;
-  const dim3 tile_grid_new(g.tile_start[kLevels], g.n_img, parts_new), tile_grid_old(g.tile_start[kLevels], g.n_img, parts_old);
-  // Box side: positives' rows -> { dense box sweep || candidates' rows with distillation } ->
-  // take-back of the candidates the NMS suppressed.  With helper streams it runs beside the
-  // class sweeps; the NMS is joined only in front of the last, list-driven launch.
-  // The two latency-bound launches go to a high-priority stream (their few CTAs must not queue
-  // behind the sweeps' thousands), the dense sweep to a low-priority one.
+  const dim3 tile_grid_new(g.tile_start[kLevels], g.n_img, parts_new);
+  // Schedule.  The only dense pass is the QFL sweep over the new-class channels (caller's
+  // stream).  Everything else is a zero fill (done by erd_step_prepare when it was given the
+  // gradient pointers, else here) overwritten by sparse, list-driven launches:
+  //   lo: [zero fill] -> wait(select) -> class-response rows of the ERS set
+  //   hi: positives' box rows -> wait(select) -> box candidates' rows incl. distillation
+  //       -> wait(NMS) -> take-back of the suppressed candidates
+  // and a 1-CTA finalize once all three streams are done.
   cudaStream_t hi = ls ? ls->late : st, lo = ls ? ls->early : st;
   if (ls) {
     e = cudaEventRecord(ls->fork, st);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(hi, ls->fork, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(lo, ls->fork, 0);
     if (e != cudaSuccess) return e;
+  }
+  if (ls && ls->cleared) {
+    e = cudaStreamWaitEvent(hi, ls->cleared, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(lo, ls->cleared, 0);
+    if (e != cudaSuccess) return e;
+  } else {
+    e = launch_zero_fill(g, a.g_cls, a.g_box, a.skip_flag, lo);
+    if (e != cudaSuccess) return e;
+    if (ls) {
+      e = cudaEventRecord(ls->pos_done, lo);   // (event reused: "zero fill done")
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(hi, ls->pos_done, 0);
+      if (e != cudaSuccess) return e;
+    }
   }
   ERD_LAUNCH(kKPosGrad, hi, (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, hi>>>(g, ws, p)));
-  if (ls) {
-    e = cudaEventRecord(ls->pos_done, hi);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(lo, ls->pos_done, 0);
-    if (e != cudaSuccess) return e;
-  }
   if (ls && ls->sel_ready) {
     e = cudaStreamWaitEvent(lo, ls->sel_ready, 0);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(hi, ls->sel_ready, 0);
     if (e != cudaSuccess) return e;
   }
-  ERD_LAUNCH(kKBoxEarly, lo, (box_sweep_kernel<<<box_grid, kTileThreads, 0, lo>>>(g, ws, a)));
+  ERD_LAUNCH(kKClsOld, lo, (cls_kd_kernel<<<cls_kd_grid, kClsKdThreads, 0, lo>>>(g, ws, a)));
   ERD_LAUNCH(kKBoxKd, hi, (box_kd_kernel<<<late_grid, kLateThreads, 0, hi>>>(g, ws, a)));
   if (ls) {
     e = cudaEventRecord(ls->early_done, lo);
@@ -780,11 +814,6 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
     if (e != cudaSuccess) return e;
   }
   ERD_LAUNCH(kKLossMain, st, (cls_sweep_kernel<<<tile_grid_new, kTileThreads, 0, st>>>(g, ws, a, parts_old)));
-  if (ls && ls->sel_ready) {
-    e = cudaStreamWaitEvent(st, ls->sel_ready, 0);
-    if (e != cudaSuccess) return e;
-  }
-  ERD_LAUNCH(kKClsOld, st, (cls_sweep_kernel<<<tile_grid_old, kTileThreads, 0, st>>>(g, ws, a, 0)));
   if (ls) {
     e = cudaStreamWaitEvent(st, ls->early_done, 0);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ls->late_done, 0);

@@ -8,8 +8,8 @@
 namespace erd {
 
 static const char* kKernelNames[kNumKernels] = {"ers_scan", "ers_select", "atss_candidates", "atss_finalize",
-                                                "pos_prepass", "nms_prep", "nms_mask", "nms_resolve", "nms_order", "upstream_check",
-                                                "qfl_sweep", "cls_old_sweep", "pos_grad", "box_sweep", "box_kd", "box_fix", "finalize"};
+                                                "pos_prepass", "nms_prep", "nms_mask", "nms_resolve", "nms_order", "upstream_check", "zero_fill",
+                                                "qfl_sweep", "cls_kd", "pos_grad", "box_kd", "box_fix", "finalize"};
 
 struct ProfState {
   std::mutex mu;

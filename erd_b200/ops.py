@@ -219,14 +219,19 @@ class ErdPath:
         N.check(self.lib.erd_loss_fwd_bwd(
             self._context(p.device), C.byref(p.shape), _ptrs(s_cls), _ptrs(s_box), _ptrs(t_cls), _ptrs(t_box), p.gt_boxes.data_ptr(),
             p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(), p.gt_inds.data_ptr(),
-            p.num_pos.data_ptr(), p.cls_count.data_ptr(), p.sel_flags.data_ptr(), p.box_inds.data_ptr(), p.box_count.data_ptr(),
+            p.num_pos.data_ptr(), p.cls_inds.data_ptr(), p.cls_count.data_ptr(), p.sel_flags.data_ptr(), p.box_inds.data_ptr(), p.box_count.data_ptr(),
             p.keep.data_ptr(),
             p.keep_count.data_ptr(), p.avg.data_ptr(), float(dist_loss_weight),
             upstream.data_ptr() if upstream is not None else None, 1 if skip_if_unit else 0,
             losses.data_ptr(), _ptrs(g_cls), _ptrs(g_box), p.ws.data_ptr(), _stream()), 'erd_loss_fwd_bwd')
 
     # ---- fused step -------------------------------------------------------------------
-    def prepare(self, p: Plan, t_cls, t_box, s_cls, s_box, ers_done: bool = False):
+    def prepare(self, p: Plan, t_cls, t_box, s_cls, s_box, ers_done: bool = False, g_cls=None, g_box=None):
+        """``g_cls`` / ``g_box``: the gradient tensors the following ``loss_fwd_bwd`` will fill; given
+        here, their zero fill runs at the start of the step beside the ERS scan."""
+        for l in range(N.MAX_LEVELS):
+            p.bufs.g_cls[l] = g_cls[l].data_ptr() if g_cls is not None else None
+            p.bufs.g_box[l] = g_box[l].data_ptr() if g_box is not None else None
         N.check(self.lib.erd_step_prepare(
             self._context(p.device), C.byref(p.shape), _ptrs(t_cls), _ptrs(t_box), _ptrs(s_cls), _ptrs(s_box),
             p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(),
@@ -254,7 +259,7 @@ class ErdPath:
         if g_box is None:
             g_box = [torch.empty_like(t) for t in s_box]
         losses = torch.empty(p.num_losses, dtype=torch.float32, device=p.device)
-        self.prepare(p, t_cls, t_box, s_cls, s_box, ers_done)
+        self.prepare(p, t_cls, t_box, s_cls, s_box, ers_done, g_cls, g_box)
         self.reduce_avg(p)
         self.loss_fwd_bwd(p, t_cls, t_box, s_cls, s_box, g_cls, g_box, losses, dist_loss_weight, upstream)
         return p, losses, g_cls, g_box

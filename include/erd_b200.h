@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define ERD_MAX_LEVELS 5
-#define ERD_ABI_VERSION 1
+#define ERD_ABI_VERSION 2
 
 typedef enum ErdStatus {
   ERD_OK = 0,
@@ -160,7 +160,7 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
                      const float* const* s_box,
                      const float* const* t_cls, const float* const* t_box, const float* gt_boxes,
                      const int64_t* gt_labels, const int32_t* gt_offsets, const int32_t* pad_hw,
-                     const int32_t* gt_inds, const int32_t* num_pos, const int32_t* cls_count,
+                     const int32_t* gt_inds, const int32_t* num_pos, const int32_t* cls_inds, const int32_t* cls_count,
                      const uint8_t* sel_flags,
                      const int32_t* box_inds, const int32_t* box_count, const int32_t* keep, const int32_t* keep_count,
                      const float* avg, float dist_loss_weight, const float* upstream,
@@ -188,6 +188,12 @@ typedef struct ErdStepBuffers {
   int32_t* keep;
   int32_t* keep_count;
   float* avg;
+  /* Optional (all NULL = off): the gradient tensors the following erd_loss_fwd_bwd(ctx, ...) call
+   * will receive.  Most of them is zero (old-class rows off the ERS set, box rows of background
+   * anchors); given here, that zero fill runs at the very start of the step, beside the ERS scan,
+   * instead of inside the loss call.  The caller must not touch the tensors in between. */
+  float* g_cls[ERD_MAX_LEVELS];
+  float* g_box[ERD_MAX_LEVELS];
 } ErdStepBuffers;
 
 int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const* t_cls,
