@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cstdlib>
 #include "erd_common.cuh"
 
 using namespace erd;

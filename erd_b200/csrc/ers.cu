@@ -536,8 +536,7 @@ cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, con
   }
   ERD_LAUNCH(kKErsSelect, st,
              (ers_select_kernel<<<dim3((g.A + kSelChunk - 1) / kSelChunk, g.n_img), kSelThreads, 0, st>>>(
-                 g, ws, tiles, cls_inds, cls_count, box_inds,
-                                                                 box_count, thr, sel_flags)));
+                 g, ws, tiles, cls_inds, cls_count, box_inds, box_count, thr, sel_flags)));
   return cudaGetLastError();
 }
 

@@ -744,7 +744,8 @@ cudaError_t launch_assign_avg(const Geo& g, const Workspace& ws, const Ptr5& s_c
   a.upstream = nullptr;
   a.skip_flag = nullptr;
   ERD_LAUNCH(kKAvg, st,
-             (assign_prepass_kernel<<<dim3((g.A + 256 * kAssignPer - 1) / (256 * kAssignPer), g.n_img), 256, 0, st>>>(g, ws, a, pad_hw, gt_inds, num_pos)));
+             (assign_prepass_kernel<<<dim3((g.A + 256 * kAssignPer - 1) / (256 * kAssignPer), g.n_img), 256, 0, st>>>(
+                 g, ws, a, pad_hw, gt_inds, num_pos)));
   return cudaGetLastError();
 }
 

@@ -3,6 +3,7 @@
 #include <mutex>
 #include <vector>
 
+#include <cstdlib>
 #include "erd_common.cuh"
 
 namespace erd {
