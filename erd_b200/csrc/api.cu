@@ -4,6 +4,8 @@
 #include <string.h>
 
 #include <cstdlib>
+#include <cstdio>
+#include <cstdlib>
 #include "erd_common.cuh"
 
 using namespace erd;
@@ -347,6 +349,7 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
     ls.late = ctx->side[2];
     ls.pos_done = ctx->pos_done;
     ls.late_done = ctx->join[2];
+    ls.main_done = ctx->join[0];
     ls.fork = ctx->fork;
     ls.early_done = ctx->early_done;
     // pre-cleared by erd_step_prepare only if these are the very tensors it was given

@@ -147,7 +147,7 @@ struct Quad {
 
 // ---------------------------------------------------------------- launch accounting (profile.cu)
 enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan, kKNmsOrder,
-                kKUpCheck, kKZero, kKLossMain, kKClsOld, kKPosGrad, kKBoxKd, kKBoxSweep, kKFinalize, kNumKernels };
+                kKUpCheck, kKZero, kKLossMain, kKClsOld, kKPosGrad, kKBoxKd, kKBoxSweep, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 // ERD_LAUNCH(id, stream, kernel<<<...>>>(...)) counts the launch and, when profiling is on,
@@ -252,7 +252,7 @@ struct LossArgs {
 struct LossStreams {
   cudaStream_t early;                 // low-priority helper: zero fill, class-response rows
   cudaStream_t late;                  // high-priority helper: positives' rows, candidates' rows, take-back
-  cudaEvent_t fork, pos_done, early_done, late_done;
+  cudaEvent_t fork, pos_done, early_done, late_done, main_done;
   cudaEvent_t cleared;                // may be null: gradient tensors not pre-cleared by erd_step_prepare
   cudaEvent_t sel_ready;              // may be null: ERS selection already ordered before the caller's stream
   cudaEvent_t nms_done;               // may be null: NMS already ordered before the caller's stream

@@ -186,7 +186,7 @@ __device__ __forceinline__ PipeTile pipe_tile(const Geo& g, int t, int tiles_per
 }
 
 __global__ void __launch_bounds__(kPipeThreads, 2) ers_scan_pipe_kernel(Geo g, Workspace ws, Ptr5 t_cls, Ptr5 t_box,
-                                                                        int tiles_per_img, int total_tiles, int stages) {
+                                                                        int tiles_per_img, int total_tiles, int stages, int l2_keep) {
   extern __shared__ __align__(128) float s_ring[];   // [stages][kPipeRows][kPipeT]
   __shared__ __align__(8) unsigned long long s_full[16], s_empty[16];
   __shared__ double s_red[kPipeT / 32][4];
@@ -205,6 +205,8 @@ __global__ void __launch_bounds__(kPipeThreads, 2) ers_scan_pipe_kernel(Geo g, W
   uint32_t phase = 0;   // parity of the current pass over the ring
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
+    unsigned long long keep_policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const PipeTile p = pipe_tile(g, t, tiles_per_img);
       const int HW = g.hw[p.l];
@@ -222,10 +224,18 @@ __global__ void __launch_bounds__(kPipeThreads, 2) ers_scan_pipe_kernel(Geo g, W
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_full[slot])),
                        "r"(row_bytes * (uint32_t)rows) : "memory");
         __syncwarp();
-        if (lane < rows)
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(smem_u32(dst + (size_t)lane * kPipeT)), "l"(src + (size_t)lane * HW), "r"(row_bytes),
-                         "r"(smem_u32(&s_full[slot])) : "memory");
+        if (lane < rows) {
+          // the distillation kernels gather rows of these tensors later in the step: ask L2 to keep
+          // them (evict_last) instead of letting the streaming traffic push them out
+          if ((l2_keep == 2) || (l2_keep == 1 && !is_cls))
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(smem_u32(dst + (size_t)lane * kPipeT)), "l"(src + (size_t)lane * HW), "r"(row_bytes),
+                           "r"(smem_u32(&s_full[slot])), "l"(keep_policy) : "memory");
+          else
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(dst + (size_t)lane * kPipeT)), "l"(src + (size_t)lane * HW), "r"(row_bytes),
+                           "r"(smem_u32(&s_full[slot])) : "memory");
+        }
         if (++slot == stages) { slot = 0; phase ^= 1u; }
       }
     }
@@ -360,6 +370,11 @@ static int launch_scan_pipe(const Geo& g, const Workspace& ws, const Ptr5& t_cls
     if (stages < 2 || stages > 6) stages = 4;
   }
   const int total = tiles * g.n_img;
+  static int l2_keep = -1;
+  if (l2_keep < 0) {
+    const char* e = getenv("ERD_SCAN_L2");
+    l2_keep = e ? atoi(e) : 2;   // 0 = no hint, 1 = box rows only, 2 = class and box rows
+  }
   static int per_sm = 0;
   if (!per_sm) {
     const char* e = getenv("ERD_SCAN_CTAS");
@@ -369,7 +384,7 @@ static int launch_scan_pipe(const Geo& g, const Workspace& ws, const Ptr5& t_cls
   const int grid = total < per_sm * sms ? total : per_sm * sms;
   ERD_LAUNCH(kKErsScan, st,
              (ers_scan_pipe_kernel<<<grid, kPipeThreads, (size_t)stages * kPipeStageFloats * 4, st>>>(
-                 g, ws, t_cls, t_box, tiles, total, stages)));
+                 g, ws, t_cls, t_box, tiles, total, stages, l2_keep)));
   return tiles;
 }
 

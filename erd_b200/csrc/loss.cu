@@ -19,7 +19,7 @@
 //                      box candidate.
 //   box_sweep_kernel   dense write of the box-logit gradients: zero, the compact rows of the
 //                      positives, and the distillation rows of the NMS survivors.
-//   finalize_kernel    accumulators -> the reference's loss values.
+//   (finalize_one)     accumulators -> the reference's loss values, by the last block of box_fix.
 #include <cstdlib>
 #include "erd_common.cuh"
 
@@ -597,6 +597,8 @@ __global__ void __launch_bounds__(kClsKdThreads) cls_kd_kernel(Geo g, Workspace 
 // latency-bound NMS chain this way, whatever fraction the NMS ends up keeping.)
 constexpr int kLateThreads = 256;
 
+__device__ __forceinline__ void finalize_one(const Geo& g, const Workspace& ws, const LossArgs& A, int i);
+
 __global__ void __launch_bounds__(kLateThreads) box_kd_kernel(Geo g, Workspace ws, LossArgs A) {
   if (A.skip_flag && *A.skip_flag == 0u) return;
   const int n = blockIdx.y;
@@ -657,6 +659,7 @@ __global__ void __launch_bounds__(kLateThreads) box_fix_kernel(Geo g, Workspace 
     for (int j = 0; j < kBins; ++j) gp[(size_t)j * HW] = prow ? prow[j] : 0.f;
   }
   __shared__ float red[kLateThreads / 32];
+  __shared__ bool last;
   kd = warp_sum(kd);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = kd;
   __syncthreads();
@@ -664,6 +667,17 @@ __global__ void __launch_bounds__(kLateThreads) box_fix_kernel(Geo g, Workspace 
     double s2 = 0.0;
     for (int w = 0; w < kLateThreads / 32; ++w) s2 += (double)red[w];
     if (s2 != 0.0) atomicAdd(ws.loss_acc + acc_dbox(g, n), s2);
+    // This is the last launch of the step (every other kernel is ordered before it): its last
+    // block turns the accumulators into the loss vector, which saves a launch at the very end
+    // of the critical path.
+    __threadfence();
+    last = atomicAdd(ws.counters + 2, 1u) == gridDim.x * gridDim.y - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    for (int i = threadIdx.x; i < 3 * kLevels + 2 * g.n_img; i += kLateThreads) finalize_one(g, ws, A, i);
+    if (threadIdx.x == 0) ws.counters[2] = 0u;
   }
 }
 
@@ -695,11 +709,6 @@ __device__ __forceinline__ void finalize_one(const Geo& g, const Workspace& ws, 
   }
   A.losses[i] = out;
   ws.loss_acc[i] = 0.0;   // clean for the next step
-}
-
-__global__ void finalize_kernel(Geo g, Workspace ws, LossArgs A) {
-  if (A.skip_flag && *A.skip_flag == 0u) return;
-  finalize_one(g, ws, A, threadIdx.x);
 }
 
 static int pos_grid_x(const Geo& g) {
@@ -775,7 +784,7 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
   //   lo: [zero fill] -> wait(select) -> class-response rows of the ERS set
   //   hi: positives' box rows -> wait(select) -> box candidates' rows incl. distillation
   //       -> wait(NMS) -> take-back of the suppressed candidates
-  // and a 1-CTA finalize once all three streams are done.
+  // whose last block also turns the accumulators into the loss vector.
   cudaStream_t hi = ls ? ls->late : st, lo = ls ? ls->early : st;
   if (ls) {
     e = cudaEventRecord(ls->fork, st);
@@ -804,23 +813,21 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
   }
   ERD_LAUNCH(kKClsOld, lo, (cls_kd_kernel<<<cls_kd_grid, kClsKdThreads, 0, lo>>>(g, ws, a)));
   ERD_LAUNCH(kKBoxKd, hi, (box_kd_kernel<<<late_grid, kLateThreads, 0, hi>>>(g, ws, a)));
-  if (ls) {
+  ERD_LAUNCH(kKLossMain, st, (cls_sweep_kernel<<<tile_grid_new, kTileThreads, 0, st>>>(g, ws, a, parts_old)));
+  if (ls) {   // the take-back pass also finalizes: order every other launch of the step before it
     e = cudaEventRecord(ls->early_done, lo);
+    if (e == cudaSuccess) e = cudaEventRecord(ls->main_done, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(hi, ls->early_done, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(hi, ls->main_done, 0);
     if (e == cudaSuccess && ls->nms_done) e = cudaStreamWaitEvent(hi, ls->nms_done, 0);
     if (e != cudaSuccess) return e;
   }
   ERD_LAUNCH(kKBoxSweep, hi, (box_fix_kernel<<<late_grid, kLateThreads, 0, hi>>>(g, ws, a)));
   if (ls) {
     e = cudaEventRecord(ls->late_done, hi);
-    if (e != cudaSuccess) return e;
-  }
-  ERD_LAUNCH(kKLossMain, st, (cls_sweep_kernel<<<tile_grid_new, kTileThreads, 0, st>>>(g, ws, a, parts_old)));
-  if (ls) {
-    e = cudaStreamWaitEvent(st, ls->early_done, 0);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ls->late_done, 0);
     if (e != cudaSuccess) return e;
   }
-  ERD_LAUNCH(kKFinalize, st, (finalize_kernel<<<1, ((total + 31) / 32) * 32, 0, st>>>(g, ws, a)));
   return cudaGetLastError();
 }
 
