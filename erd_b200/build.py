@@ -36,6 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
            '-shared', '-Xcompiler', '-fPIC', '--cudart', 'shared',
            '-o', LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd[1:1] = os.environ.get('ERD_EXTRA_NVCC', '').split()   # developer builds, e.g. -DERD_DEV_ABLATE
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -150,10 +150,19 @@ enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort,
                 kKUpCheck, kKZero, kKLossMain, kKClsOld, kKPosGrad, kKBoxKd, kKBoxSweep, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
+// Developer build only (-DERD_DEV_ABLATE): ERD_ABLATE=<mask> skips kernels by id to measure what
+// each one costs inside the full schedule (scripts/ablate.sh).  Results are garbage when set.
+#ifdef ERD_DEV_ABLATE
+bool ablated(int id);
+#define ERD_ABLATED(id) ::erd::ablated(id)
+#else
+#define ERD_ABLATED(id) false
+#endif
 // ERD_LAUNCH(id, stream, kernel<<<...>>>(...)) counts the launch and, when profiling is on,
 // brackets it with CUDA events on the launching stream.
 #define ERD_LAUNCH(id, st, ...) \
   do {                          \
+    if (ERD_ABLATED(id)) break; \
     ::erd::prof_begin(id, st);  \
     __VA_ARGS__;                \
     ::erd::prof_end(id, st);    \

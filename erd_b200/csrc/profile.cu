@@ -51,6 +51,14 @@ void prof_begin(int id, cudaStream_t st) {
   g_prof.pending[id].push_back({a, b});
 }
 
+#ifdef ERD_DEV_ABLATE
+bool ablated(int id) {
+  static long mask = -1;
+  if (mask < 0) { const char* e = getenv("ERD_ABLATE"); mask = e ? strtol(e, nullptr, 0) : 0; }
+  return (mask >> id) & 1;
+}
+#endif
+
 void prof_end(int id, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
   if (!(g_prof.mask >> id & 1u)) return;
