@@ -378,17 +378,31 @@ __device__ __forceinline__ void cls_tile(const Geo& g, const Workspace& ws, cons
   const float inv_avg1 = 1.0f / (float)((double)A.avg[0] + (double)kEps32);            // losses/utils.py:60-61
   const float scale_cls = upstream_of(A.upstream, acc_cls(l)) * g.w_cls * inv_avg1;
   float loss_cls = 0.f;
+  float gs[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) gs[k] = lw[k] * scale_cls;
+  // every element as a negative first: the hot loop stays branch-free ...
 #pragma unroll 4
   for (int c = c0; c < c1; ++c) {
     float x[4], gr[4];
     q.load(scls + (size_t)(g.ori + c) * HW, x, 0.f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const QflTerm t = (c == label[k]) ? qfl_pos(x[k], score[k]) : qfl_neg(x[k]);
-      loss_cls += lw[k] * t.loss;
-      gr[k] = lw[k] * scale_cls * t.grad;
+      const QflTerm t = qfl_neg(x[k]);
+      loss_cls = fmaf(lw[k], t.loss, loss_cls);
+      gr[k] = gs[k] * t.grad;
     }
     q.store(gcls + (size_t)(g.ori + c) * HW, gr);
+  }
+  // ... then the label channel of the (rare) positives is redone with its soft target
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (label[k] < 0) continue;
+    const size_t off = (size_t)(g.ori + label[k]) * HW + q.hw[k];
+    const float x = scls[off];
+    const QflTerm tp = qfl_pos(x, score[k]), tn = qfl_neg(x);
+    loss_cls += lw[k] * (tp.loss - tn.loss);
+    gcls[off] = gs[k] * tp.grad;
   }
   out_loss += loss_cls;
 }
