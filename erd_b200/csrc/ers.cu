@@ -23,12 +23,6 @@ namespace erd {
 // independent of register pressure (a register-staged version of this pass sat at 2.7 TB/s,
 // latency-bound).  Bulk copies need 16 B aligned rows (hw % 4 == 0); tiles of the other levels
 // (a few % of the anchors) are filled with ordinary loads.
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {

@@ -44,7 +44,7 @@ struct QflTerm {
 //              the odd series through s^13 is exact to ~1e-7 relative on the whole range,
 //              without the cancellation a log(1+e) has for the small e of background anchors.
 __device__ __forceinline__ void sig_sp(float x, float& sig, float& sp) {
-  const float e = __expf(-fabsf(x));
+  const float e = ex2_approx(-1.4426950408889634f * fabsf(x));
   const float r = __fdividef(1.0f, 1.0f + e);
   sig = x >= 0.f ? r : e * r;
   const float s = __fdividef(e, 2.0f + e);
