@@ -39,6 +39,12 @@ ORI, NUM_CLASSES, REG_MAX = 40, 80, 16
 CN = NUM_CLASSES - ORI
 BYTES_PER_ANCHOR = {'path': 1616, 'ers_scan': 4 * (ORI + 68), 'qfl_sweep': 4 * (CN + CN),
                     'zero_fill': 4 * (ORI + 68)}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload (16 images), from
+# profiles/r1c_traffic.csv.  Kernels that only write (zero_fill) or write as much as they read (qfl_sweep)
+# show less than their algorithmic bytes: dirty lines still sit in the 126 MB L2 when the kernel ends and
+# are written back during the next one.
+NCU_TRAFFIC_BYTES = {'ers_scan': 155160448 + 10928896, 'qfl_sweep': 58870528 + 13393664,
+                     'zero_fill': 14507 + 91372203}
 
 
 def parse():
@@ -327,7 +333,9 @@ def run_ours(args):
                        'images_per_gpu': n, 'parallelism': f'dp{world} over images',
                        'l2': 'inputs+grads 579 MB per step > 126 MB L2, no flush needed'},
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                         'frac': (achieved / peak) if achieved else None,
+                         'traffic': NCU_TRAFFIC_BYTES.get(dom) if n == IMGS_PER_GPU else None,
+                         'traffic_source': 'profiles/r1c_traffic.csv (ncu, per launch, bytes)',
                          'peak_source': 'measured' if peaks else 'fallback',
                          'algorithmic_bytes_per_anchor': BYTES_PER_ANCHOR[dom],
                          'path_bytes_per_anchor': BYTES_PER_ANCHOR['path'],
