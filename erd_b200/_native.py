@@ -56,6 +56,8 @@ SIGNATURES = {
                          _P, _P, _P, _F, _P, _I, _P, PtrArray, PtrArray, _P, _P],
     'erd_step_prepare': [_P, _SH, PtrArray, PtrArray, PtrArray, PtrArray, _P, _P, _P, _P, _F,
                          C.POINTER(ErdStepBuffers), _P, _P, C.c_uint32],
+    'erd_avg_exchange_bytes': [],
+    'erd_avg_exchange': [_P, C.POINTER(_P), _I, _I, _P],
     'erd_profile_enable': [C.c_uint],
     'erd_launch_count': [],
     'erd_profile_num_kernels': [],
@@ -84,7 +86,8 @@ def load():
         fn = getattr(lib, name)   # AttributeError here == header/library drift
         fn.argtypes = argtypes
         fn.restype = (C.c_char_p if name in ('erd_last_error', 'erd_profile_kernel_name')
-                      else C.c_ulonglong if name == 'erd_launch_count' else C.c_int)
+                      else C.c_ulonglong if name == 'erd_launch_count'
+                      else C.c_size_t if name == 'erd_avg_exchange_bytes' else C.c_int)
     if lib.erd_abi_version() != ABI_VERSION:
         raise RuntimeError(f'liberd_b200 ABI {lib.erd_abi_version()} != binding {ABI_VERSION}')
     _lib = lib

@@ -4,8 +4,6 @@
 #include <string.h>
 
 #include <cstdlib>
-#include <cstdio>
-#include <cstdlib>
 #include "erd_common.cuh"
 
 using namespace erd;

@@ -28,6 +28,69 @@ def reduce_mean_(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+class PeerAvgExchange:
+    """``reduce_mean`` of the (2,) avg-factor tensor as one kernel over NVLink peer memory
+    (``erd_avg_exchange``): every rank owns a small symmetric buffer all peers have mapped.
+    Plumbing only: torch symmetric memory allocates and maps the buffers.  ``create`` returns
+    None (the caller then keeps the NCCL all-reduce) when the process group is not initialised,
+    has one rank, spans more than one node, or symmetric memory cannot be set up."""
+
+    def __init__(self, lib, buf, handle, rank: int, world_size: int):
+        import ctypes as C
+        self.lib, self.buf, self.handle = lib, buf, handle
+        self.rank, self.world_size = rank, world_size
+        self.peers = (C.c_void_p * world_size)(*[int(p) for p in handle.buffer_ptrs])
+
+    @classmethod
+    def create(cls, lib, device: torch.device):
+        import os
+        rank, ws = world()
+        if ws < 2 or ws > 64 or os.environ.get('ERD_PEER_EXCHANGE', '1') == '0':
+            return None
+        if int(os.environ.get('LOCAL_WORLD_SIZE', ws)) != ws:
+            return None                      # peer memory is a single-node mechanism
+        try:
+            import torch.distributed._symmetric_memory as symm
+            nbytes = int(lib.erd_avg_exchange_bytes())
+            with torch.cuda.device(device):
+                buf = symm.empty((nbytes + 3) // 4, dtype=torch.int32, device=device)
+                buf.zero_()
+                handle = symm.rendezvous(buf, dist.group.WORLD)
+                torch.cuda.synchronize(device)
+            dist.barrier()                   # every buffer is zero before anyone stores into it
+            return cls(lib, buf, handle, rank, ws)
+        except Exception as e:               # noqa: BLE001 -- any failure means "use NCCL"
+            import warnings
+            warnings.warn(f'erd_b200: peer-memory avg exchange unavailable ({e!r}); using NCCL all_reduce')
+            return None
+
+    def reduce_mean_(self, t: torch.Tensor) -> torch.Tensor:
+        assert t.dtype == torch.float32 and t.numel() == 2 and t.is_contiguous()
+        rc = self.lib.erd_avg_exchange(t.data_ptr(), self.peers, self.rank, self.world_size,
+                                       torch.cuda.current_stream(t.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f'erd_avg_exchange failed ({rc})')
+        return t
+
+    def timed_out(self) -> bool:
+        """True if a peer never arrived in some earlier exchange (host sync; for tests / teardown)."""
+        return bool(self.buf[int(self.lib.erd_avg_exchange_bytes()) // 4 - 3].item())
+
+
+_peer_exchange = None
+_peer_exchange_tried = False
+
+
+def peer_exchange(lib, device: torch.device):
+    """The process-wide PeerAvgExchange (created on first use -- a collective call, made by every
+    rank at its first reduction, outside any CUDA-graph capture) or None."""
+    global _peer_exchange, _peer_exchange_tried
+    if not _peer_exchange_tried:
+        _peer_exchange_tried = True
+        _peer_exchange = PeerAvgExchange.create(lib, device)
+    return _peer_exchange
+
+
 def shard_images(num_global: int, rank: int, world_size: int) -> List[int]:
     """Contiguous block of image indices owned by ``rank`` (DDP shards the batch by
     image; the path needs no halo and no data-path collective)."""

@@ -11,7 +11,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _native as N
-from .dist_utils import reduce_mean_
+from .dist_utils import peer_exchange, reduce_mean_
 
 STRIDES = (8, 16, 32, 64, 128)
 
@@ -211,8 +211,13 @@ class ErdPath:
                                          _stream()), 'erd_teacher_nms')
 
     def reduce_avg(self, p: Plan):
-        """reduce_mean of both normalisers in one 8-byte all-reduce (dist_utils.py:59-65)."""
-        reduce_mean_(p.avg)
+        """reduce_mean of both normalisers (dist_utils.py:59-65) in one 8-byte exchange: a single
+        kernel over NVLink peer memory when the ranks share a node, else one NCCL all-reduce."""
+        ex = peer_exchange(self.lib, p.device)
+        if ex is not None:
+            ex.reduce_mean_(p.avg)
+        else:
+            reduce_mean_(p.avg)
 
     def loss_fwd_bwd(self, p: Plan, t_cls, t_box, s_cls, s_box, g_cls, g_box, losses, dist_loss_weight: float,
                      upstream: Optional[torch.Tensor] = None, skip_if_unit: bool = False):

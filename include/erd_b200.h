@@ -205,6 +205,17 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
 #define ERD_PREPARE_ERS_DONE 1u /* erd_ers_select already ran on these teacher tensors (sel_pos);
                                    its lists, counts, sel_flags and the teacher cache are reused */
 
+/* reduce_mean of the two avg factors (mmdet/utils/dist_utils.py:59-65, call sites
+ * gfl_head_increment_erd.py:390-391,406-407) over NVLink peer memory, for one process per GPU
+ * on one node: avg[0..1] <- sum_r avg_r / world, identical bits on every rank, one small
+ * kernel on `stream` (CUDA-graph capturable) instead of an NCCL launch.
+ * peer_bufs[r]: rank r's exchange buffer of erd_avg_exchange_bytes() bytes as mapped into THIS
+ * process (the host maps them, e.g. with torch symmetric memory or CUDA IPC), zeroed once by
+ * its owner before the first call.  Collective: every rank calls it once per step.
+ * Word [erd_avg_exchange_bytes()/4 - 3] of the own buffer becomes 1 if a peer never arrived. */
+size_t erd_avg_exchange_bytes(void);
+int erd_avg_exchange(float* avg, void* const* peer_bufs, int32_t rank, int32_t world, void* stream);
+
 /* Launch accounting and optional per-kernel timing (CUDA events on the launching stream).
  * No reference counterpart; bench.py reports roofline numbers from it. */
 int erd_profile_enable(unsigned int kernel_mask);   /* bit k set: time kernel id k; 0 = off */
