@@ -88,6 +88,12 @@ def peer_exchange(lib, device: torch.device):
     if not _peer_exchange_tried:
         _peer_exchange_tried = True
         _peer_exchange = PeerAvgExchange.create(lib, device)
+        if world()[1] > 1:
+            # all or nothing: a rank that could not set it up must not leave the others spinning
+            ok = torch.tensor([1 if _peer_exchange is not None else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                _peer_exchange = None
     return _peer_exchange
 
 
