@@ -3,8 +3,6 @@
 // Reference: GFLIncrementERD.sel_pos / sel_pos_single
 // (mmdet/models/detectors/gfl_increment_erd.py:143-200); the Integral decode fused into the
 // pass is gfl_head_increment_erd.py:40-54,189-195.
-#include <stdlib.h>
-
 #include <cstdlib>
 #include "erd_common.cuh"
 
@@ -149,11 +147,13 @@ __global__ void __launch_bounds__(T) ers_scan_kernel(Geo g, Workspace ws, Ptr5 t
 }
 
 // ----------------------------------------------------------------------------- pass 1, pipelined
-// Persistent, warp-specialised form of the same pass: one CTA per SM; warp 0 is the producer
-// (bulk copies of 17-row x 256-anchor stages into a ring of shared-memory slots, full/empty
-// mbarriers per slot), warps 1..8 are consumers (one anchor per thread).  The producer runs
-// ahead by the whole ring (~200 KB of requests in flight per SM) no matter what the consumers
-// are doing, so the pass is bound by HBM, not by load latency.
+// Persistent, warp-specialised form of the same pass (the default): two CTAs per SM; warp 0 is
+// the producer (bulk copies of 17-row x 256-anchor stages into a ring of shared-memory slots,
+// full/empty mbarriers per slot, L2 evict_last hint), warps 1..8 are consumers (one anchor per
+// thread).  The producer runs ahead by the whole ring no matter what the consumers are doing.
+// Ring depth is a trade: a deep ring (6 stages = 30 MB of requests in flight over the chip)
+// floods the memory system's queues and makes every kernel running beside the scan 2-3x slower
+// without making the scan faster; 4 stages measured best inside the full step.
 constexpr int kPipeT = 256;                 // anchors per tile = consumer threads
 constexpr int kPipeRows = kBins;            // rows per stage
 constexpr int kPipeThreads = kPipeT + 32;

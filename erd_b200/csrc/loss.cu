@@ -1,5 +1,5 @@
 // Fused forward + backward of the GT losses (QFL / GIoU / DFL) and the two distillation
-// losses, writing dense NCHW gradients in one sweep over the student head outputs.
+// losses, writing dense NCHW gradients of the student head outputs.
 // Reference: GFLHeadIncrementERD.loss_by_feat_single / distill_loss_by_image_single /
 // loss_by_feat (dense_heads/gfl_head_increment_erd.py:142-454), quality_focal_loss and
 // distribution_focal_loss (losses/gfocal_loss.py:12-53,143-165), giou_loss
@@ -7,19 +7,21 @@
 // knowledge_distillation_kl_div_loss (losses/kd_loss.py:12-37), weight_reduce_loss
 // (losses/utils.py:30-65).  Closed-form gradients: SURVEY.md Appendix A.
 //
-// Kernels
-//   pos_kernel<false>  (prepare phase) 4 threads per positive anchor: weight, softmax-integral
-//                      decode, IoU score, GIoU/DFL loss sums, and the two avg factors.
-//   pos_kernel<true>   box-logit gradient rows of the positives (needs the reduced avg factor),
-//                      written to a compact row buffer.
-//   cls_sweep_kernel   streaming sweep over the class logits: QFL on the new-class channels of
-//                      every anchor, class-response L2 on the old-class channels (zero off
-//                      the ERS rows), gradients written once, densely.
-//   (kd_side)          DFL-distribution KL of the NMS survivors, computed where box_late writes
-//                      box candidate.
-//   box_sweep_kernel   dense write of the box-logit gradients: zero, the compact rows of the
-//                      positives, and the distillation rows of the NMS survivors.
-//   (finalize_one)     accumulators -> the reference's loss values, by the last block of box_fix.
+// Kernels (schedule: launch_loss at the end of this file)
+//   pos_kernel<false>      (erd_avg_factors) 4 threads per positive anchor: weight, softmax-integral
+//                          decode, IoU score, GIoU/DFL loss sums, and the two avg factors.
+//   assign_prepass_kernel  (erd_step_prepare) the ATSS decode and that prepass in one launch.
+//   zero_fill_kernel       the structurally-zero part of the gradient (old-class channels, all
+//                          box channels) with streaming stores, at the start of the step.
+//   cls_sweep_kernel       the one dense read-modify-write pass: QFL on the new-class channels.
+//   cls_kd_kernel          class-response L2 rows of the ERS set, list driven.
+//   pos_kernel<true>       box-logit gradient rows of the positives (needs the reduced avg
+//                          factor): compact copy + scattered into the gradient tensor.
+//   box_kd_kernel          rows of every ERS box candidate incl. the DFL-distribution KL, written
+//                          beside the NMS as if kept.
+//   box_fix_kernel         after the NMS: takes the suppressed candidates back, sums the
+//                          survivors' KL; its last block turns the fp64 accumulators into the
+//                          reference's loss values (finalize_one).
 #include <cstdlib>
 #include "erd_common.cuh"
 
