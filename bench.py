@@ -316,6 +316,12 @@ def run_ours(args):
                'd2h_bytes_per_step': plan.num_losses * 4, 'steps': e_steps,
                'api': 'GFLIncrementERD.sel_pos + GFLHeadIncrementERD.loss_by_feat + backward, pinned host tensors'}
 
+    if world > 1:
+        from erd_b200.dist_utils import peer_exchange
+        collective = ('8-byte avg-factor mean: one kernel over NVLink peer memory (erd_avg_exchange)'
+                      if peer_exchange(lib, dev) is not None else '8-byte avg-factor mean: ncclAllReduce')
+    else:
+        collective = 'none (1 rank)'
     if rank == 0:
         peaks = {}
         try:
@@ -330,7 +336,7 @@ def run_ours(args):
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'GFL R50-FPN 40+40 ERD loss fwd+bwd, {n} img/GPU 800x1333, 80-class head, '
                                    f'reg_max=16 (BASELINE.json configs[1])', 'anchors_per_image': A,
-                       'images_per_gpu': n, 'parallelism': f'dp{world} over images',
+                       'images_per_gpu': n, 'parallelism': f'dp{world} over images', 'collective': collective,
                        'l2': 'inputs+grads 579 MB per step > 126 MB L2, no flush needed'},
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': (achieved / peak) if achieved else None,
