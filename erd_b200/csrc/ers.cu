@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(T) ers_scan_kernel(Geo g, Workspace ws, Ptr5 t
 // thread).  The producer runs ahead by the whole ring no matter what the consumers are doing.
 // Ring depth is a trade: a deep ring (6 stages = 30 MB of requests in flight over the chip)
 // floods the memory system's queues and makes every kernel running beside the scan 2-3x slower
-// without making the scan faster; 4 stages measured best inside the full step.
+// without making the scan faster; 3 stages (102 KB of shared memory per SM) measured best inside
+// the full step: 0.189 ms against 0.199 ms with 4 and 0.200 ms with 2.
 constexpr int kPipeT = 256;                 // anchors per tile = consumer threads
 constexpr int kPipeRows = kBins;            // rows per stage
 constexpr int kPipeThreads = kPipeT + 32;
@@ -360,8 +361,8 @@ static int launch_scan_pipe(const Geo& g, const Workspace& ws, const Ptr5& t_cls
   static int stages = 0;   // 2 CTAs/SM x stages x 17 KB of copies in flight per SM
   if (!stages) {
     const char* e = getenv("ERD_SCAN_STAGES");
-    stages = e ? atoi(e) : 4;
-    if (stages < 2 || stages > 6) stages = 4;
+    stages = e ? atoi(e) : 3;
+    if (stages < 2 || stages > 6) stages = 3;
   }
   const int total = tiles * g.n_img;
   static int l2_keep = -1;
