@@ -153,9 +153,10 @@ __global__ void __launch_bounds__(T) ers_scan_kernel(Geo g, Workspace ws, Ptr5 t
 // thread).  The producer runs ahead by the whole ring no matter what the consumers are doing.
 // Ring depth is a trade: a deep ring (6 stages = 30 MB of requests in flight over the chip)
 // floods the memory system's queues and makes every kernel running beside the scan 2-3x slower
-// without making the scan faster; 3 stages (102 KB of shared memory per SM) measured best inside
-// the full step: 0.189 ms against 0.199 ms with 4 and 0.200 ms with 2.
-constexpr int kPipeT = 256;                 // anchors per tile = consumer threads
+// without making the scan faster; 3 stages measured best inside the full step (0.189 ms against
+// 0.199 ms with 4 and 0.200 ms with 2, 256-anchor tiles), and 224-anchor tiles -- both CTAs' rings
+// inside a 100 KB carve-out -- shave another 2 us.
+constexpr int kPipeT = 224;                 // anchors per tile = consumer threads (7 warps)
 constexpr int kPipeRows = kBins;            // rows per stage
 constexpr int kPipeThreads = kPipeT + 32;
 constexpr int kPipeStageFloats = kPipeRows * kPipeT;
