@@ -12,7 +12,6 @@ from . import build as _build
 
 MAX_LEVELS = 5
 ABI_VERSION = 2
-PREPARE_ERS_DONE, PREPARE_JOIN_AVG = 1, 2      # flags of erd_step_prepare
 
 
 class ErdShape(C.Structure):

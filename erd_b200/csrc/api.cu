@@ -133,10 +133,8 @@ static MPtr5 mptr5(float* const* p) {
 }
 
 struct ErdContext {
-  cudaStream_t side[4];          // [0] lo: zero fill, class-response rows; [1] hi: teacher chain;
-                                 // [2] hi: positives' rows, box candidates, take-back; [3] hi: positives prepass
-  cudaEvent_t fork, join[3], pos_done, sel_done, early_done, nms_all, clear_done, assign_done, avg1_done;
-  bool avg1_pending;             // avg1_done recorded by erd_step_prepare, not yet waited on
+  cudaStream_t side[3];          // [0] early box sectors, [1] teacher chain, [2] positives' rows + late box groups
+  cudaEvent_t fork, join[3], pos_done, sel_done, early_done, nms_all, clear_done;
   bool clear_pending;            // gradient tensors below were zero-filled by erd_step_prepare
   float* cleared_cls[kLevels];
   float* cleared_box[kLevels];
@@ -181,20 +179,18 @@ int erd_create(ErdContext** ctx) {
   // CTAs are not queued behind the bandwidth-bound kernels running beside it
   int prio_least = 0, prio_greatest = 0;
   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-  for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
     e = cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, i == 0 ? prio_least : prio_greatest);
-  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming);
+  }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->pos_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->clear_done, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->assign_done, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->avg1_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->early_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->nms_all, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sel_done, cudaEventDisableTiming);
   c->nms_pending = false;
   c->clear_pending = false;
-  c->avg1_pending = false;
   if (e != cudaSuccess) {
     delete c;
     return fail_cuda(e, "erd_create");
@@ -205,13 +201,13 @@ int erd_create(ErdContext** ctx) {
 
 int erd_destroy(ErdContext* c) {
   if (!c) return ERD_OK;
-  for (int i = 0; i < 4; ++i) cudaStreamDestroy(c->side[i]);
-  for (int i = 0; i < 3; ++i) cudaEventDestroy(c->join[i]);
+  for (int i = 0; i < 3; ++i) {
+    cudaStreamDestroy(c->side[i]);
+    cudaEventDestroy(c->join[i]);
+  }
   cudaEventDestroy(c->fork);
   cudaEventDestroy(c->pos_done);
   cudaEventDestroy(c->clear_done);
-  cudaEventDestroy(c->assign_done);
-  cudaEventDestroy(c->avg1_done);
   cudaEventDestroy(c->early_done);
   cudaEventDestroy(c->nms_all);
   cudaEventDestroy(c->sel_done);
@@ -245,8 +241,7 @@ int erd_atss_assign(const ErdShape* shape, const float* gt_boxes, const int64_t*
     return fail(ERD_ERR_NULL, "erd_atss_assign: NULL argument");
   Workspace ws;
   carve(g, wsp, &ws);
-  cudaError_t e = launch_atss(g, ws, gt_boxes, gt_labels, gt_offsets, pad_hw, gt_inds, num_pos, nullptr,
-                              (cudaStream_t)stream);
+  cudaError_t e = launch_atss(g, ws, gt_boxes, gt_labels, gt_offsets, pad_hw, gt_inds, num_pos, (cudaStream_t)stream);
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_atss_assign");
 }
 
@@ -263,7 +258,7 @@ int erd_avg_factors(const ErdShape* shape, const float* const* s_cls, const floa
   Workspace ws;
   carve(g, wsp, &ws);
   cudaError_t e = launch_avg(g, ws, ptr5(s_cls), ptr5(s_box), gt_boxes, gt_labels, gt_offsets, gt_inds, num_pos, avg,
-                             false, (cudaStream_t)stream);
+                             (cudaStream_t)stream);
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_avg_factors");
 }
 
@@ -353,8 +348,6 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
     ls.pos_done = ctx->pos_done;
     ls.late_done = ctx->join[2];
     ls.main_done = ctx->join[0];
-    ls.avg1_done = ctx->avg1_pending ? ctx->avg1_done : nullptr;
-    ctx->avg1_pending = false;
     ls.fork = ctx->fork;
     ls.early_done = ctx->early_done;
     // pre-cleared by erd_step_prepare only if these are the very tensors it was given
@@ -385,9 +378,7 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   cudaError_t e = cudaSuccess;
   if (ctx->nms_pending) {   // a previous prepare nobody consumed: do not race its teacher cache
     e = cudaStreamWaitEvent(main, ctx->nms_all, 0);
-    if (e == cudaSuccess && ctx->avg1_pending) e = cudaStreamWaitEvent(main, ctx->avg1_done, 0);
     ctx->nms_pending = false;
-    ctx->avg1_pending = false;
   }
   // Stream layout.  The caller's stream only carries what the avg-factor all-reduce needs
   // (ATSS + positives prepass), so the caller can all-reduce and start the QFL sweep at once.
@@ -438,24 +429,8 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   if (g.total_gt > 0 && ((uintptr_t)gt_boxes & 15)) return fail(ERD_ERR_BAD_SHAPE, "gt_boxes must be 16 B aligned");
   Workspace ws;
   carve(g, wsp, &ws);
-  // Assignment on the caller's stream: its last block already publishes avg[0] (the assignment
-  // does not depend on the student), which is all the QFL sweep needs.  The positives prepass
-  // (avg[1], loss sums) continues on a high-priority helper stream and is joined by the loss
-  // call in front of the positives' gradient rows -- or right here, when the caller is going to
-  // all-reduce the avg buffer itself (ERD_PREPARE_JOIN_AVG).
-  e = launch_atss(g, ws, gt_boxes, gt_labels, gt_offsets, pad_hw, b->gt_inds, b->num_pos, b->avg, main);
-  if (e == cudaSuccess) e = cudaEventRecord(ctx->assign_done, main);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[3], ctx->assign_done, 0);
-  if (e == cudaSuccess)
-    e = launch_avg(g, ws, ptr5(s_cls), ptr5(s_box), gt_boxes, gt_labels, gt_offsets, b->gt_inds, b->num_pos, b->avg,
-                   true, ctx->side[3]);
-  if (e == cudaSuccess) e = cudaEventRecord(ctx->avg1_done, ctx->side[3]);
-  if (e == cudaSuccess) {
-    if (flags & ERD_PREPARE_JOIN_AVG)
-      e = cudaStreamWaitEvent(main, ctx->avg1_done, 0);
-    else
-      ctx->avg1_pending = true;
-  }
+  e = launch_assign_avg(g, ws, ptr5(s_cls), ptr5(s_box), gt_boxes, gt_labels, gt_offsets, pad_hw, b->gt_inds,
+                        b->num_pos, b->avg, main);
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_step_prepare assignment");
 }
 

@@ -176,8 +176,7 @@ __global__ void __launch_bounds__(kCandThreads) atss_candidates_kernel(Geo g, Wo
 __global__ void __launch_bounds__(256) atss_finalize_kernel(Geo g, Workspace ws, const int32_t* __restrict__ pad_hw,
                                                             const int32_t* __restrict__ gt_offsets,
                                                             int32_t* __restrict__ gt_inds,
-                                                            int32_t* __restrict__ num_pos,
-                                                            float* __restrict__ avg0) {
+                                                            int32_t* __restrict__ num_pos) {
   const int n = blockIdx.y;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a < g.A) atss_decode_anchor(g, ws, pad_hw, gt_offsets, gt_inds, n, a);
@@ -193,26 +192,11 @@ __global__ void __launch_bounds__(256) atss_finalize_kernel(Geo g, Workspace ws,
   __syncthreads();
   if (!last) return;
   __threadfence();
-  // avg0 (optional) = sum_img max(num_pos, 1) (sampling_result.py:96-100): the assignment does
-  // not depend on the student, so the first avg factor -- all the QFL sweep needs -- exists
-  // here already, long before the positives prepass has produced the second one
-  __shared__ int s_cnt[256 / 32];
-  int cnt = 0;
   for (int i = threadIdx.x; i < g.n_img; i += blockDim.x) {
-    const int np = ((volatile int*)ws.pos_counter)[i];
-    num_pos[i] = np;
+    num_pos[i] = ((volatile int*)ws.pos_counter)[i];
     ws.pos_counter[i] = 0;
-    cnt += max(np, 1);
   }
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int total = 0;
-    for (int w = 0; w < 256 / 32; ++w) total += s_cnt[w];
-    if (avg0) avg0[0] = (float)total;
-    ws.counters[3] = 0u;
-  }
+  if (threadIdx.x == 0) ws.counters[3] = 0u;
 }
 
 cudaError_t launch_atss_candidates(const Geo& g, const Workspace& ws, const float* gt_boxes, const int32_t* gt_offsets,
@@ -225,12 +209,12 @@ cudaError_t launch_atss_candidates(const Geo& g, const Workspace& ws, const floa
 
 cudaError_t launch_atss(const Geo& g, const Workspace& ws, const float* gt_boxes, const int64_t* gt_labels,
                         const int32_t* gt_offsets, const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos,
-                        float* avg0, cudaStream_t st) {
+                        cudaStream_t st) {
   (void)gt_labels;
   cudaError_t e = launch_atss_candidates(g, ws, gt_boxes, gt_offsets, pad_hw, st);
   if (e != cudaSuccess) return e;
   ERD_LAUNCH(kKAtssFin, st,
-             (atss_finalize_kernel<<<dim3((g.A + 255) / 256, g.n_img), 256, 0, st>>>(g, ws, pad_hw, gt_offsets, gt_inds, num_pos, avg0)));
+             (atss_finalize_kernel<<<dim3((g.A + 255) / 256, g.n_img), 256, 0, st>>>(g, ws, pad_hw, gt_offsets, gt_inds, num_pos)));
   return cudaGetLastError();
 }
 

@@ -230,14 +230,16 @@ cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, con
 // ---------------------------------------------------------------- host launchers (one per .cu)
 cudaError_t launch_atss_candidates(const Geo& g, const Workspace& ws, const float* gt_boxes, const int32_t* gt_offsets,
                                    const int32_t* pad_hw, cudaStream_t st);
-// avg0: NULL, or where the decode's last block publishes the first avg factor
 cudaError_t launch_atss(const Geo& g, const Workspace& ws, const float* gt_boxes, const int64_t* gt_labels,
                         const int32_t* gt_offsets, const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos,
-                        float* avg0, cudaStream_t st);
-// avg0_done: avg[0] was already published by launch_atss (and possibly reduced): write avg[1] only
+                        cudaStream_t st);
+// atss_finalize + pos_prepass in one launch (the step's student-side chain is latency bound)
+cudaError_t launch_assign_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
+                              const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                              const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos, float* avg, cudaStream_t st);
 cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
                        const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
-                       const int32_t* gt_inds, const int32_t* num_pos, float* avg, bool avg0_done, cudaStream_t st);
+                       const int32_t* gt_inds, const int32_t* num_pos, float* avg, cudaStream_t st);
 cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_inds, const int32_t* box_count,
                        const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count, uint8_t* sel_flags,
                        cudaStream_t st, cudaEvent_t prepped, cudaEvent_t resolved);
@@ -269,7 +271,6 @@ struct LossStreams {
   cudaStream_t late;                  // high-priority helper: positives' rows, candidates' rows, take-back
   cudaEvent_t fork, pos_done, early_done, late_done, main_done;
   cudaEvent_t cleared;                // may be null: gradient tensors not pre-cleared by erd_step_prepare
-  cudaEvent_t avg1_done;              // may be null: positives prepass already ordered before the caller's stream
   cudaEvent_t sel_ready;              // may be null: ERS selection already ordered before the caller's stream
   cudaEvent_t nms_done;               // may be null: NMS already ordered before the caller's stream
 };

@@ -93,14 +93,13 @@ constexpr int kPosThreads = 256;
 
 struct PosArgs {
   Ptr5 s_cls, s_box;
-  MPtr5 g_box, g_cls;     // GRAD=true only
+  MPtr5 g_box;
   const float* gt_boxes;
   const int64_t* gt_labels;
   const int32_t* gt_offsets;
   const int32_t* gt_inds;
   const int32_t* num_pos;
   float* avg;             // GRAD=false: written by the last block; GRAD=true: read
-  bool avg0_done;         // GRAD=false: avg[0] already published (and possibly reduced) by the ATSS decode
   const float* upstream;
   const unsigned int* skip_flag;
 };
@@ -203,16 +202,6 @@ __device__ __forceinline__ void pos_item(const Geo& g, const Workspace& ws, cons
     else gd = g_uni * wid + g_ih * pick_gt(ty2, py2) + g_eh * pick_gt(py2, ty2);                  // d/dy2
     const float cb = upstream_of(A.upstream, acc_bbox(l)) * g.w_bbox / (1.0f + kEps32) / avg2 * w * gd;
     const float cd = upstream_of(A.upstream, acc_dfl(l)) * g.w_dfl / 4.0f / avg2 * w;
-    // the positive's label channel of the QFL (gfocal_loss.py:47-50): soft target = the IoU
-    // score computed above; the class sweep treats this one element as not its own
-    if (side == 0) {
-      const float* xs = A.s_cls.p[l] + ((size_t)n * g.C + g.ori + (int)lab) * HW + hw;
-      const QflTerm tp = qfl_pos(__ldg(xs), iou);
-      const float inv_avg1 = 1.0f / (float)((double)A.avg[0] + (double)kEps32);          // losses/utils.py:60-61
-      A.g_cls.p[l][((size_t)n * g.C + g.ori + (int)lab) * HW + hw] =
-          upstream_of(A.upstream, acc_cls(l)) * g.w_cls * inv_avg1 * tp.grad;
-      atomicAdd(ws.loss_acc + acc_cls(l), (double)tp.loss);
-    }
     // compact copy (the candidates' kernels merge it) + the gradient tensor itself
     float* row = ws.pos_rows + ((size_t)n * g.pos_cap + p) * kBoxCh + side * kBins;
     float* gp = A.g_box.p[l] + ((size_t)n * kBoxCh + side * kBins) * HW + hw;
@@ -272,12 +261,87 @@ __global__ void __launch_bounds__(kPosThreads) pos_kernel(Geo g, Workspace ws, P
     if (threadIdx.x == 2 * kLevels) A.avg[1] = (float)v;
   }
   if (threadIdx.x == 32) {
-    if (!A.avg0_done) {
-      long long cnt = 0;
-      for (int i = 0; i < g.n_img; ++i) cnt += max(A.num_pos[i], 1);
-      A.avg[0] = (float)cnt;
-    }
+    long long cnt = 0;
+    for (int i = 0; i < g.n_img; ++i) cnt += max(A.num_pos[i], 1);
+    A.avg[0] = (float)cnt;
     ws.counters[0] = 0u;
+  }
+}
+
+// ATSS decode + positives prepass in ONE launch (erd_step_prepare): the student-side chain in
+// front of the sweeps is a sequence of short latency-bound kernels, so every launch boundary
+// and every list round trip removed from it moves the sweeps earlier.  Per anchor like
+// atss_finalize_kernel; a warp that found positives then works them off eight at a time
+// (lane = positive-in-batch x side) with the body of pos_kernel<false>.  The last block
+// publishes num_pos and both avg factors.
+constexpr int kAssignPer = 4;   // anchors per thread: the whole grid is one wave
+
+__global__ void __launch_bounds__(256) assign_prepass_kernel(Geo g, Workspace ws, PosArgs A,
+                                                             const int32_t* __restrict__ pad_hw,
+                                                             int32_t* __restrict__ gt_inds,
+                                                             int32_t* __restrict__ num_pos) {
+  const int n = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  __shared__ double s_acc[2 * kLevels + 1];
+  if (threadIdx.x < 2 * kLevels + 1) s_acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  // one batch of independent loads: the argmax-table entries of this thread's anchors
+  const int a0 = blockIdx.x * (256 * kAssignPer) + threadIdx.x;
+  unsigned long long key[kAssignPer];
+#pragma unroll
+  for (int i = 0; i < kAssignPer; ++i) {
+    const int a = a0 + i * 256;
+    key[i] = a < g.A ? ws.atss_key[(size_t)n * g.A + a] : 0ull;
+  }
+  const int pad_h = pad_hw[n * 2], pad_w = pad_hw[n * 2 + 1], first_gt = A.gt_offsets[n];
+#pragma unroll
+  for (int i = 0; i < kAssignPer; ++i) {
+    const int a = a0 + i * 256;
+    const int gidx = a < g.A ? atss_decode_key(g, ws, pad_h, pad_w, first_gt, gt_inds, n, a, key[i]) : -1;
+    unsigned todo = __ballot_sync(0xffffffffu, gidx >= 0);
+    while (todo) {   // warp-uniform
+      // the (lane >> 2)-th positive still to do, if there is one
+      unsigned m = todo;
+      for (int k = 0; k < (lane >> 2); ++k) m &= m - 1;
+      const bool live = m != 0;
+      const int src = live ? __ffs(m) - 1 : 0;
+      const int pa = __shfl_sync(0xffffffffu, a, src);
+      const int pg = __shfl_sync(0xffffffffu, gidx, src);
+      pos_item<false>(g, ws, A, n, live, live ? pa : 0, live ? pg : 0, 0, lane & 3, s_acc, 1.0f);
+      for (int k = 0; k < 8 && todo; ++k) todo &= todo - 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kLevels + 1 && s_acc[threadIdx.x] != 0.0)
+    atomicAdd(ws.pre_acc + threadIdx.x, s_acc[threadIdx.x]);
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(ws.counters + 3, 1u) == gridDim.x * gridDim.y - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 2 * kLevels + 1) {
+    const double v = ((volatile double*)ws.pre_acc)[threadIdx.x];
+    ws.pre_pub[threadIdx.x] = v;
+    ws.pre_acc[threadIdx.x] = 0.0;
+    if (threadIdx.x == 2 * kLevels) A.avg[1] = (float)v;
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 64) {   // avg[0] = sum_img max(num_pos, 1) (sampling_result.py:96-100)
+    long long cnt = 0;
+    for (int i = lane; i < g.n_img; i += 32) {
+      const int np = ((volatile int*)ws.pos_counter)[i];
+      num_pos[i] = np;
+      ws.pos_counter[i] = 0;
+      cnt += max(np, 1);
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) {
+      A.avg[0] = (float)cnt;
+      ws.counters[3] = 0u;
+    }
   }
 }
 
@@ -298,18 +362,18 @@ __device__ __forceinline__ void cls_tile(const Geo& g, const Workspace& ws, cons
   // QFL over new-class channels of every anchor (:260-261,317-320)
   const int c0 = (part - parts_old) * kSweepCh, c1 = min(c0 + kSweepCh, g.cn);
   int label[4];
-  float lw[4];
-  bool has_label = false;
+  float score[4], lw[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int gi = q.ok[k] ? A.gt_inds[abase + q.hw[k]] : -1;
     lw[k] = gi >= 0 ? 1.0f : 0.0f;                                  // label_weights, gfl_head.py:650-655,663
     label[k] = -1;
+    score[k] = 0.f;
     if (gi > 0) {
       const long long lab = A.gt_labels[A.gt_offsets[n] + gi - 1];
       if (lab >= c0 && lab < c1) {
         label[k] = (int)lab;
-        has_label = true;
+        score[k] = ws.pos_score[abase + q.hw[k]];
       }
     }
   }
@@ -319,24 +383,7 @@ __device__ __forceinline__ void cls_tile(const Geo& g, const Workspace& ws, cons
   float gs[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) gs[k] = lw[k] * scale_cls;
-  // The label channel of a positive has a soft target (its IoU score), which only exists after
-  // the positives prepass: that one element -- value and loss -- belongs to pos_kernel<true>,
-  // so this sweep depends on the assignment alone.  Threads holding such an element (rare)
-  // take an element-wise path around it; everybody else runs the branch-free loop.
-  if (has_label) {
-    for (int c = c0; c < c1; ++c) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (!q.ok[k] || c == label[k]) continue;
-        const size_t off = (size_t)(g.ori + c) * HW + q.hw[k];
-        const QflTerm t = qfl_neg(scls[off]);
-        loss_cls = fmaf(lw[k], t.loss, loss_cls);
-        gcls[off] = gs[k] * t.grad;
-      }
-    }
-    out_loss += loss_cls;
-    return;
-  }
+  // every element as a negative first: the hot loop stays branch-free ...
 #pragma unroll 4
   for (int c = c0; c < c1; ++c) {
     float x[4], gr[4];
@@ -348,6 +395,16 @@ __device__ __forceinline__ void cls_tile(const Geo& g, const Workspace& ws, cons
       gr[k] = gs[k] * t.grad;
     }
     q.store(gcls + (size_t)(g.ori + c) * HW, gr);
+  }
+  // ... then the label channel of the (rare) positives is redone with its soft target
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (label[k] < 0) continue;
+    const size_t off = (size_t)(g.ori + label[k]) * HW + q.hw[k];
+    const float x = scls[off];
+    const QflTerm tp = qfl_pos(x, score[k]), tn = qfl_neg(x);
+    loss_cls += lw[k] * (tp.loss - tn.loss);
+    gcls[off] = gs[k] * tp.grad;
   }
   out_loss += loss_cls;
 }
@@ -677,7 +734,7 @@ static int pos_grid_x(const Geo& g) {
 
 cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
                        const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
-                       const int32_t* gt_inds, const int32_t* num_pos, float* avg, bool avg0_done, cudaStream_t st) {
+                       const int32_t* gt_inds, const int32_t* num_pos, float* avg, cudaStream_t st) {
   PosArgs a;
   a.s_cls = s_cls;
   a.s_box = s_box;
@@ -688,11 +745,32 @@ cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, con
   a.gt_inds = gt_inds;
   a.num_pos = num_pos;
   a.avg = avg;
-  a.avg0_done = avg0_done;
-  for (int l = 0; l < kLevels; ++l) a.g_cls.p[l] = nullptr;
   a.upstream = nullptr;
   a.skip_flag = nullptr;
   ERD_LAUNCH(kKAvg, st, (pos_kernel<false><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, st>>>(g, ws, a)));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_assign_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
+                              const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                              const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos, float* avg, cudaStream_t st) {
+  cudaError_t e = launch_atss_candidates(g, ws, gt_boxes, gt_offsets, pad_hw, st);
+  if (e != cudaSuccess) return e;
+  PosArgs a;
+  a.s_cls = s_cls;
+  a.s_box = s_box;
+  for (int l = 0; l < kLevels; ++l) a.g_box.p[l] = nullptr;
+  a.gt_boxes = gt_boxes;
+  a.gt_labels = gt_labels;
+  a.gt_offsets = gt_offsets;
+  a.gt_inds = gt_inds;
+  a.num_pos = num_pos;
+  a.avg = avg;
+  a.upstream = nullptr;
+  a.skip_flag = nullptr;
+  ERD_LAUNCH(kKAvg, st,
+             (assign_prepass_kernel<<<dim3((g.A + 256 * kAssignPer - 1) / (256 * kAssignPer), g.n_img), 256, 0, st>>>(
+                 g, ws, a, pad_hw, gt_inds, num_pos)));
   return cudaGetLastError();
 }
 
@@ -704,8 +782,6 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
   p.s_cls = a.s_cls;
   p.s_box = a.s_box;
   p.g_box = a.g_box;
-  p.g_cls = a.g_cls;
-  p.avg0_done = false;
   p.gt_boxes = a.gt_boxes;
   p.gt_labels = a.gt_labels;
   p.gt_offsets = a.gt_offsets;
@@ -744,10 +820,6 @@ cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cu
       if (e == cudaSuccess) e = cudaStreamWaitEvent(hi, ls->pos_done, 0);
       if (e != cudaSuccess) return e;
     }
-  }
-  if (ls && ls->avg1_done) {   // avg[1] and the prepass sums: first needed here
-    e = cudaStreamWaitEvent(hi, ls->avg1_done, 0);
-    if (e != cudaSuccess) return e;
   }
   ERD_LAUNCH(kKPosGrad, hi, (pos_kernel<true><<<dim3(pos_grid_x(g), g.n_img), kPosThreads, 0, hi>>>(g, ws, p)));
   if (ls && ls->sel_ready) {

@@ -11,7 +11,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _native as N
-from .dist_utils import peer_exchange, reduce_mean_, world
+from .dist_utils import peer_exchange, reduce_mean_
 
 STRIDES = (8, 16, 32, 64, 128)
 
@@ -240,8 +240,7 @@ class ErdPath:
         N.check(self.lib.erd_step_prepare(
             self._context(p.device), C.byref(p.shape), _ptrs(t_cls), _ptrs(t_box), _ptrs(s_cls), _ptrs(s_box),
             p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(),
-            self.nms_iou_thr, C.byref(p.bufs), p.ws.data_ptr(), _stream(),
-            (N.PREPARE_ERS_DONE if ers_done else 0) | (N.PREPARE_JOIN_AVG if world()[1] > 1 else 0)),
+            self.nms_iou_thr, C.byref(p.bufs), p.ws.data_ptr(), _stream(), 1 if ers_done else 0),
             'erd_step_prepare')
         if not ers_done:
             p.ers_generation += 1

@@ -204,11 +204,6 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
 /* flags for erd_step_prepare */
 #define ERD_PREPARE_ERS_DONE 1u /* erd_ers_select already ran on these teacher tensors (sel_pos);
                                    its lists, counts, sel_flags and the teacher cache are reused */
-#define ERD_PREPARE_JOIN_AVG 2u /* order avg[1] on `stream` too before returning.  Without it only
-                                   avg[0] (known from the assignment alone, all the class sweep needs)
-                                   is ordered on `stream`; the positives prepass that produces avg[1]
-                                   keeps running on a helper stream and erd_loss_fwd_bwd(ctx, ...) joins
-                                   it.  Set it when the caller reads or all-reduces avg in between. */
 
 /* reduce_mean of the two avg factors (mmdet/utils/dist_utils.py:59-65, call sites
  * gfl_head_increment_erd.py:390-391,406-407) over NVLink peer memory, for one process per GPU
