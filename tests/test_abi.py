@@ -64,3 +64,32 @@ def test_null_pointers_are_rejected_before_any_launch():
     assert lib.erd_atss_assign(C.byref(s), None, None, None, None, None, None, None, None) == -2
     assert lib.erd_teacher_nms(C.byref(s), None, None, None, 0.005, None, None, None, None, None) == -2
     assert lib.erd_launch_count() == 0
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The header is plain C: compile a probe with gcc and compare sizeof / offsetof of every
+    struct that crosses the boundary with the ctypes mirror in erd_b200/_native.py."""
+    import os
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        import pytest
+        pytest.skip('no gcc')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {'ErdShape': N.ErdShape, 'ErdSizes': N.ErdSizes, 'ErdStepBuffers': N.ErdStepBuffers}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "erd_b200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'probe.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'probe'
+    subprocess.run([gcc, '-std=c99', '-I', os.path.join(root, 'include'), str(src), '-o', str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(out[name]) == C.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(out[f'{name}.{field}']) == getattr(cls, field).offset, f'{name}.{field}'
