@@ -47,6 +47,8 @@ class PeerAvgExchange:
         rank, ws = world()
         if ws < 2 or ws > 64 or os.environ.get('ERD_PEER_EXCHANGE', '1') == '0':
             return None
+        if torch.device(device).type != 'cuda' or dist.get_backend() != 'nccl':
+            return None
         if int(os.environ.get('LOCAL_WORLD_SIZE', ws)) != ws:
             return None                      # peer memory is a single-node mechanism
         try:

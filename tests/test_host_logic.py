@@ -85,6 +85,10 @@ reduce_mean_(avg)
 exp0 = sum(max(p, 1) for p in num_pos) / 2.0
 exp1 = sum(wsum) / 2.0
 assert abs(float(avg[0]) - exp0) < 1e-6 and abs(float(avg[1]) - exp1) < 1e-6, (avg, exp0, exp1)
+# the NVLink peer-memory exchange is a CUDA + NCCL mechanism: on this group it must decline
+# (the caller then keeps the all-reduce above) instead of trying to map device memory
+from erd_b200.dist_utils import PeerAvgExchange
+assert PeerAvgExchange.create(None, torch.device('cpu')) is None
 dist.destroy_process_group()
 print('ok', rank)
 '''
@@ -100,3 +104,9 @@ def test_reduce_mean_world_size_two_gloo(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all('ok' in o for o in outs)
+
+
+def test_peer_exchange_declines_without_a_process_group():
+    from erd_b200.dist_utils import PeerAvgExchange
+    import torch
+    assert PeerAvgExchange.create(None, torch.device('cpu')) is None
