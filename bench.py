@@ -43,6 +43,10 @@ BYTES_PER_ANCHOR = {'path': 1616, 'ers_scan': 4 * (ORI + 68), 'qfl_sweep': 4 * (
 # profiles/r1c_traffic.csv.  Kernels that only write (zero_fill) or write as much as they read (qfl_sweep)
 # show less than their algorithmic bytes: dirty lines still sit in the 126 MB L2 when the kernel ends and
 # are written back during the next one.
+# per-launch duration of the same kernels run one at a time (ncu launch list, cold cache, serialised):
+# profiles/r1d_launches.csv.  Inside the step they overlap each other and the latency chains, so the live
+# per-kernel durations bench.py measures are longer; both are reported.
+NCU_ALONE_US = {'ers_scan': 43.56, 'qfl_sweep': 29.76, 'zero_fill': 28.93}
 NCU_TRAFFIC_BYTES = {'ers_scan': 155160448 + 10928896, 'qfl_sweep': 58870528 + 13393664,
                      'zero_fill': 14507 + 91372203}
 
@@ -342,6 +346,11 @@ def run_ours(args):
                          'frac': (achieved / peak) if achieved else None,
                          'traffic': NCU_TRAFFIC_BYTES.get(dom) if n == IMGS_PER_GPU else None,
                          'traffic_source': 'profiles/r1c_traffic.csv (ncu, per launch, bytes)',
+                         'kernel_alone': ({'us': NCU_ALONE_US[dom],
+                                           'achieved_gbs': round(n * A * BYTES_PER_ANCHOR[dom] / (NCU_ALONE_US[dom] * 1e-6) / 1e9, 1),
+                                           'frac': round(n * A * BYTES_PER_ANCHOR[dom] / (NCU_ALONE_US[dom] * 1e-6) / 1e9 / peak, 3),
+                                           'source': 'profiles/r1d_launches.csv (ncu launch list, kernel run alone)'}
+                                          if n == IMGS_PER_GPU and dom in NCU_ALONE_US else None),
                          'peak_source': 'measured' if peaks else 'fallback',
                          'algorithmic_bytes_per_anchor': BYTES_PER_ANCHOR[dom],
                          'path_bytes_per_anchor': BYTES_PER_ANCHOR['path'],
