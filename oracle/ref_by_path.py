@@ -80,6 +80,13 @@ class InstanceData:
             return len(v)
         return 0
 
+    # the inference post-process indexes its results (base_dense_head.py:474,481-484)
+    def __getitem__(self, item):
+        return InstanceData(**{k: v[item] for k, v in self.__dict__.items()})
+
+    def pop(self, k):
+        return self.__dict__.pop(k)
+
 
 class ConfigDict(dict):
     def __getattr__(self, k):
@@ -227,6 +234,7 @@ def load_reference(batched_nms=None):
     sb.bbox_overlaps = bo.bbox_overlaps
     tr = _load('mmdet.structures.bbox.transforms', 'mmdet/structures/bbox/transforms.py')
     sb.distance2bbox, sb.bbox2distance = tr.distance2bbox, tr.bbox2distance
+    sb.get_box_wh, sb.scale_boxes = tr.get_box_wh, tr.scale_boxes   # base_dense_head.py:461,471
 
     ml = 'mmdet.models.losses.'
     _load(ml + 'utils', 'mmdet/models/losses/utils.py')
