@@ -47,7 +47,7 @@ class PeerAvgExchange:
         rank, ws = world()
         if ws < 2 or ws > 64 or os.environ.get('ERD_PEER_EXCHANGE', '1') == '0':
             return None
-        if torch.device(device).type != 'cuda' or dist.get_backend() != 'nccl':
+        if torch.device(device).type != 'cuda' or 'nccl' not in str(dist.get_backend()):
             return None
         if int(os.environ.get('LOCAL_WORLD_SIZE', ws)) != ws:
             return None                      # peer memory is a single-node mechanism
