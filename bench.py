@@ -37,8 +37,7 @@ ORI, NUM_CLASSES, REG_MAX = 40, 80, 16
 # non-zero rows -- ERS rows, positives, box candidates -- are written over it by small list-driven kernels,
 # which are also the only readers of the student's old-class and box logits)
 CN = NUM_CLASSES - ORI
-BYTES_PER_ANCHOR = {'path': 1616, 'ers_scan': 4 * (ORI + 68), 'qfl_sweep': 4 * (CN + CN),
-                    'zero_fill': 4 * (ORI + 68)}
+BYTES_PER_ANCHOR = {'path': 1616, 'ers_scan': 4 * (ORI + 68), 'student_pass': 8 * (NUM_CLASSES + 68)}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload (16 images), from
 # profiles/r1c_traffic.csv.  Kernels that only write (zero_fill) or write as much as they read (qfl_sweep)
 # show less than their algorithmic bytes: dirty lines still sit in the 126 MB L2 when the kernel ends and
@@ -46,9 +45,8 @@ BYTES_PER_ANCHOR = {'path': 1616, 'ers_scan': 4 * (ORI + 68), 'qfl_sweep': 4 * (
 # per-launch duration of the same kernels run one at a time (ncu launch list, cold cache, serialised):
 # profiles/r1d_launches.csv.  Inside the step they overlap each other and the latency chains, so the live
 # per-kernel durations bench.py measures are longer; both are reported.
-NCU_ALONE_US = {'ers_scan': 43.56, 'qfl_sweep': 29.76, 'zero_fill': 28.93}
-NCU_TRAFFIC_BYTES = {'ers_scan': 155160448 + 10928896, 'qfl_sweep': 58870528 + 13393664,
-                     'zero_fill': 14507 + 91372203}
+NCU_ALONE_US = {}
+NCU_TRAFFIC_BYTES = {}
 
 
 def parse():
@@ -196,7 +194,7 @@ def run_ours(args):
 
     def step():
         # the two C-ABI calls around the 8-byte all-reduce; grads written into fixed buffers
-        path.prepare(plan, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls=g_cls, g_box=g_box)
+        path.prepare(plan, b.t_cls, b.t_box, b.s_cls, b.s_box)
         path.reduce_avg(plan)
         path.loss_fwd_bwd(plan, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls, g_box, losses, 1.0)
 
@@ -207,7 +205,7 @@ def run_ours(args):
 
     nk = lib.erd_profile_num_kernels()
     names = [lib.erd_profile_kernel_name(i).decode() for i in range(nk)]
-    dense = [k for k in ('ers_scan', 'qfl_sweep', 'zero_fill') if k in names]
+    dense = [k for k in ('ers_scan', 'student_pass') if k in names]
 
     def collect():
         tot, cnt = (C.c_float * nk)(), (C.c_int * nk)()

@@ -11,7 +11,7 @@ import os
 from . import build as _build
 
 MAX_LEVELS = 5
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class ErdShape(C.Structure):
@@ -32,8 +32,7 @@ class ErdSizes(C.Structure):
 
 class ErdStepBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('cls_inds', 'cls_count', 'box_inds', 'box_count', 'thr',
-                                           'sel_flags', 'gt_inds', 'num_pos', 'keep', 'keep_count', 'avg')] + \
-               [('g_cls', C.c_void_p * 5), ('g_box', C.c_void_p * 5)]   # optional early zero fill
+                                           'sel_flags', 'gt_inds', 'num_pos', 'keep', 'keep_count', 'avg')]
 
 
 PtrArray = C.c_void_p * MAX_LEVELS
@@ -49,6 +48,7 @@ SIGNATURES = {
     'erd_create': [C.POINTER(_P)],
     'erd_destroy': [_P],
     'erd_ers_select': [_SH, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P],
+    'erd_selection_replaced': [_SH, _P, _P],
     'erd_atss_assign': [_SH, _P, _P, _P, _P, _P, _P, _P, _P],
     'erd_avg_factors': [_SH, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P],
     'erd_teacher_nms': [_SH, _P, _P, _P, _F, _P, _P, _P, _P, _P],

@@ -79,16 +79,25 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->t_arg = (int*)take(NA * 4);
   ws->t_u = (float*)take(NA * 4);
   ws->t_dist = (float4*)take(NA * 16);
-  ws->ers_part = (double*)take((size_t)g.n_img * (g.A / 64 + kLevels) * 4 * 8);
+  const size_t tiles32 = (size_t)g.A / 32 + kLevels;   // >= sum_l ceil(hw_l / 32)
+  ws->ers_part = (double*)take((size_t)g.n_img * tiles32 * 4 * 8);
+  ws->img_cnt = (int*)take((size_t)g.n_img * 4);
+  ws->img_flag = (unsigned int*)take((size_t)g.n_img * 4);
+  ws->teacher_epoch = (unsigned int*)take(4);
+  ws->teacher_done = (unsigned int*)take(4);
+  ws->stash_valid = (unsigned int*)take(4);
+  ws->stash_cnt = (int*)take((size_t)g.n_img * 2 * 4);
+  ws->stash_base = (int2*)take((size_t)g.n_img * tiles32 * 8);
+  ws->stash_cls = (float*)take(NS * (size_t)((g.ori + 3) & ~3) * 4);
+  ws->stash_box = (float*)take(NS * (size_t)kBoxCh * 4);
   ws->atss_key = (unsigned long long*)take(NA * 8);
   ws->pos_list = (int2*)take(NA * 8);
   ws->pos_counter = (int*)take((size_t)g.n_img * 4);
-  ws->pos_score = (float*)take(NA * 4);
+  ws->pos_rec = (PosRec*)take(NA * sizeof(PosRec));
   ws->pre_acc = (double*)take((size_t)(2 * kLevels + 1) * 8);
   ws->pre_pub = (double*)take((size_t)(2 * kLevels + 1) * 8);
-  ws->pos_slot = (int*)take(NA * 4);
   ws->keep_raw = (int*)take(NS * 4);
-  ws->kd_loss = (float*)take(NS * 4);
+  ws->kd_loss = (float*)take(NA * 4);
   ws->pos_rows = (float*)take((size_t)g.n_img * g.pos_cap * kBoxCh * 4);
   ws->nms_nz = (unsigned long long*)take(NS * nms_nz_words(g.sel_cap) * 8);
   ws->counters = (unsigned int*)take(8 * 4);
@@ -133,12 +142,9 @@ static MPtr5 mptr5(float* const* p) {
 }
 
 struct ErdContext {
-  cudaStream_t side[3];          // [0] early box sectors, [1] teacher chain, [2] positives' rows + late box groups
-  cudaEvent_t fork, join[3], pos_done, sel_done, early_done, nms_all, clear_done;
-  bool clear_pending;            // gradient tensors below were zero-filled by erd_step_prepare
-  float* cleared_cls[kLevels];
-  float* cleared_box[kLevels];
-  bool nms_pending;              // join[1] recorded by erd_step_prepare, not yet waited on
+  cudaStream_t side;             // teacher chain: ERS scan + select -> NMS
+  cudaEvent_t fork, sel_done, nms_resolved, nms_all;
+  bool nms_pending;              // nms_resolved recorded by erd_step_prepare, not yet waited on
 };
 
 extern "C" {
@@ -174,23 +180,16 @@ int erd_workspace_init(const ErdShape* shape, void* wsp, void* stream) {
 int erd_create(ErdContext** ctx) {
   if (!ctx) return fail(ERD_ERR_NULL, "ctx is NULL");
   ErdContext* c = new ErdContext();
-  cudaError_t e = cudaSuccess;
-  // the NMS chain is short, serial and latency-bound: give it the highest priority so its few
-  // CTAs are not queued behind the bandwidth-bound kernels running beside it
+  // the teacher chain is short kernels behind one streaming pass: give it the highest priority so
+  // its few CTAs are not queued behind the bandwidth-bound student pass running beside it
   int prio_least = 0, prio_greatest = 0;
   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-  for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
-    e = cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, i == 0 ? prio_least : prio_greatest);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming);
-  }
+  cudaError_t e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_greatest);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->pos_done, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->clear_done, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->early_done, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->nms_all, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sel_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->nms_resolved, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->nms_all, cudaEventDisableTiming);
   c->nms_pending = false;
-  c->clear_pending = false;
   if (e != cudaSuccess) {
     delete c;
     return fail_cuda(e, "erd_create");
@@ -201,16 +200,11 @@ int erd_create(ErdContext** ctx) {
 
 int erd_destroy(ErdContext* c) {
   if (!c) return ERD_OK;
-  for (int i = 0; i < 3; ++i) {
-    cudaStreamDestroy(c->side[i]);
-    cudaEventDestroy(c->join[i]);
-  }
+  cudaStreamDestroy(c->side);
   cudaEventDestroy(c->fork);
-  cudaEventDestroy(c->pos_done);
-  cudaEventDestroy(c->clear_done);
-  cudaEventDestroy(c->early_done);
-  cudaEventDestroy(c->nms_all);
   cudaEventDestroy(c->sel_done);
+  cudaEventDestroy(c->nms_resolved);
+  cudaEventDestroy(c->nms_all);
   delete c;
   return ERD_OK;
 }
@@ -262,6 +256,17 @@ int erd_avg_factors(const ErdShape* shape, const float* const* s_cls, const floa
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_avg_factors");
 }
 
+int erd_selection_replaced(const ErdShape* shape, void* wsp, void* stream) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (!wsp) return fail(ERD_ERR_NULL, "erd_selection_replaced: NULL workspace");
+  Workspace ws;
+  carve(g, wsp, &ws);
+  cudaError_t e = cudaMemsetAsync(ws.stash_valid, 0, 4, (cudaStream_t)stream);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_selection_replaced");
+}
+
 int erd_teacher_nms(const ErdShape* shape, const int32_t* box_inds, const int32_t* box_count, const int32_t* pad_hw,
                     float iou_thr, int32_t* keep, int32_t* keep_count, uint8_t* sel_flags, void* wsp, void* stream) {
   Geo g;
@@ -286,8 +291,8 @@ static int nms_on_side_stream(ErdContext* ctx, const ErdShape* shape, const ErdS
   Workspace ws;
   carve(g, wsp, &ws);
   cudaError_t e = launch_nms(g, ws, b->box_inds, b->box_count, pad_hw, iou_thr, b->keep, b->keep_count, b->sel_flags,
-                             ctx->side[1], nullptr, ctx->join[1]);
-  if (e == cudaSuccess) e = cudaEventRecord(ctx->nms_all, ctx->side[1]);
+                             ctx->side, nullptr, ctx->nms_resolved);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->nms_all, ctx->side);
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_step_prepare nms");
 }
 
@@ -337,27 +342,13 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
   a.skip_flag = (upstream && skip_if_unit_upstream) ? ws.counters + 1 : nullptr;
   a.losses = losses;
   a.dlw = dist_loss_weight;
-  // With a context the box sectors that cannot depend on the NMS are written on a helper
-  // stream beside the class sweep; the NMS forked by erd_step_prepare is joined only in front
-  // of the late box launch.
+  // With a context the teacher chain forked by erd_step_prepare is joined where its results are
+  // consumed: the ERS selection in front of the student pass, the NMS in front of the take-back.
   cudaError_t e;
   if (ctx) {
     LossStreams ls;
-    ls.early = ctx->side[0];
-    ls.late = ctx->side[2];
-    ls.pos_done = ctx->pos_done;
-    ls.late_done = ctx->join[2];
-    ls.main_done = ctx->join[0];
-    ls.fork = ctx->fork;
-    ls.early_done = ctx->early_done;
-    // pre-cleared by erd_step_prepare only if these are the very tensors it was given
-    bool cleared = ctx->clear_pending;
-    for (int l = 0; l < kLevels && cleared; ++l)
-      cleared = ctx->cleared_cls[l] == g_cls[l] && ctx->cleared_box[l] == g_box[l];
-    ls.cleared = cleared ? ctx->clear_done : nullptr;
-    ctx->clear_pending = false;
     ls.sel_ready = ctx->nms_pending ? ctx->sel_done : nullptr;
-    ls.nms_done = ctx->nms_pending ? ctx->join[1] : nullptr;
+    ls.nms_done = ctx->nms_pending ? ctx->nms_resolved : nullptr;
     const bool had_nms = ctx->nms_pending;
     e = launch_loss(g, ws, a, (cudaStream_t)stream, &ls);
     // the score-ordered keep list is an output only: join it last
@@ -381,38 +372,31 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
     ctx->nms_pending = false;
   }
   // Stream layout.  The caller's stream only carries what the avg-factor all-reduce needs
-  // (ATSS + positives prepass), so the caller can all-reduce and start the QFL sweep at once.
-  // The teacher side runs beside it: side[1] = ERS scan + select (sel_done) -> NMS (join[1] when
-  // the survivors are marked, nms_all when the keep list is ordered).
-  // erd_loss_fwd_bwd(ctx, ...) joins them exactly where their results are consumed.
+  // (ATSS + positives prepass).  The teacher side runs beside it on ctx->side: ERS scan + select
+  // (sel_done) -> NMS (nms_resolved when the survivors are marked, nms_all when the keep list is
+  // ordered).  erd_loss_fwd_bwd(ctx, ...) joins them exactly where their results are consumed.
   if (e == cudaSuccess) e = cudaEventRecord(ctx->fork, main);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side[1], ctx->fork, 0);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side, ctx->fork, 0);
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork");
   int rc = 0;
-  // optional: zero fill of the gradient tensors now, beside the scan (low priority)
-  ctx->clear_pending = false;
-  if (b->g_cls[0] || b->g_box[0]) {
-    Geo gz;
-    rc = make_geo(shape, &gz);
+  if (!(flags & ERD_PREPARE_ERS_DONE)) {
+    // the student pass only needs the teacher pass (flags + stash); the ordered lists are for the NMS
+    Geo gt;
+    rc = make_geo(shape, &gt);
     if (rc) return rc;
-    MPtr5 zc, zb;
-    for (int l = 0; l < kLevels; ++l) {
-      if (!b->g_cls[l] || !b->g_box[l]) return fail(ERD_ERR_NULL, "erd_step_prepare: g_cls / g_box must be all set or all NULL");
-      zc.p[l] = ctx->cleared_cls[l] = b->g_cls[l];
-      zb.p[l] = ctx->cleared_box[l] = b->g_box[l];
-    }
-    set_vec(&gz, nullptr, nullptr, b->g_cls, b->g_box);
-    e = cudaStreamWaitEvent(ctx->side[0], ctx->fork, 0);
-    if (e == cudaSuccess) e = launch_zero_fill(gz, zc, zb, nullptr, ctx->side[0]);
-    if (e == cudaSuccess) e = cudaEventRecord(ctx->clear_done, ctx->side[0]);
-    if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare zero fill");
-    ctx->clear_pending = true;
+    if (NULLS(t_cls) || NULLS(t_box) || !b->cls_inds || !b->cls_count || !b->box_inds || !b->box_count || !b->thr ||
+        !b->sel_flags || !wsp)
+      return fail(ERD_ERR_NULL, "erd_step_prepare: NULL ERS argument");
+    set_vec(&gt, t_cls, t_box);
+    Workspace wt;
+    carve(gt, wsp, &wt);
+    e = launch_teacher_pass(gt, wt, ptr5(t_cls), ptr5(t_box), b->thr, b->sel_flags, ctx->side);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->sel_done, ctx->side);
+    if (e == cudaSuccess)
+      e = launch_ers_lists(gt, wt, b->cls_inds, b->cls_count, b->box_inds, b->box_count, b->thr, b->sel_flags, ctx->side);
+  } else {
+    e = cudaEventRecord(ctx->sel_done, ctx->side);
   }
-  if (!(flags & ERD_PREPARE_ERS_DONE))
-    rc = erd_ers_select(shape, t_cls, t_box, b->cls_inds, b->cls_count, b->box_inds, b->box_count, b->thr,
-                        b->sel_flags, wsp, ctx->side[1]);
-  if (rc) return rc;
-  e = cudaEventRecord(ctx->sel_done, ctx->side[1]);
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare sel");
   if (!b->box_inds || !b->box_count || !pad_hw || !b->keep || !b->keep_count || !b->sel_flags || !wsp)
     return fail(ERD_ERR_NULL, "erd_step_prepare: NULL NMS buffer");

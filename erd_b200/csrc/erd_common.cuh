@@ -15,6 +15,16 @@ constexpr int kTileThreads = 128;     // 4 anchors per thread
 constexpr int kTopK = 9;              // ATSSAssigner topk (config train_cfg.assigner)
 constexpr float kEps32 = 1.1920928955078125e-07f;  // torch.finfo(float32).eps
 
+// Per-anchor record of an assigned (positive) anchor, written by the positives' prepass and
+// fetched by the student pass with two 16-byte asynchronous copies.
+struct __align__(32) PosRec {
+  float4 gt;      // assigned GT box, px
+  int label;      // new-class label, -1 when the GT's label lies outside the new-class range
+  float score;    // IoU quality score of the decoded box (detached)   gfl_head_increment_erd.py:289-292
+  float w;        // weight_targets: max_c sigmoid(new-class logits)  :283-284
+  int pslot;      // index in the image's positives list / row of ws.pos_rows
+};
+
 struct Ptr5 {
   const float* p[kLevels];
 };
@@ -42,17 +52,25 @@ struct Workspace {
   int* t_arg;                     // [N][A] teacher argmax class
   float* t_u;                     // [N][A] teacher max raw box logit
   float4* t_dist;                 // [N][A] teacher softmax-integral distances (l,t,r,b), bin units
-  double* ers_part;               // [N][tiles][4] per-CTA sums: m, m^2, u, u^2
+  double* ers_part;               // [N][tiles of 32 anchors][4] per-tile sums: m, m^2, u, u^2
+  int* img_cnt;                   // [N] scanned tiles of the image (teacher pass; zero between launches)
+  unsigned int* img_flag;         // [N] == the launch's epoch once the image's thresholds are published
+  unsigned int* teacher_epoch;    // [1] stamp of the last completed teacher pass
+  unsigned int* teacher_done;     // [1] finished consumer warps (ticket; zero between launches)
+  unsigned int* stash_valid;      // [1] != 0: flags + stash below describe the current ERS selection
+  int* stash_cnt;                 // [N][2] rows allocated in the stash (class, box) == K_cls, K_bbox after the pass
+  int2* stash_base;               // [N][tiles of 32 anchors] first (class, box) stash row of the tile's selected anchors
+  float* stash_cls;               // [N][sel_cap][ori rounded up to 4] teacher class logits of the ERS class rows
+  float* stash_box;               // [N][sel_cap][68] teacher box logits of the ERS box candidates
   unsigned long long* atss_key;   // [N][A] packed (iou bits << 32 | ~gt) argmax table
   int2* pos_list;                 // [N][A] (anchor, global GT row) of the assigned anchors (unordered)
   int* pos_counter;               // [N] running length of pos_list (zero between steps)
-  float* pos_score;               // [N][A] IoU quality score, defined at positives only
+  struct PosRec* pos_rec;         // [N][A] what the student pass needs of a positive, defined at positives only
   double* pre_pub;                // [2L+1] pre_acc of the last avg-factor pass, read by finalize
   double* pre_acc;                // [2L+1] sum w(1-giou) per level, sum w*dfl per level, sum w
   int* keep_raw;                  // [N][sel_cap] NMS survivors as list positions, unordered (resolve pass)
-  float* kd_loss;                 // [N][sel_cap] weighted KL of every ERS box candidate
-  int* pos_slot;                  // [N][A] index into pos_list / pos_rows, defined at positives only
-  float* pos_rows;                // [N][pos_cap][68] box-logit gradient rows of the positives
+  float* kd_loss;                 // [N][A] weighted KL of every ERS box candidate, at its anchor
+  float* pos_rows;                // [N][pos_cap][68] box-logit gradient rows of positives that are also ERS box candidates
   unsigned long long* nms_nz;     // [N][sel_cap][nz_words] which words of a predecessor row are non-zero
   unsigned int* counters;         // [8] last-block tickets
   float* nms_score;               // [N][sel_cap] teacher confidence of each selected row, list order
@@ -155,7 +173,7 @@ struct Quad {
 
 // ---------------------------------------------------------------- launch accounting (profile.cu)
 enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan, kKNmsOrder,
-                kKUpCheck, kKZero, kKLossMain, kKClsOld, kKPosGrad, kKBoxKd, kKBoxSweep, kNumKernels };
+                kKUpCheck, kKStudent, kKBoxFix, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 // Developer build only (-DERD_DEV_ABLATE): ERD_ABLATE=<mask> skips kernels by id to measure what
@@ -211,7 +229,7 @@ __device__ __forceinline__ int atss_decode_key(const Geo& g, const Workspace& ws
   if (out <= 0) return -1;
   const int slot = atomicAdd(ws.pos_counter + n, 1);
   ws.pos_list[(size_t)n * g.A + slot] = make_int2(a, first_gt + out - 1);
-  ws.pos_slot[(size_t)n * g.A + a] = slot;
+  ws.pos_rec[(size_t)n * g.A + a].pslot = slot;
   return first_gt + out - 1;
 }
 
@@ -227,6 +245,11 @@ __device__ __forceinline__ int atss_decode_anchor(const Geo& g, const Workspace&
 cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box,
                        int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds, int32_t* box_count,
                        float* thr, uint8_t* sel_flags, cudaStream_t st);
+// the two halves of launch_ers: the streaming pass (flags, thresholds, cache, stash) and the ordered lists
+cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box, float* thr,
+                                uint8_t* sel_flags, cudaStream_t st);
+cudaError_t launch_ers_lists(const Geo& g, const Workspace& ws, int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds,
+                             int32_t* box_count, const float* thr, uint8_t* sel_flags, cudaStream_t st);
 // ---------------------------------------------------------------- host launchers (one per .cu)
 cudaError_t launch_atss_candidates(const Geo& g, const Workspace& ws, const float* gt_boxes, const int32_t* gt_offsets,
                                    const int32_t* pad_hw, cudaStream_t st);
@@ -267,15 +290,9 @@ struct LossArgs {
   float dlw;
 };
 struct LossStreams {
-  cudaStream_t early;                 // low-priority helper: zero fill, class-response rows
-  cudaStream_t late;                  // high-priority helper: positives' rows, candidates' rows, take-back
-  cudaEvent_t fork, pos_done, early_done, late_done, main_done;
-  cudaEvent_t cleared;                // may be null: gradient tensors not pre-cleared by erd_step_prepare
   cudaEvent_t sel_ready;              // may be null: ERS selection already ordered before the caller's stream
   cudaEvent_t nms_done;               // may be null: NMS already ordered before the caller's stream
 };
-cudaError_t launch_zero_fill(const Geo& g, const MPtr5& g_cls, const MPtr5& g_box, const unsigned int* skip_flag,
-                             cudaStream_t st);
 cudaError_t launch_loss(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st, const LossStreams* ls);
 
 }  // namespace erd

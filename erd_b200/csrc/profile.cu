@@ -9,8 +9,8 @@
 namespace erd {
 
 static const char* kKernelNames[kNumKernels] = {"ers_scan", "ers_select", "atss_candidates", "atss_finalize",
-                                                "pos_prepass", "nms_prep", "nms_mask", "nms_resolve", "nms_order", "upstream_check", "zero_fill",
-                                                "qfl_sweep", "cls_kd", "pos_grad", "box_kd", "box_fix"};
+                                                "pos_prepass", "nms_prep", "nms_mask", "nms_resolve", "nms_order", "upstream_check",
+                                                "student_pass", "box_fix"};
 
 struct ProfState {
   std::mutex mu;

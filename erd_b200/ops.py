@@ -125,6 +125,8 @@ class Plan:
         arguments): pad them into the plan buffers and rebuild the per-anchor flags."""
         if len(cls_inds) != self.n or len(box_inds) != self.n:
             raise AssertionError('one index tensor per image expected')
+        N.check(N.load().erd_selection_replaced(C.byref(self.shape), self.ws.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), 'erd_selection_replaced')
         self.sel_flags.zero_()
         for lst, inds, cnt, bit in ((cls_inds, self.cls_inds, self.cls_count, 1),
                                     (box_inds, self.box_inds, self.box_count, 2)):
@@ -231,12 +233,7 @@ class ErdPath:
             losses.data_ptr(), _ptrs(g_cls), _ptrs(g_box), p.ws.data_ptr(), _stream()), 'erd_loss_fwd_bwd')
 
     # ---- fused step -------------------------------------------------------------------
-    def prepare(self, p: Plan, t_cls, t_box, s_cls, s_box, ers_done: bool = False, g_cls=None, g_box=None):
-        """``g_cls`` / ``g_box``: the gradient tensors the following ``loss_fwd_bwd`` will fill; given
-        here, their zero fill runs at the start of the step beside the ERS scan."""
-        for l in range(N.MAX_LEVELS):
-            p.bufs.g_cls[l] = g_cls[l].data_ptr() if g_cls is not None else None
-            p.bufs.g_box[l] = g_box[l].data_ptr() if g_box is not None else None
+    def prepare(self, p: Plan, t_cls, t_box, s_cls, s_box, ers_done: bool = False):
         N.check(self.lib.erd_step_prepare(
             self._context(p.device), C.byref(p.shape), _ptrs(t_cls), _ptrs(t_box), _ptrs(s_cls), _ptrs(s_box),
             p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(),
@@ -264,7 +261,7 @@ class ErdPath:
         if g_box is None:
             g_box = [torch.empty_like(t) for t in s_box]
         losses = torch.empty(p.num_losses, dtype=torch.float32, device=p.device)
-        self.prepare(p, t_cls, t_box, s_cls, s_box, ers_done, g_cls, g_box)
+        self.prepare(p, t_cls, t_box, s_cls, s_box, ers_done)
         self.reduce_avg(p)
         self.loss_fwd_bwd(p, t_cls, t_box, s_cls, s_box, g_cls, g_box, losses, dist_loss_weight, upstream)
         return p, losses, g_cls, g_box

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define ERD_MAX_LEVELS 5
-#define ERD_ABI_VERSION 2
+#define ERD_ABI_VERSION 3
 
 typedef enum ErdStatus {
   ERD_OK = 0,
@@ -100,6 +100,12 @@ int erd_destroy(ErdContext* ctx);
 int erd_ers_select(const ErdShape* shape, const float* const* t_cls, const float* const* t_box,
                    int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds, int32_t* box_count,
                    float* thr, uint8_t* sel_flags, void* ws, void* stream);
+
+/* Tell the library that the caller overwrote cls_inds / box_inds / their counts / sel_flags with a
+ * selection of its own (the reference's loss_by_feat takes the index lists as arguments,
+ * gfl_head_increment_erd.py:334-343): the teacher-row stash erd_ers_select built no longer matches
+ * it, and erd_loss_fwd_bwd gathers the teacher rows from the tensors instead. */
+int erd_selection_replaced(const ErdShape* shape, void* ws, void* stream);
 
 /* Anchors, valid flags, ATSS assignment, pseudo sampling.
  * Replaces AnchorHead.get_anchors (dense_heads/anchor_head.py:164-199),
@@ -188,12 +194,6 @@ typedef struct ErdStepBuffers {
   int32_t* keep;
   int32_t* keep_count;
   float* avg;
-  /* Optional (all NULL = off): the gradient tensors the following erd_loss_fwd_bwd(ctx, ...) call
-   * will receive.  Most of them is zero (old-class rows off the ERS set, box rows of background
-   * anchors); given here, that zero fill runs at the very start of the step, beside the ERS scan,
-   * instead of inside the loss call.  The caller must not touch the tensors in between. */
-  float* g_cls[ERD_MAX_LEVELS];
-  float* g_box[ERD_MAX_LEVELS];
 } ErdStepBuffers;
 
 int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const* t_cls,

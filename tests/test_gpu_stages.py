@@ -128,7 +128,7 @@ def _staged(path, b, ctx_none=False, preclear=False, poison=False):
     g_box = [torch.full_like(t, fill) for t in b.s_box]
     losses = torch.empty(p.num_losses, device='cuda')
     if preclear:
-        path.prepare(p, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls=g_cls, g_box=g_box)
+        path.prepare(p, b.t_cls, b.t_box, b.s_cls, b.s_box)
     else:
         path.ers_select(p, b.t_cls, b.t_box)
         path.atss_assign(p)
@@ -149,9 +149,9 @@ def _staged(path, b, ctx_none=False, preclear=False, poison=False):
     return p, losses, g_cls, g_box
 
 
-@pytest.mark.parametrize('mode', ['staged_ctx', 'staged_null_ctx', 'prepare_preclear'])
+@pytest.mark.parametrize('mode', ['staged_ctx', 'staged_null_ctx', 'prepare'])
 def test_every_call_sequence_gives_the_same_bits(mode):
-    """The fused step (erd_step_prepare with early zero fill + loss), the stage-by-stage sequence
+    """The fused step (erd_step_prepare + loss), the stage-by-stage sequence
     and the NULL-context single-stream sequence run the same kernels in different orders on
     different streams: identical index lists, losses and gradients, and every gradient element
     is written (buffers are poisoned with NaN first)."""
@@ -164,7 +164,7 @@ def test_every_call_sequence_gives_the_same_bits(mode):
     torch.cuda.synchronize()
     ref_l, ref_gc, ref_gb = ref_l.clone(), [t.clone() for t in ref_gc], [t.clone() for t in ref_gb]
     ref_keep = ref_p.keep.clone(), ref_p.keep_count.clone()
-    p, l, gc, gb = _staged(path, b, ctx_none=(mode == 'staged_null_ctx'), preclear=(mode == 'prepare_preclear'),
+    p, l, gc, gb = _staged(path, b, ctx_none=(mode == 'staged_null_ctx'), preclear=(mode == 'prepare'),
                            poison=True)
     assert torch.equal(p.keep_count, ref_keep[1])
     for i in range(batch.num_imgs):
