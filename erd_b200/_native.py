@@ -48,7 +48,6 @@ SIGNATURES = {
     'erd_create': [C.POINTER(_P)],
     'erd_destroy': [_P],
     'erd_ers_select': [_SH, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P],
-    'erd_selection_replaced': [_SH, _P, _P],
     'erd_atss_assign': [_SH, _P, _P, _P, _P, _P, _P, _P, _P],
     'erd_avg_factors': [_SH, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P],
     'erd_teacher_nms': [_SH, _P, _P, _P, _F, _P, _P, _P, _P, _P],

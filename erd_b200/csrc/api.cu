@@ -81,15 +81,6 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->t_dist = (float4*)take(NA * 16);
   const size_t tiles32 = (size_t)g.A / 32 + kLevels;   // >= sum_l ceil(hw_l / 32)
   ws->ers_part = (double*)take((size_t)g.n_img * tiles32 * 4 * 8);
-  ws->img_cnt = (int*)take((size_t)g.n_img * 4);
-  ws->img_flag = (unsigned int*)take((size_t)g.n_img * 4);
-  ws->teacher_epoch = (unsigned int*)take(4);
-  ws->teacher_done = (unsigned int*)take(4);
-  ws->stash_valid = (unsigned int*)take(4);
-  ws->stash_cnt = (int*)take((size_t)g.n_img * 2 * 4);
-  ws->stash_base = (int2*)take((size_t)g.n_img * tiles32 * 8);
-  ws->stash_cls = (float*)take(NS * (size_t)((g.ori + 3) & ~3) * 4);
-  ws->stash_box = (float*)take(NS * (size_t)kBoxCh * 4);
   ws->atss_key = (unsigned long long*)take(NA * 8);
   ws->pos_list = (int2*)take(NA * 8);
   ws->pos_counter = (int*)take((size_t)g.n_img * 4);
@@ -256,17 +247,6 @@ int erd_avg_factors(const ErdShape* shape, const float* const* s_cls, const floa
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_avg_factors");
 }
 
-int erd_selection_replaced(const ErdShape* shape, void* wsp, void* stream) {
-  Geo g;
-  int rc = make_geo(shape, &g);
-  if (rc) return rc;
-  if (!wsp) return fail(ERD_ERR_NULL, "erd_selection_replaced: NULL workspace");
-  Workspace ws;
-  carve(g, wsp, &ws);
-  cudaError_t e = cudaMemsetAsync(ws.stash_valid, 0, 4, (cudaStream_t)stream);
-  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_selection_replaced");
-}
-
 int erd_teacher_nms(const ErdShape* shape, const int32_t* box_inds, const int32_t* box_count, const int32_t* pad_hw,
                     float iou_thr, int32_t* keep, int32_t* keep_count, uint8_t* sel_flags, void* wsp, void* stream) {
   Geo g;
@@ -380,7 +360,7 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   if (e != cudaSuccess) return fail_cuda(e, "erd_step_prepare fork");
   int rc = 0;
   if (!(flags & ERD_PREPARE_ERS_DONE)) {
-    // the student pass only needs the teacher pass (flags + stash); the ordered lists are for the NMS
+    // the student pass only needs the teacher pass and the flags; the ordered lists are for the NMS
     Geo gt;
     rc = make_geo(shape, &gt);
     if (rc) return rc;
@@ -390,7 +370,9 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
     set_vec(&gt, t_cls, t_box);
     Workspace wt;
     carve(gt, wsp, &wt);
-    e = launch_teacher_pass(gt, wt, ptr5(t_cls), ptr5(t_box), b->thr, b->sel_flags, ctx->side);
+    int tiles = 0;
+    e = launch_teacher_pass(gt, wt, ptr5(t_cls), ptr5(t_box), b->cls_count, b->box_count, &tiles, ctx->side);
+    if (e == cudaSuccess) e = launch_ers_flags(gt, wt, tiles, b->thr, b->sel_flags, b->cls_count, b->box_count, ctx->side);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->sel_done, ctx->side);
     if (e == cudaSuccess)
       e = launch_ers_lists(gt, wt, b->cls_inds, b->cls_count, b->box_inds, b->box_count, b->thr, b->sel_flags, ctx->side);

@@ -53,15 +53,6 @@ struct Workspace {
   float* t_u;                     // [N][A] teacher max raw box logit
   float4* t_dist;                 // [N][A] teacher softmax-integral distances (l,t,r,b), bin units
   double* ers_part;               // [N][tiles of 32 anchors][4] per-tile sums: m, m^2, u, u^2
-  int* img_cnt;                   // [N] scanned tiles of the image (teacher pass; zero between launches)
-  unsigned int* img_flag;         // [N] == the launch's epoch once the image's thresholds are published
-  unsigned int* teacher_epoch;    // [1] stamp of the last completed teacher pass
-  unsigned int* teacher_done;     // [1] finished consumer warps (ticket; zero between launches)
-  unsigned int* stash_valid;      // [1] != 0: flags + stash below describe the current ERS selection
-  int* stash_cnt;                 // [N][2] rows allocated in the stash (class, box) == K_cls, K_bbox after the pass
-  int2* stash_base;               // [N][tiles of 32 anchors] first (class, box) stash row of the tile's selected anchors
-  float* stash_cls;               // [N][sel_cap][ori rounded up to 4] teacher class logits of the ERS class rows
-  float* stash_box;               // [N][sel_cap][68] teacher box logits of the ERS box candidates
   unsigned long long* atss_key;   // [N][A] packed (iou bits << 32 | ~gt) argmax table
   int2* pos_list;                 // [N][A] (anchor, global GT row) of the assigned anchors (unordered)
   int* pos_counter;               // [N] running length of pos_list (zero between steps)
@@ -172,7 +163,7 @@ struct Quad {
 };
 
 // ---------------------------------------------------------------- launch accounting (profile.cu)
-enum KernelId { kKErsScan, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan, kKNmsOrder,
+enum KernelId { kKErsScan, kKErsFlags, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan, kKNmsOrder,
                 kKUpCheck, kKStudent, kKBoxFix, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
@@ -245,9 +236,12 @@ __device__ __forceinline__ int atss_decode_anchor(const Geo& g, const Workspace&
 cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box,
                        int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds, int32_t* box_count,
                        float* thr, uint8_t* sel_flags, cudaStream_t st);
-// the two halves of launch_ers: the streaming pass (flags, thresholds, cache, stash) and the ordered lists
-cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box, float* thr,
-                                uint8_t* sel_flags, cudaStream_t st);
+// the three parts of launch_ers: the streaming pass (cache, thresholds), the flags + counts, the ordered lists
+cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box,
+                                int32_t* cls_count, int32_t* box_count, int* tiles_per_img,
+                                cudaStream_t st);   // also zeroes the two count vectors
+cudaError_t launch_ers_flags(const Geo& g, const Workspace& ws, int tiles_per_img, float* thr, uint8_t* sel_flags,
+                             int32_t* cls_count, int32_t* box_count, cudaStream_t st);
 cudaError_t launch_ers_lists(const Geo& g, const Workspace& ws, int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds,
                              int32_t* box_count, const float* thr, uint8_t* sel_flags, cudaStream_t st);
 // ---------------------------------------------------------------- host launchers (one per .cu)

@@ -1,6 +1,6 @@
-// Elastic Response Selection, part 2: the ordered index lists the reference's sel_pos returns
-// (and the teacher NMS consumes).  Part 1 -- the streaming pass over the teacher logits, the
-// thresholds, the per-anchor flags and the teacher-row stash -- is teacher.cu.
+// Elastic Response Selection, part 2: the per-anchor flags and the ordered index lists the
+// reference's sel_pos returns (and the teacher NMS consumes).  Part 1 -- the streaming pass over
+// the teacher logits, the per-anchor cache and the thresholds -- is teacher.cu.
 // Reference: GFLIncrementERD.sel_pos / sel_pos_single
 // (mmdet/models/detectors/gfl_increment_erd.py:143-200).
 #include <cstdlib>
@@ -8,13 +8,103 @@
 
 namespace erd {
 
-cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box, float* thr,
-                                uint8_t* sel_flags, cudaStream_t st);   // teacher.cu
+// ----------------------------------------------------------------------------- flags + counts
+// The part of the selection the student pass needs -- per-anchor flag byte (bit 0: class-response
+// row, bit 1: box candidate) and the per-image counts K_cls / K_bbox -- in one short launch right
+// behind the teacher pass; the ordered lists follow off the critical path.
+constexpr int kFlagThreads = 256;
+constexpr int kFlagPer = 4;
+
+__global__ void __launch_bounds__(kFlagThreads) ers_flags_kernel(Geo g, Workspace ws, int tiles, float* __restrict__ thr_out,
+                                                                 uint8_t* __restrict__ sel_flags, int32_t* cls_count,
+                                                                 int32_t* box_count) {
+  const int n = blockIdx.y;
+  // thr = mean + 2 std (unbiased) of the image (gfl_increment_erd.py:149,157) from the teacher pass's
+  // per-tile fp64 sums.  Every block of the image reduces them itself (22 KB out of L2) with the same
+  // thread -> element mapping and the same tree, so all blocks hold identical bits and the result is
+  // reproducible run to run; block 0 publishes it for the lists kernel and the caller.
+  __shared__ double s_red[kFlagThreads / 32];
+  __shared__ double s_sum[4];
+  __shared__ float s_thr[2];
+  {
+    const double* p = ws.ers_part + (size_t)n * tiles * 4;
+    const int total = tiles * 4;
+    double acc = 0.0;   // thread t sums elements t, t + 256, ...: all of component t % 4
+    for (int e0 = threadIdx.x; e0 < total; e0 += kFlagThreads * 8) {
+      double v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = e0 + kFlagThreads * j;
+        v[j] = e < total ? p[e] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);   // lanes 0..3: the warp's sums of m, m^2, u, u^2
+    for (int comp = 0; comp < 4; ++comp) {
+      if ((threadIdx.x & 31) == comp) s_red[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kFlagThreads / 32; ++w) t += s_red[w];
+        s_sum[comp] = t;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < 2) {
+      const double s1 = s_sum[threadIdx.x * 2], s2 = s_sum[threadIdx.x * 2 + 1];
+      const double An = (double)g.A;
+      const double mean = s1 / An;
+      double var = (s2 - s1 * s1 / An) / (An - 1.0);   // A == 1 -> NaN, as torch.std
+      if (var < 0.0) var = 0.0;
+      const float t = __fadd_rn((float)mean, __fmul_rn(2.0f, (float)sqrt(var)));
+      s_thr[threadIdx.x] = t;
+      if (blockIdx.x == 0) thr_out[n * 2 + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+  const float thr_c = s_thr[0], thr_b = s_thr[1];
+  const int a0 = (blockIdx.x * kFlagThreads + threadIdx.x) * kFlagPer;
+  const float* m = ws.t_m + (size_t)n * g.A;
+  const float* u = ws.t_u + (size_t)n * g.A;
+  int nc = 0, nb = 0;
+  unsigned packed = 0u;
+#pragma unroll
+  for (int k = 0; k < kFlagPer; ++k) {
+    const bool in = a0 + k < g.A;
+    const bool c = in && m[a0 + k] > thr_c, b = in && u[a0 + k] > thr_b;   // strict (gfl_increment_erd.py:150,158)
+    nc += c;
+    nb += b;
+    packed |= (unsigned)((c ? 1 : 0) | (b ? 2 : 0)) << (8 * k);
+  }
+  uint8_t* out = sel_flags + (size_t)n * g.A + a0;
+  if (a0 + kFlagPer <= g.A && (((uintptr_t)out) & 3) == 0) {
+    *reinterpret_cast<unsigned*>(out) = packed;
+  } else {
+    for (int k = 0; k < kFlagPer && a0 + k < g.A; ++k) out[k] = (uint8_t)(packed >> (8 * k));
+  }
+  __shared__ int s_c[kFlagThreads / 32], s_b[kFlagThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nc += __shfl_xor_sync(0xffffffffu, nc, o);
+    nb += __shfl_xor_sync(0xffffffffu, nb, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = nc; s_b[threadIdx.x >> 5] = nb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tc = 0, tb = 0;
+    for (int w = 0; w < kFlagThreads / 32; ++w) { tc += s_c[w]; tb += s_b[w]; }
+    if (tc) atomicAdd(cls_count + n, tc);
+    if (tb) atomicAdd(box_count + n, tb);
+  }
+}
 
 // ----------------------------------------------------------------------------- ordered lists
 // Rows strictly above the image's thresholds, in ascending anchor order (what nonzero() yields,
-// gfl_increment_erd.py:150-151,158-159).  Off the step's critical path: the student pass works
-// from the flags and the stash the teacher pass wrote.  Each CTA owns a 2048-anchor chunk
+// gfl_increment_erd.py:150-151,158-159).  Off the step's critical path: the student pass derives
+// the same flags itself from the teacher pass's cache and thresholds.  Each CTA owns a 2048-anchor chunk
 // of one image; it recounts the flags of the anchors before its chunk from the L2-resident
 // cache instead of waiting on a cross-CTA prefix, so one launch suffices.
 constexpr int kSelThreads = 1024;
@@ -29,8 +119,8 @@ __global__ void __launch_bounds__(kSelThreads) ers_select_kernel(Geo g, Workspac
   const int chunk0 = blockIdx.x * kSelChunk;
   __shared__ int s_warp[2][kSelThreads / 32];
   __shared__ int s_base[2];
-  // the thresholds the teacher pass published (recomputing them here with another summation order
-  // could differ in the last bit and make the lists disagree with the flags and the stash)
+  // the thresholds the teacher pass published (the student pass derives its roles from the same
+  // numbers: recomputing them here with another summation order could differ in the last bit)
   const float thr_c = thr_in[n * 2], thr_b = thr_in[n * 2 + 1];
   const float* m = ws.t_m + (size_t)n * g.A;
   const float* u = ws.t_u + (size_t)n * g.A;
@@ -108,6 +198,15 @@ __global__ void __launch_bounds__(kSelThreads) ers_select_kernel(Geo g, Workspac
   }
 }
 
+cudaError_t launch_ers_flags(const Geo& g, const Workspace& ws, int tiles_per_img, float* thr, uint8_t* sel_flags,
+                             int32_t* cls_count, int32_t* box_count, cudaStream_t st) {
+  const int per_block = kFlagThreads * kFlagPer;
+  ERD_LAUNCH(kKErsFlags, st,
+             (ers_flags_kernel<<<dim3((g.A + per_block - 1) / per_block, g.n_img), kFlagThreads, 0, st>>>(
+                 g, ws, tiles_per_img, thr, sel_flags, cls_count, box_count)));
+  return cudaGetLastError();
+}
+
 cudaError_t launch_ers_lists(const Geo& g, const Workspace& ws, int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds,
                              int32_t* box_count, const float* thr, uint8_t* sel_flags, cudaStream_t st) {
   ERD_LAUNCH(kKErsSelect, st,
@@ -119,7 +218,9 @@ cudaError_t launch_ers_lists(const Geo& g, const Workspace& ws, int32_t* cls_ind
 cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box, int32_t* cls_inds,
                        int32_t* cls_count, int32_t* box_inds, int32_t* box_count, float* thr, uint8_t* sel_flags,
                        cudaStream_t st) {
-  cudaError_t e = launch_teacher_pass(g, ws, t_cls, t_box, thr, sel_flags, st);
+  int tiles = 0;
+  cudaError_t e = launch_teacher_pass(g, ws, t_cls, t_box, cls_count, box_count, &tiles, st);
+  if (e == cudaSuccess) e = launch_ers_flags(g, ws, tiles, thr, sel_flags, cls_count, box_count, st);
   if (e != cudaSuccess) return e;
   return launch_ers_lists(g, ws, cls_inds, cls_count, box_inds, box_count, thr, sel_flags, st);
 }

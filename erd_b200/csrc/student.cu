@@ -20,6 +20,7 @@
 // have a tensor map; their tiles take the same path with plain loads / stores by the consumers.
 #include <cuda.h>   // CUtensorMap types; the encoder itself is looked up through the runtime (below)
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "loss_math.cuh"
@@ -31,18 +32,19 @@ constexpr int kBConsumers = 512;           // 16 consumer warps
 constexpr int kBGroups = kBConsumers / kBT;   // channel groups of the dense part: thread = (column, group)
 constexpr int kBLoaders = 3;               // loader warps (tile k of the CTA is loaded by warp k % 3)
 constexpr int kBThreads = kBConsumers + 32 * (kBLoaders + 1);   // + the store warp
-constexpr int kStageItems = 12;            // special columns per tile whose teacher rows / records are staged in the slot
+constexpr int kStageItems = 12;            // positives per tile whose records are staged in the slot (more: read from global)
 
 constexpr unsigned kRoleValid = 1u, kRolePos = 2u, kRoleCls = 4u, kRoleCand = 8u;
 constexpr unsigned kRoleSpecial = kRolePos | kRoleCls | kRoleCand;
 
-// Header of a ring slot, behind the tile's logits.  `rec` and the teacher rows behind the header
-// are filled by asynchronous copies (cp.async) that complete on the slot's full barrier.
+// Header of a ring slot, behind the tile's logits.  `rec` is filled by asynchronous copies
+// (cp.async) that complete on the slot's full barrier.
 struct __align__(32) TileHeader {
-  PosRec rec[kStageItems];          // records of the staged items that are positives
+  PosRec rec[kStageItems];          // records of the tile's first positives (index: rec_of[item])
   unsigned char role[kBT];
   unsigned char item_col[kBT];      // special columns of the tile, ascending
   unsigned char col_item[kBT];      // column -> its item index
+  unsigned char rec_of[kBT];        // item -> index into rec[], 255: not staged
   float kd[kBT];                    // weighted KL of the items that are box candidates (consumers -> store warp)
   int n_items, cls_k, pad0, pad1;   // cls_k: K_cls of the tile's image (class-response normaliser)
 };
@@ -62,13 +64,12 @@ struct StudentArgs {
   int dev;                           // TEMPORARY dev switches: 1 skip sparse, 2 skip dense, 4 skip stores
   unsigned long long* trace;         // TEMPORARY: per-tile timestamps of CTA 0 [tile][8]
   int lvl_tile_start[kLevels + 1];   // prefix of ceil(hw / kBT)
-  int sub_start[kLevels];            // prefix of ceil(hw / 32): the teacher pass's tiles (two per student tile)
-  int subs_per_img;
   int use_tma[kLevels];
 };
 
 struct __align__(64) StudentMaps {
-  CUtensorMap s_cls[kLevels], s_box[kLevels], g_cls[kLevels], g_box[kLevels];
+  CUtensorMap s_cls[kLevels], s_box[kLevels], g_cls[kLevels], g_box[kLevels];   // [C x 64] / [68 x 64] tiles
+  CUtensorMap t_cls[kLevels], t_box[kLevels];                                   // [ori x 4] / [68 x 4]: one anchor's teacher column
 };
 
 struct BTile {
@@ -77,8 +78,9 @@ struct BTile {
 
 __device__ __forceinline__ BTile b_tile(const Geo& g, const StudentArgs& A, int t) {
   BTile b;
-  b.n = t / A.tiles_per_img;
-  const int r = t - b.n * A.tiles_per_img;
+  const int q = t / A.tiles_per_img;
+  const int r = t - q * A.tiles_per_img;
+  b.n = g.n_img - 1 - q;   // last image first: its teacher rows are the freshest in L2 (the teacher pass ran 0 .. N-1)
   b.l = 0;
 #pragma unroll
   for (int i = 1; i < kLevels; ++i) b.l += (r >= A.lvl_tile_start[i]) ? 1 : 0;
@@ -137,13 +139,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
 // Box rows of one special column (a positive and / or an ERS box candidate), by one whole warp, in
 // place in the tile.  lane = side * 8 + b holds bins b, b + 8 (b == 0: also 16) of its side.
 __device__ __forceinline__ void item_box_rows(const Geo& g, const Workspace& ws, const StudentArgs& A, const BTile& b,
-                                              float* data, const TileHeader* hd, float* hd_kd, const float* tbox_staged,
+                                              const float* box_in, float* box_out, int pitch, const TileHeader* hd, float* hd_kd, const float* tbox_staged,
                                               const float* tbox_global, int HW, int it, int icol, int hwI, bool is_pos,
-                                              bool is_cand, bool staged, float w_kd, float avg2, float inv_T, size_t ga0,
-                                              int lane) {
+                                              bool is_cand, float w_kd, float avg2, float inv_T, size_t ga0, int lane) {
   const int side = lane >> 3, bb = lane & 7;
-  const int C = g.C;
-  float* brow = data + (size_t)(C + side * kBins) * kBT + icol;
+  const float* brow_in = box_in + (size_t)(side * kBins) * pitch + icol;
+  float* brow = box_out + (size_t)(side * kBins) * pitch + icol;
   int jb[3];
   bool ok[3];
   float zs[3], out[3];
@@ -151,7 +152,7 @@ __device__ __forceinline__ void item_box_rows(const Geo& g, const Workspace& ws,
   for (int i = 0; i < 3; ++i) {
     jb[i] = bb + 8 * i;
     ok[i] = jb[i] < kBins;
-    zs[i] = ok[i] ? brow[jb[i] * kBT] : -INFINITY;
+    zs[i] = ok[i] ? brow_in[(size_t)jb[i] * pitch] : -INFINITY;
     out[i] = 0.f;
   }
   if (is_cand) {   // DFL-distribution KL at temperature T (:204-221, kd_loss.py:12-37), written as if the NMS kept it
@@ -160,7 +161,7 @@ __device__ __forceinline__ void item_box_rows(const Geo& g, const Workspace& ws,
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int ch = side * kBins + jb[i];
-      const float zt = !ok[i] ? -INFINITY : tbox_staged ? tbox_staged[ch] : __ldg(tbox_global + (size_t)ch * HW);
+      const float zt = !ok[i] ? -INFINITY : tbox_staged ? tbox_staged[ch * 4] : __ldg(tbox_global + (size_t)ch * HW);
       a[i] = zs[i] * inv_T;
       t[i] = zt * inv_T;
       ms = fmaxf(ms, a[i]);
@@ -200,7 +201,8 @@ __device__ __forceinline__ void item_box_rows(const Geo& g, const Workspace& ws,
     if (lane == 0) hd_kd[it] = w_kd * (kl / (float)kBins * (kT * kT));   // .mean(1) * T*T; the store warp files it
   }
   if (is_pos) {   // GIoU + DFL rows of a positive, through the softmax Jacobian (:285-310)
-    const PosRec rec = staged ? hd->rec[it] : ws.pos_rec[ga0 + icol];
+    const int ri = hd->rec_of[it];
+    const PosRec rec = ri != 255 ? hd->rec[ri] : ws.pos_rec[ga0 + icol];
     float zm = fmaxf(fmaxf(zs[0], zs[1]), zs[2]);
     zm = oct_max(zm);
     float e[3], sum = 0.f, num = 0.f;
@@ -243,7 +245,164 @@ __device__ __forceinline__ void item_box_rows(const Geo& g, const Workspace& ws,
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i)
-    if (ok[i]) brow[jb[i] * kBT] = out[i];
+    if (ok[i]) brow[(size_t)jb[i] * pitch] = out[i];
+}
+
+// What a consumer warp needs to know beyond the tile itself.
+struct ConsumerCtx {
+  const Geo& g;
+  const Workspace& ws;
+  const StudentArgs& A;
+  const StudentMaps& maps;
+  float* tcol;                   // this warp's teacher-column staging buffer
+  unsigned long long* tbar;      // ... and the barrier its fetches complete on
+  unsigned long long pol_keep;
+  int tbox_off, lane, cwarp, col, q, oq, cq;
+  float inv_avg1, avg2, inv_T;
+};
+
+// One tile, one consumer warp: the dense part of this warp's threads and the items of the tile that
+// fall to this warp.  RING: the tile is in the ring slot `data` (logits in, gradients out, in place);
+// else (level without a tensor map) it is read from / written to global memory directly.
+template <bool RING>
+__device__ __forceinline__ void consume_tile(const ConsumerCtx& cc, const BTile& b, int k, float* data, TileHeader* hd,
+                                             float& qfl_part, float& dcls_part, uint32_t& tphase) {
+  const Geo& g = cc.g;
+  const Workspace& ws = cc.ws;
+  const StudentArgs& A = cc.A;
+  const StudentMaps& maps = cc.maps;
+  float* tcol = cc.tcol;
+  const int tbox_off = cc.tbox_off, lane = cc.lane, cwarp = cc.cwarp, col = cc.col, q = cc.q, oq = cc.oq, cq = cc.cq;
+  const float inv_avg1 = cc.inv_avg1, avg2 = cc.avg2, inv_T = cc.inv_T;
+  const int C = g.C, ori = g.ori, cn = g.cn;
+  constexpr int bq = (kBoxCh + kBGroups - 1) / kBGroups;
+  const int HW = g.hw[b.l];
+    // Start the asynchronous fetch of item `it`'s teacher column into this warp's staging buffer: two
+    // TMA loads of [rows x 4] boxes -- the aligned group of four columns holding the anchor (the lines
+    // were left in L2 by the teacher pass).  Returns true when a fetch is in flight or nothing needs fetching.
+    auto fetch_teacher = [&](int item) {
+      const int icol = hd->item_col[item];
+      const unsigned irole = hd->role[icol];
+      if (!RING || !(irole & (kRoleCls | kRoleCand))) return true;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the buffer before the bulk write
+      __syncwarp();
+      if (lane == 0) {
+        const int hwI = b.hw0 + icol;
+        const uint32_t bytes = ((irole & kRoleCls) ? (uint32_t)ori * 16u : 0u) + ((irole & kRoleCand) ? (uint32_t)kBoxCh * 16u : 0u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(cc.tbar)), "r"(bytes) : "memory");
+        // (a box must start 16 B aligned in global memory: fetch the aligned group of four columns around the anchor)
+        if (irole & kRoleCls) tma_load_2d(tcol, &maps.t_cls[b.l], hwI & ~3, b.n * ori, cc.tbar, cc.pol_keep);
+        if (irole & kRoleCand) tma_load_2d(tcol + tbox_off, &maps.t_box[b.l], hwI & ~3, b.n * kBoxCh, cc.tbar, cc.pol_keep);
+      }
+      return true;
+    };
+    const size_t ga0 = (size_t)b.n * g.A + g.start[b.l] + b.hw0;
+    // this warp's first item of the tile: request its teacher column now, use it after the dense part
+    const int n_items = (A.dev & 1) ? 0 : hd->n_items;
+    int it = (cwarp - k) & (kBConsumers / 32 - 1);
+    bool fetched = false;
+    if (it < n_items) fetched = fetch_teacher(it);
+    // Where the tile lives: in the ring slot (logits in, gradients out, in place), or -- levels without a
+    // tensor map -- straight in global memory.  Everything below addresses rows through (pointer, pitch).
+    constexpr bool in_ring = RING;
+    const size_t goff_c = (size_t)b.n * C * HW + b.hw0, goff_b = (size_t)b.n * kBoxCh * HW + b.hw0;
+    const float* cls_in = in_ring ? data : A.s_cls.p[b.l] + goff_c;
+    float* cls_out = in_ring ? data : A.g_cls.p[b.l] + goff_c;
+    const float* box_in = in_ring ? data + (size_t)C * kBT : A.s_box.p[b.l] + goff_b;
+    float* box_out = in_ring ? data + (size_t)C * kBT : A.g_box.p[b.l] + goff_b;
+    const int pitch = RING ? kBT : HW;   // a compile-time stride in the ring
+    // Dense part and sparse items touch disjoint addresses of the tile (the dense part skips the
+    // rows a special column's item owns), so nothing orders them inside a tile.
+    // ------------------------------------------------------------ dense part
+    {
+      const unsigned role = hd->role[col];
+      const float lw = (role & kRoleValid) ? 1.0f : 0.0f;                // label_weights, gfl_head.py:650-655,663
+      const float gs = lw * (upstream_of(A.upstream, acc_cls(b.l)) * g.w_cls * inv_avg1);
+      int label = -1;
+      float score = 0.f;
+      if (role & kRolePos) {   // rare
+        const int ri = hd->rec_of[hd->col_item[col]];
+        const PosRec* rec = ri != 255 ? &hd->rec[ri] : ws.pos_rec + ga0 + col;
+        label = rec->label;
+        score = rec->score;
+      }
+      float loss = 0.f;
+      const int c0 = q * cq, c1 = min(c0 + cq, cn);
+      if (in_ring || col < b.cnt) {   // (columns past a level's end: zero-filled in the ring, absent in global memory)
+        const float* nin = cls_in + (size_t)ori * pitch + col;
+        float* nout = cls_out + (size_t)ori * pitch + col;
+        const bool own_label = label >= c0 && label < c1;    // a positive's label channel lies in this thread's share
+        const float x_label = own_label ? nin[(size_t)label * pitch] : 0.f;
+#pragma unroll 4
+        for (int c = c0; c < ((A.dev & 2) ? c0 : c1); ++c) {   // QFL, every element as a negative first: branch free (:260-261,317-320)
+          const QflTerm tn = qfl_neg(nin[(size_t)c * pitch]);
+          loss = fmaf(lw, tn.loss, loss);
+          nout[(size_t)c * pitch] = gs * tn.grad;
+        }
+        if (own_label) {   // ... then the label channel of the (rare) positive is redone with its soft target
+          const QflTerm tp = qfl_pos(x_label, score), tn = qfl_neg(x_label);
+          loss += lw * (tp.loss - tn.loss);
+          nout[(size_t)label * pitch] = gs * tp.grad;
+        }
+        qfl_part += loss;
+        // structural zeros: the old-class rows of columns without a class-response row or a box
+        // candidate's weight to read, the box rows of columns that are neither positive nor candidate
+        if (!(role & (kRoleCls | kRoleCand))) {
+          const int o0 = q * oq, o1 = min(o0 + oq, ori);
+          for (int c = o0; c < o1; ++c) cls_out[(size_t)c * pitch + col] = 0.f;
+        }
+        if (!(role & (kRolePos | kRoleCand))) {
+          float* brow = box_out + (size_t)(q * bq) * pitch + col;
+#pragma unroll
+          for (int j = 0; j < bq; ++j)
+            if (q * bq + j < kBoxCh) brow[(size_t)j * pitch] = 0.f;
+        }
+      }
+    }
+    // ------------------------------------------------------------ sparse items: one WARP per special column
+    // Item i of tile k goes to warp (i + k) % 16.  Lane layout for the box rows: lane = side * 8 + b,
+    // holding bins b, b + 8 (and 16 for b == 0) of its side; reductions over a side are 8-lane shuffles.
+    for (; it < n_items; it += kBConsumers / 32) {
+      if (!fetched) fetched = fetch_teacher(it);   // a second item of this warp in the same tile (rare)
+      const int icol = hd->item_col[it];
+      const unsigned irole = hd->role[icol];
+      const bool is_cls = (irole & kRoleCls) != 0u, is_cand = (irole & kRoleCand) != 0u, is_pos = (irole & kRolePos) != 0u;
+      const bool staged = in_ring;   // teacher column in this warp's staging buffer, else straight from global
+      const int hwI = b.hw0 + icol;
+      const float* tc_g = A.t_cls.p[b.l] + (size_t)b.n * ori * HW + hwI;
+      const float* tb_g = A.t_box.p[b.l] + (size_t)b.n * kBoxCh * HW + hwI;
+      if (staged && (is_cls || is_cand)) {
+        mbar_wait_parity(cc.tbar, tphase);
+        tphase ^= 1u;
+      }
+      fetched = false;
+      // old-class rows of the column: lane owns channels lane, lane + 32, ...
+      if (is_cls || is_cand) {
+        const float kc = (float)hd->cls_k * (float)ori;
+        const float scale_dc = upstream_of(A.upstream, acc_dcls(b.n)) * A.dlw * 2.0f / kc;
+        float mx_old = -INFINITY;
+        for (int c = lane; c < ori; c += 32) {
+          const float xs = cls_in[(size_t)c * pitch + icol];
+          mx_old = fmaxf(mx_old, xs);
+          float gr = 0.f;
+          if (is_cls) {   // class-response L2 (:181-186,324-332): g = 2 (x_s - x_t) / (K ori)
+            const float xt = staged ? tcol[c * 4 + (hwI & 3)] : __ldg(tc_g + (size_t)c * HW);
+            const float df = xs - xt;
+            dcls_part = fmaf(df, df, dcls_part);
+            gr = scale_dc * df;
+          }
+          cls_out[(size_t)c * pitch + icol] = gr;
+        }
+        if (is_pos || is_cand) {
+          const float w_kd = sigmoid_ref(warp_max(mx_old));                                      // :217-218
+          item_box_rows(g, ws, A, b, box_in, box_out, pitch, hd, hd->kd, staged ? tcol + tbox_off + (hwI & 3) : nullptr, tb_g, HW, it, icol, hwI, is_pos, is_cand,
+                        w_kd, avg2, inv_T, ga0, lane);
+        }
+      } else {
+        item_box_rows(g, ws, A, b, box_in, box_out, pitch, hd, hd->kd, nullptr, tb_g, HW, it, icol, hwI, is_pos, false, 0.f, avg2, inv_T,
+                      ga0, lane);
+      }
+    }
 }
 
 // ----------------------------------------------------------------------------- the kernel
@@ -258,11 +417,12 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
   const int S = A.stages;
   const int C = g.C, ori = g.ori, cn = g.cn;
   const int rows = C + kBoxCh;
-  const int ori_pad = (ori + 3) & ~3;
-  const int trow_len = ori_pad + kBoxCh;   // staged teacher row of an item: [class logits, padded to 16 B | 68 box logits]
-  // teacher rows come from the teacher pass's compact stash when it describes the current selection,
-  // else (caller-provided index lists) straight from the teacher tensors
-  const bool use_stash = *reinterpret_cast<volatile unsigned int*>(ws.stash_valid) != 0u;
+  // per consumer warp: a staging buffer for one anchor's teacher column ([ori + 68 rows][4 floats], filled by
+  // two TMA loads of [rows x 4] boxes whose first column is the anchor) and the barrier those loads complete on
+  const int tbox_off = ((ori * 16 + 127) & ~127) / 4;                  // floats: the box part starts 128 B aligned (TMA destination)
+  const int tcol_stride = tbox_off + ((kBoxCh * 16 + 127) & ~127) / 4;   // floats per warp
+  float* s_tcol = reinterpret_cast<float*>(s_raw + (size_t)A.stages * A.stage_bytes + (((size_t)(kLevels + g.n_img) * sizeof(double) + 127) & ~(size_t)127));
+  __shared__ __align__(8) unsigned long long s_tbar[kBConsumers / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -270,6 +430,7 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
       mbar_init(&s_done[s], kBConsumers / 32);   // one arrival per consumer warp
       mbar_init(&s_empty[s], 1);
     }
+    for (int w = 0; w < kBConsumers / 32; ++w) mbar_init(&s_tbar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < kLevels + g.n_img; i += kBThreads) s_loss[i] = 0.0;
@@ -278,11 +439,6 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
   auto slot_head = [&](int s) {
     return reinterpret_cast<TileHeader*>(s_raw + (size_t)s * A.stage_bytes + (size_t)rows * kBT * sizeof(float));
   };
-  auto slot_trow = [&](int s) {
-    return reinterpret_cast<float*>(s_raw + (size_t)s * A.stage_bytes + (size_t)rows * kBT * sizeof(float) +
-                                    sizeof(TileHeader));
-  };
-
   if (warp >= kBConsumers / 32 && warp < kBConsumers / 32 + kBLoaders) {
     // ================================================================== loader warps
     // Everything a loader does per tile is asynchronous (TMA, cp.async) except the tile's roles,
@@ -294,7 +450,6 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
     int gi[2] = {-1, -1};
     unsigned fl[2] = {0u, 0u};
     int kcls = 0;
-    int2 sbase[2] = {make_int2(0, 0), make_int2(0, 0)};
     auto fetch_roles = [&](int t) {
       if (t >= A.total_tiles) return;
       const BTile b = b_tile(g, A, t);
@@ -305,13 +460,7 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
         gi[h] = col < b.cnt ? A.gt_inds[ga] : -1;
         fl[h] = col < b.cnt ? (unsigned)A.sel_flags[ga] : 0u;
       }
-      kcls = use_stash ? ws.stash_cnt[b.n * 2] : A.cls_count[b.n];
-      if (use_stash) {
-        const int sub = A.sub_start[b.l] + b.hw0 / 32;
-        const int2* sp = ws.stash_base + (size_t)b.n * A.subs_per_img + sub;
-        sbase[0] = sp[0];
-        sbase[1] = b.cnt > 32 ? sp[1] : make_int2(0, 0);
-      }
+      kcls = A.cls_count[b.n];
     };
     fetch_roles(blockIdx.x + lw * gridDim.x);
     for (int k = lw; ; k += kBLoaders) {
@@ -325,39 +474,23 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
       TRACE(k, 0);
       float* data = slot_data(slot);
       TileHeader* hd = slot_head(slot);
-      float* trow = slot_trow(slot);
       if (A.use_tma[b.l]) {
         if (lane == 0) {
           mbar_expect_tx(&s_full[slot], (uint32_t)(rows * kBT * sizeof(float)));
           tma_load_2d(data, &maps.s_cls[b.l], b.hw0, b.n * C, &s_full[slot], pol_stream);
           tma_load_2d(data + (size_t)C * kBT, &maps.s_box[b.l], b.hw0, b.n * kBoxCh, &s_full[slot], pol_stream);
         }
-      } else {
-        // rows of this level are not 16 B aligned (H*W % 4 != 0): no tensor map; the tile comes in as
-        // 4-byte asynchronous copies, a warp-wide 128 B request per half row, columns past the level's end zeroed
-        const float* sc = A.s_cls.p[b.l] + (size_t)b.n * C * HW + b.hw0;
-        const float* sb = A.s_box.p[b.l] + (size_t)b.n * kBoxCh * HW + b.hw0;
-        const int c0 = lane, c1 = lane + 32;
-        const bool in0 = c0 < b.cnt, in1 = c1 < b.cnt;
-#pragma unroll 8
-        for (int r = 0; r < rows; ++r) {
-          const float* src = r < C ? sc + (size_t)r * HW : sb + (size_t)(r - C) * HW;
-          float* dst = data + r * kBT;
-          if (in0) cp_async_4(dst + c0, src + c0);
-          else dst[c0] = 0.f;
-          if (in1) cp_async_4(dst + c1, src + c1);
-          else dst[c1] = 0.f;
-        }
       }
+      // (tiles of levels without a tensor map -- rows not 16 B aligned -- never enter the ring: the
+      // consumers read and write global memory directly; the slot only carries the header)
       TRACE(k, 8);
       // the roles requested one iteration ago
       const int cgi[2] = {gi[0], gi[1]};
       const unsigned cfl[2] = {fl[0], fl[1]};
       const int ckcls = kcls;
-      const int2 csb[2] = {sbase[0], sbase[1]};
       unsigned role[2];
       int item[2];
-      int cslot[2], bslot[2];   // stash rows of this lane's columns (the stash orders a 32-anchor tile's rows by anchor)
+      int n_pos = 0;
       int n_items = 0;
       if (cgi[0] == 12345678 && cfl[1] == 99u) n_items = 1;   // (touch the registers: wait for the loads)
       TRACE(k, 9);
@@ -367,11 +500,6 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
         role[h] = (cgi[h] >= 0 ? kRoleValid : 0u) | (cgi[h] > 0 ? kRolePos : 0u) | ((cfl[h] & 1u) ? kRoleCls : 0u) |
                   ((cfl[h] & 2u) ? kRoleCand : 0u);
         const bool special = (role[h] & kRoleSpecial) != 0u;
-        {
-          const unsigned below = (1u << lane) - 1u;
-          cslot[h] = csb[h].x + __popc(__ballot_sync(0xffffffffu, (role[h] & kRoleCls) != 0u) & below);
-          bslot[h] = csb[h].y + __popc(__ballot_sync(0xffffffffu, (role[h] & kRoleCand) != 0u) & below);
-        }
         const unsigned m = __ballot_sync(0xffffffffu, special);
         item[h] = special ? n_items + __popc(m & ((1u << lane) - 1u)) : 255;
         n_items += __popc(m);
@@ -379,47 +507,26 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
         hd->col_item[col] = (unsigned char)item[h];
         if (special) hd->item_col[item[h]] = (unsigned char)col;
       }
+      // (second sweep, all lanes converged: the positives' staging indices)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int col = lane + 32 * h;
+        const bool pos = (role[h] & kRolePos) != 0u;
+        const unsigned mp = __ballot_sync(0xffffffffu, pos);
+        const int ri = n_pos + __popc(mp & ((1u << lane) - 1u));
+        n_pos += __popc(mp);
+        if (pos) {
+          hd->rec_of[item[h]] = (unsigned char)(ri < kStageItems ? ri : 255);
+          if (ri < kStageItems) {
+            const PosRec* src = ws.pos_rec + (size_t)b.n * g.A + g.start[b.l] + b.hw0 + col;
+            cp_async_16(reinterpret_cast<char*>(&hd->rec[ri]), reinterpret_cast<const char*>(src));
+            cp_async_16(reinterpret_cast<char*>(&hd->rec[ri]) + 16, reinterpret_cast<const char*>(src) + 16);
+          }
+        }
+      }
       if (lane == 0) {
         hd->n_items = n_items;
         hd->cls_k = ckcls;
-      }
-      TRACE(k, 10);
-      // stage the teacher rows and the positives' records of the first kStageItems items: the lanes
-      // walk the items, each copying a strided share of the item's words
-      const int staged = (A.dev & 8) ? 0 : min(n_items, kStageItems);   // dev 8: TIMING ONLY, teacher rows read as garbage
-      for (int it = 0; it < staged; ++it) {
-        // the item's column and role live in the lane that owns the column
-        const int owner_h0 = __ffs(__ballot_sync(0xffffffffu, item[0] == it));
-        const int owner_h1 = __ffs(__ballot_sync(0xffffffffu, item[1] == it));
-        const int col = owner_h0 ? owner_h0 - 1 : owner_h1 - 1 + 32;
-        const unsigned r = __shfl_sync(0xffffffffu, owner_h0 ? role[0] : role[1], (col & 31));
-        const size_t hw = (size_t)b.hw0 + col;
-        float* dst = trow + (size_t)it * trow_len;
-        if (use_stash) {
-          // contiguous rows: 16-byte copies, the class chunks first, then the 17 box chunks
-          const int cs = __shfl_sync(0xffffffffu, owner_h0 ? cslot[0] : cslot[1], (col & 31));
-          const int bs = __shfl_sync(0xffffffffu, owner_h0 ? bslot[0] : bslot[1], (col & 31));
-          const int nc = (r & kRoleCls) ? ori_pad / 4 : 0, nb = (r & kRoleCand) ? kBoxCh / 4 : 0;
-          const float* srcc = ws.stash_cls + ((size_t)b.n * g.sel_cap + cs) * ori_pad;
-          const float* srcb = ws.stash_box + ((size_t)b.n * g.sel_cap + bs) * kBoxCh;
-          for (int q = lane; q < nc + nb; q += 32) {
-            if (q < nc) cp_async_16(dst + 4 * q, srcc + 4 * q);
-            else cp_async_16(dst + ori_pad + 4 * (q - nc), srcb + 4 * (q - nc));
-          }
-        } else {
-          if (r & kRoleCls) {
-            const float* src = A.t_cls.p[b.l] + (size_t)b.n * ori * HW + hw;
-            for (int c = lane; c < ori; c += 32) cp_async_4(dst + c, src + (size_t)c * HW);
-          }
-          if (r & kRoleCand) {
-            const float* src = A.t_box.p[b.l] + (size_t)b.n * kBoxCh * HW + hw;
-            for (int c = lane; c < kBoxCh; c += 32) cp_async_4(dst + ori_pad + c, src + (size_t)c * HW);
-          }
-        }
-        if ((r & kRolePos) && lane < 2) {
-          const PosRec* src = ws.pos_rec + (size_t)b.n * g.A + g.start[b.l] + hw;
-          cp_async_16(reinterpret_cast<char*>(&hd->rec[it]) + 16 * lane, reinterpret_cast<const char*>(src) + 16 * lane);
-        }
       }
       TRACE(k, 11);
       __syncwarp();
@@ -461,30 +568,6 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the engine has read the slot
         }
-      } else {
-        const int HW = g.hw[b.l];
-        float* gc = A.g_cls.p[b.l] + (size_t)b.n * C * HW + b.hw0;
-        float* gb2 = A.g_box.p[b.l] + (size_t)b.n * kBoxCh * HW + b.hw0;
-        const int c0 = lane, c1 = lane + 32;
-        const bool in0 = c0 < b.cnt, in1 = c1 < b.cnt;
-        for (int r0 = 0; r0 < rows; r0 += 8) {   // eight rows of shared-memory reads in flight per lane
-          float v0[8], v1[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = min(r0 + i, rows - 1);
-            v0[i] = data[r * kBT + c0];
-            v1[i] = data[r * kBT + c1];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = r0 + i;
-            if (r < rows) {
-              float* dst = r < C ? gc + (size_t)r * HW : gb2 + (size_t)(r - C) * HW;
-              if (in0) __stcs(dst + c0, v0[i]);
-              if (in1) __stcs(dst + c1, v1[i]);
-            }
-          }
-        }
       }
       __syncwarp();
       TRACE(k, 5);
@@ -508,6 +591,11 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
   const float inv_avg1 = 1.0f / (float)((double)A.avg[0] + (double)kEps32);   // losses/utils.py:60-61
   const float avg2 = fmaxf(A.avg[1], 1.0f);                                   // :407 clamp_(min=1)
   const float inv_T = 1.0f / g.T;
+  unsigned long long pol_keep;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  float* tcol = s_tcol + (size_t)cwarp * tcol_stride;   // this warp's teacher-column staging: [ori][4] | [68][4]
+  uint32_t tphase = 0;
+  const ConsumerCtx cc{g, ws, A, maps, tcol, &s_tbar[cwarp], pol_keep, tbox_off, lane, cwarp, col, q, oq, cq, inv_avg1, avg2, inv_T};
   int cur_img = -1, cur_lvl = -1;
   float dcls_part = 0.f;   // sum (x_s - x_t)^2 of the current image, this thread
   float qfl_part = 0.f;    // QFL loss sum of the current (image, level), this thread
@@ -528,7 +616,6 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
     const int HW = g.hw[b.l];
     float* data = slot_data(slot);
     TileHeader* hd = slot_head(slot);
-    const float* trow = slot_trow(slot);
     if (b.n != cur_img || b.l != cur_lvl) {   // warp-uniform
       flush();
       cur_img = b.n;
@@ -537,93 +624,8 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
     mbar_wait_parity(&s_full[slot], ph);
     if (cwarp == 0) TRACE(k, 2);
     if (cwarp == 15) TRACE(k, 6);
-    const size_t ga0 = (size_t)b.n * g.A + g.start[b.l] + b.hw0;
-    // Dense part and sparse items touch disjoint addresses of the tile (the dense part skips the
-    // rows a special column's item owns), so nothing orders them inside a tile.
-    // ------------------------------------------------------------ dense part
-    {
-      const unsigned role = hd->role[col];
-      const float lw = (role & kRoleValid) ? 1.0f : 0.0f;                // label_weights, gfl_head.py:650-655,663
-      const float gs = lw * (upstream_of(A.upstream, acc_cls(b.l)) * g.w_cls * inv_avg1);
-      int label = -1;
-      float score = 0.f;
-      if (role & kRolePos) {   // rare
-        const int it = hd->col_item[col];
-        const PosRec* rec = it < kStageItems ? &hd->rec[it] : ws.pos_rec + ga0 + col;
-        label = rec->label;
-        score = rec->score;
-      }
-      float loss = 0.f;
-      const int c0 = q * cq, c1 = min(c0 + cq, cn);
-      float* nrow = data + (size_t)ori * kBT + col;
-      const bool own_label = label >= c0 && label < c1;    // a positive's label channel lies in this thread's share
-      const float x_label = own_label ? nrow[label * kBT] : 0.f;
-#pragma unroll 4
-      for (int c = c0; c < ((A.dev & 2) ? c0 : c1); ++c) {   // QFL, every element as a negative first: branch free (:260-261,317-320)
-        const QflTerm tn = qfl_neg(nrow[c * kBT]);
-        loss = fmaf(lw, tn.loss, loss);
-        nrow[c * kBT] = gs * tn.grad;
-      }
-      if (own_label) {   // ... then the label channel of the (rare) positive is redone with its soft target
-        const QflTerm tp = qfl_pos(x_label, score), tn = qfl_neg(x_label);
-        loss += lw * (tp.loss - tn.loss);
-        nrow[label * kBT] = gs * tp.grad;
-      }
-      qfl_part += loss;
-      // structural zeros: the old-class rows of columns without a class-response row or a box
-      // candidate's weight to read, the box rows of columns that are neither positive nor candidate
-      if (!(role & (kRoleCls | kRoleCand))) {
-        const int o0 = q * oq, o1 = min(o0 + oq, ori);
-        for (int c = o0; c < o1; ++c) data[c * kBT + col] = 0.f;
-      }
-      if (!(role & (kRolePos | kRoleCand))) {
-        float* brow = data + (size_t)(C + q * bq) * kBT + col;
-#pragma unroll
-        for (int j = 0; j < bq; ++j)
-          if (q * bq + j < kBoxCh) brow[j * kBT] = 0.f;
-      }
-    }
-    if (cwarp == 0) TRACE(k, 12);
-    // ------------------------------------------------------------ sparse items: one WARP per special column
-    // Item i of tile k goes to warp (i + k) % 16.  Lane layout for the box rows: lane = side * 8 + b,
-    // holding bins b, b + 8 (and 16 for b == 0) of its side; reductions over a side are 8-lane shuffles.
-    const int n_items = (A.dev & 1) ? 0 : hd->n_items;
-    for (int it = (cwarp - k) & (kBConsumers / 32 - 1); it < n_items; it += kBConsumers / 32) {
-      const int icol = hd->item_col[it];
-      const unsigned irole = hd->role[icol];
-      const bool is_cls = (irole & kRoleCls) != 0u, is_cand = (irole & kRoleCand) != 0u, is_pos = (irole & kRolePos) != 0u && !(A.dev & 8);
-      const bool staged = it < kStageItems;
-      const int hwI = b.hw0 + icol;
-      const float* tc_s = trow + (size_t)it * trow_len;                                        // staged teacher row
-      const float* tc_g = A.t_cls.p[b.l] + (size_t)b.n * ori * HW + hwI;                        // or straight from global
-      const float* tb_g = A.t_box.p[b.l] + (size_t)b.n * kBoxCh * HW + hwI;
-      // old-class rows of the column: lane owns channels lane, lane + 32, ...
-      if (is_cls || is_cand) {
-        const float kc = (float)hd->cls_k * (float)ori;
-        const float scale_dc = upstream_of(A.upstream, acc_dcls(b.n)) * A.dlw * 2.0f / kc;
-        float mx_old = -INFINITY;
-        for (int c = lane; c < ori; c += 32) {
-          const float xs = data[c * kBT + icol];
-          mx_old = fmaxf(mx_old, xs);
-          float gr = 0.f;
-          if (is_cls) {   // class-response L2 (:181-186,324-332): g = 2 (x_s - x_t) / (K ori)
-            const float xt = staged ? tc_s[c] : __ldg(tc_g + (size_t)c * HW);
-            const float df = xs - xt;
-            dcls_part = fmaf(df, df, dcls_part);
-            gr = scale_dc * df;
-          }
-          data[c * kBT + icol] = gr;
-        }
-        if (is_pos || is_cand) {
-          const float w_kd = sigmoid_ref(warp_max(mx_old));                                      // :217-218
-          item_box_rows(g, ws, A, b, data, hd, hd->kd, staged ? tc_s + ori_pad : nullptr, tb_g, HW, it, icol, hwI, is_pos, is_cand,
-                        staged, w_kd, avg2, inv_T, ga0, lane);
-        }
-      } else {
-        item_box_rows(g, ws, A, b, data, hd, hd->kd, nullptr, tb_g, HW, it, icol, hwI, is_pos, false, staged, 0.f, avg2, inv_T,
-                      ga0, lane);
-      }
-    }
+    if (A.use_tma[b.l]) consume_tile<true>(cc, b, k, data, hd, qfl_part, dcls_part, tphase);
+    else consume_tile<false>(cc, b, k, data, hd, qfl_part, dcls_part, tphase);
     if (cwarp == 0) TRACE(k, 13);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> the TMA store
     __syncwarp();
@@ -705,22 +707,15 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
   }
   A.lvl_tile_start[kLevels] = tiles;
   A.tiles_per_img = tiles;
-  {
-    int subs = 0;
-    for (int l = 0; l < kLevels; ++l) {
-      A.sub_start[l] = subs;
-      subs += (g.hw[l] + 31) / 32;
-    }
-    A.subs_per_img = subs;
-  }
   A.total_tiles = tiles * g.n_img;
   const int rows = g.C + kBoxCh;
-  A.stage_bytes = (int)(((size_t)rows * kBT * sizeof(float) + sizeof(TileHeader) +
-                         (size_t)kStageItems * (((g.ori + 3) & ~3) + kBoxCh) * sizeof(float) + 127) & ~(size_t)127);
+  A.stage_bytes = (int)(((size_t)rows * kBT * sizeof(float) + sizeof(TileHeader) + 127) & ~(size_t)127);
   // (the ring must be at least as deep as there are loader warps: a loader may only ever be one
   // phase ahead of a slot's empty barrier)
   int want_stages = g_dev_stages >= kBLoaders ? g_dev_stages : env_int("ERD_STUDENT_STAGES", 5, kBLoaders, 8);
-  const int max_smem = 227 * 1024 - 2048 - (int)((kLevels + g.n_img) * sizeof(double));
+  const size_t tail_bytes = (((size_t)(kLevels + g.n_img) * sizeof(double) + 127) & ~(size_t)127) +
+                            (size_t)(kBConsumers / 32) * (((g.ori * 16 + 127) & ~127) + ((kBoxCh * 16 + 127) & ~127));   // loss sums + teacher-column staging
+  const int max_smem = 227 * 1024 - 1024 - (int)tail_bytes;
   int S = max_smem / A.stage_bytes;
   if (S > want_stages) S = want_stages;
   if (S > 8) S = 8;
@@ -730,22 +725,24 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
   A.dev = g_dev_mask >= 0 ? g_dev_mask : env_int("ERD_STUDENT_DEV", 0, 0, 255);
   // tensor maps, cached on the pointers they were built for (the training loop reuses its buffers)
   struct MapCache {
-    const void* key[4 * kLevels];
-    int hw[kLevels], n_img, C;
+    const void* key[6 * kLevels];
+    int hw[kLevels], n_img, C, ori;
     int use_tma[kLevels];
     StudentMaps maps;
     bool valid = false;
   };
   static thread_local MapCache cache;
-  const void* key[4 * kLevels];
+  const void* key[6 * kLevels];
   for (int l = 0; l < kLevels; ++l) {
     key[l] = a.s_cls.p[l];
     key[kLevels + l] = a.s_box.p[l];
     key[2 * kLevels + l] = a.g_cls.p[l];
     key[3 * kLevels + l] = a.g_box.p[l];
+    key[4 * kLevels + l] = a.t_cls.p[l];
+    key[5 * kLevels + l] = a.t_box.p[l];
   }
-  bool hit = cache.valid && cache.n_img == g.n_img && cache.C == g.C;
-  for (int i = 0; hit && i < 4 * kLevels; ++i) hit = cache.key[i] == key[i];
+  bool hit = cache.valid && cache.n_img == g.n_img && cache.C == g.C && cache.ori == g.ori;
+  for (int i = 0; hit && i < 6 * kLevels; ++i) hit = cache.key[i] == key[i];
   for (int l = 0; hit && l < kLevels; ++l) hit = cache.hw[l] == g.hw[l];
   if (!hit) {
     static int allow_tma = env_int("ERD_STUDENT_TMA", 1, 0, 1);
@@ -755,12 +752,15 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
                          tma_encode_rows(&cache.maps.s_cls[l], a.s_cls.p[l], g.hw[l], rc, g.C, kBT) &&
                          tma_encode_rows(&cache.maps.s_box[l], a.s_box.p[l], g.hw[l], rb, kBoxCh, kBT) &&
                          tma_encode_rows(&cache.maps.g_cls[l], a.g_cls.p[l], g.hw[l], rc, g.C, kBT) &&
-                         tma_encode_rows(&cache.maps.g_box[l], a.g_box.p[l], g.hw[l], rb, kBoxCh, kBT);
+                         tma_encode_rows(&cache.maps.g_box[l], a.g_box.p[l], g.hw[l], rb, kBoxCh, kBT) &&
+                         tma_encode_rows(&cache.maps.t_cls[l], a.t_cls.p[l], g.hw[l], (long long)g.n_img * g.ori, g.ori, 4) &&
+                         tma_encode_rows(&cache.maps.t_box[l], a.t_box.p[l], g.hw[l], rb, kBoxCh, 4);
       cache.hw[l] = g.hw[l];
     }
-    for (int i = 0; i < 4 * kLevels; ++i) cache.key[i] = key[i];
+    for (int i = 0; i < 6 * kLevels; ++i) cache.key[i] = key[i];
     cache.n_img = g.n_img;
     cache.C = g.C;
+    cache.ori = g.ori;
     cache.valid = true;
   }
   for (int l = 0; l < kLevels; ++l) A.use_tma[l] = cache.use_tma[l];
@@ -771,7 +771,7 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const size_t smem = (size_t)S * A.stage_bytes + (size_t)(kLevels + g.n_img) * sizeof(double);
+  const size_t smem = (size_t)S * A.stage_bytes + tail_bytes;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(student_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -779,7 +779,11 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
   }
   const int grid = A.total_tiles < sms ? A.total_tiles : sms;
   ERD_LAUNCH(kKStudent, st, (student_pass_kernel<<<grid, kBThreads, smem, st>>>(g, ws, A, cache.maps)));
-  return cudaGetLastError();
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess)
+    fprintf(stderr, "student_pass launch failed: %s grid=%d threads=%d smem=%zu S=%d stage=%d tail=%zu params=%zu\n", cudaGetErrorString(le), grid,
+            kBThreads, smem, S, A.stage_bytes, tail_bytes, sizeof(Geo) + sizeof(Workspace) + sizeof(StudentArgs) + sizeof(StudentMaps));
+  return le;
 }
 
 }  // namespace erd

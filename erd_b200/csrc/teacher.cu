@@ -1,23 +1,20 @@
-// The teacher pass: ONE persistent kernel over the teacher head outputs that does everything
-// Elastic Response Selection needs except the ordered index lists:
-//   scan     per anchor m = max_c sigmoid(t_cls) (sigmoid is monotone: sigmoid(max logit)), the first
-//            argmax class, u = max_j raw box logit and the four softmax-integral distances -- the
-//            per-anchor cache the NMS and the ordered lists read -- plus fp64 partial sums per tile;
-//   thresholds  the warp that completes an image's last tile turns the partial sums into
-//            thr = mean + 2 std (unbiased) with a fixed reduction tree and publishes them
-//            (epoch-stamped flag, release / acquire);
-//   extract  once an image's thresholds are known, every warp revisits its tiles of that image --
-//            whose logits are still in L2 -- writes the per-anchor selection flags and copies the
-//            selected anchors' teacher rows into a compact, row-major STASH, so the student pass
-//            reads 160 + 272 contiguous bytes per selected anchor instead of 108 scattered sectors.
+// The teacher pass: ONE persistent streaming kernel over the teacher head outputs.
+//   scan        per anchor m = max_c sigmoid(t_cls) (sigmoid is monotone: sigmoid(max logit)), the
+//               first argmax class, u = max_j raw box logit and the four softmax-integral distances
+//               -- the per-anchor cache every later stage reads (ordered lists, NMS, the student
+//               pass's roles) -- plus fp64 partial sums per tile;
+//   (the thresholds thr = mean + 2 std come out of those sums in the short flags kernel that follows,
+//   ers.cu: a reduction inside this kernel would put a fence and an atomic behind every tile).
 // Reference: GFLIncrementERD.sel_pos / sel_pos_single (mmdet/models/detectors/
 // gfl_increment_erd.py:143-200); the Integral decode fused into the scan is
 // gfl_head_increment_erd.py:40-54,189-195.
 //
-// Structure: one CTA per SM.  A loader warp streams tiles of 32 anchors -- [ori x 32] class logits
-// and [68 x 32] box logits, two 2-D TMA loads (cp.async.bulk.tensor) -- into a ring of shared-memory
-// slots; 16 consumer warps take the tiles round robin, one anchor per lane, and never synchronise
-// with each other.  Levels whose rows are not 16-byte aligned come in as 4-byte cp.async copies.
+// Structure: one CTA per SM, up to 16 warps, each its own pipeline with its own shared-memory slot
+// for one tile of 32 anchors -- [ori x 32] class logits and [68 x 32] box logits, two 2-D TMA
+// loads (cp.async.bulk.tensor), one anchor per lane: request, wait, scan, publish, request the
+// next.  Nothing synchronises the warps.  The loads carry an L2 evict_last hint: the student pass
+// comes back for the rows of the selected anchors, and 126 MB of L2 hold most of the teacher.
+// Levels whose rows are not 16-byte aligned come in as 4-byte cp.async copies.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -27,18 +24,19 @@
 namespace erd {
 
 constexpr int kAT = 32;                      // anchors per tile = one warp
-constexpr int kAWarps = 16;                  // consumer warps
-constexpr int kAThreads = 32 * (kAWarps + 1);   // + the loader warp
-constexpr int kAMaxStages = 16;
+constexpr int kAMaxWarps = 16;               // consumer warps == ring slots (each warp owns one slot)
+constexpr int kAMaxThreads = 32 * kAMaxWarps;
 
 struct TeacherArgs {
   Ptr5 t_cls, t_box;
-  float* thr_out;        // (N, 2)
-  uint8_t* sel_flags;    // (N, A)
+  int32_t* cls_count;    // (N,) zeroed here for the flags kernel that follows
+  int32_t* box_count;
   int tiles_per_img, total_tiles, stages, stage_bytes;
   int lvl_tile_start[kLevels + 1];   // prefix of ceil(hw / kAT)
   int use_tma[kLevels];
   int l2_keep;
+  unsigned long long* trace;   // TEMPORARY: timestamps of one warp of CTA 0, [tile][8]
+  int trace_warp;
 };
 
 struct __align__(64) TeacherMaps {
@@ -61,6 +59,13 @@ __device__ __forceinline__ ATile a_tile(const Geo& g, const TeacherArgs& A, int 
   return b;
 }
 
+__device__ __forceinline__ unsigned long long t_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TTRACE(j, id) do { if (A.trace && blockIdx.x == 0 && warp == (A.trace_warp) && lane == 0) A.trace[(size_t)(j) * 8 + (id)] = t_gtime(); } while (0)
+
 __device__ __forceinline__ uint32_t t_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void t_wait(unsigned long long* bar, uint32_t parity) {
   uint32_t done = 0;
@@ -69,156 +74,80 @@ __device__ __forceinline__ void t_wait(unsigned long long* bar, uint32_t parity)
                  : "=r"(done) : "r"(t_smem(bar)), "r"(parity) : "memory");
 }
 
-// mean + 2 std (unbiased) of one image from its per-tile fp64 partial sums, by one warp: fixed
-// lane -> tile mapping and a fixed shuffle tree, so the thresholds are bit-reproducible run to run.
-__device__ __forceinline__ void image_thresholds(const Geo& g, const Workspace& ws, const TeacherArgs& A, int n, int lane) {
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  const double* p = ws.ers_part + (size_t)n * A.tiles_per_img * 4;
-  for (int t = lane; t < A.tiles_per_img; t += 32) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] += __ldcg(p + (size_t)t * 4 + i);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i] = warp_sum(acc[i]);
-  if (lane < 2) {
-    const double s1 = acc[lane * 2], s2 = acc[lane * 2 + 1];
-    const double An = (double)g.A;
-    const double mean = s1 / An;
-    double var = (s2 - s1 * s1 / An) / (An - 1.0);   // A == 1 -> NaN, as torch.std
-    if (var < 0.0) var = 0.0;
-    A.thr_out[n * 2 + lane] = __fadd_rn((float)mean, __fmul_rn(2.0f, (float)sqrt(var)));   // gfl_increment_erd.py:149,157
-  }
-}
-
-__global__ void __launch_bounds__(kAThreads, 1)
+__global__ void __launch_bounds__(kAMaxThreads, 1)
 teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ TeacherMaps maps) {
   extern __shared__ __align__(128) unsigned char s_raw[];
-  __shared__ __align__(8) unsigned long long s_full[kAMaxStages], s_empty[kAMaxStages];
-  const int S = A.stages;
+  __shared__ __align__(8) unsigned long long s_full[kAMaxWarps];
+  // Every warp is its own pipeline over the tiles k = warp, warp + W, ... of the CTA's sequence, with
+  // its own shared-memory slot: request the tile, scan it, publish its sums, wait for the image's
+  // thresholds, extract the selected rows from the slot.  Warps only meet at the per-image flag.
+  // A warp never waits for a flag while it holds an unscanned tile, and its tiles come in image
+  // order, so by induction over the images every flag is eventually published.
+  const int W = A.stages;   // warps == slots
   const int ori = g.ori;
   const int rows = ori + kBoxCh;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_smem(&s_full[s])), "r"(1 + 32));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t_smem(&s_empty[s])));
-    }
+    for (int s = 0; s < W; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_smem(&s_full[s])), "r"(1 + 32));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ws.teacher_epoch) + 1u;   // this launch's stamp
-
-  if (warp == kAWarps) {
-    // ================================================================== loader
-    unsigned long long pol;
-    if (A.l2_keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-    int k = 0;
-    for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, ++k) {
-      const int slot = k % S;
-      const uint32_t ph = (uint32_t)(k / S) & 1u;
-      const ATile b = a_tile(g, A, t);
-      const int HW = g.hw[b.l];
-      t_wait(&s_empty[slot], ph ^ 1u);
-      float* data = reinterpret_cast<float*>(s_raw + (size_t)slot * A.stage_bytes);
-      if (A.use_tma[b.l]) {
-        if (lane == 0) {
-          asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(t_smem(&s_full[slot])),
-                       "r"((uint32_t)(rows * kAT * sizeof(float))) : "memory");
-          asm volatile(
-              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
-              ::"r"(t_smem(data)), "l"(&maps.t_cls[b.l]), "r"(b.hw0), "r"(b.n * ori), "r"(t_smem(&s_full[slot])), "l"(pol) : "memory");
-          asm volatile(
-              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
-              ::"r"(t_smem(data + (size_t)ori * kAT)), "l"(&maps.t_box[b.l]), "r"(b.hw0), "r"(b.n * kBoxCh), "r"(t_smem(&s_full[slot])), "l"(pol) : "memory");
-        }
-      } else {
-        const float* sc = A.t_cls.p[b.l] + (size_t)b.n * ori * HW + b.hw0 + lane;
-        const float* sb = A.t_box.p[b.l] + (size_t)b.n * kBoxCh * HW + b.hw0 + lane;
-        const bool in = lane < b.cnt;
-#pragma unroll 8
-        for (int r = 0; r < rows; ++r) {
-          const float* src = r < ori ? sc + (size_t)r * HW : sb + (size_t)(r - ori) * HW;
-          if (in) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(t_smem(data + r * kAT + lane)), "l"(src) : "memory");
-          else data[r * kAT + lane] = 0.f;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(t_smem(&s_full[slot])) : "memory");
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(t_smem(&s_full[slot])) : "memory");
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < g.n_img; i += blockDim.x) {
+      A.cls_count[i] = 0;
+      A.box_count[i] = 0;
     }
-    return;
-  }
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));   // the student pass comes back for rows of these lines
+  float* data = reinterpret_cast<float*>(s_raw + (size_t)warp * A.stage_bytes);
+  unsigned long long* full = &s_full[warp];
 
-  // ==================================================================== consumer warps
-  // Tile k of the CTA belongs to warp k % 16.  A warp scans its tiles in order and, between scans,
-  // extracts those of its earlier tiles whose image thresholds have been published; it only ever
-  // BLOCKS on a threshold after its last scan, so every scan -- and with it every threshold --
-  // completes no matter how the warps interleave.
-  const float4 kZero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  (void)kZero4;
-  const int cap = g.sel_cap;
-  const int ori_pad = (ori + 3) & ~3;
-  int k_extract = warp;   // next tile of this warp to extract
-  auto flag_ready = [&](int n) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ws.img_flag + n) : "memory");
-    return v == epoch;
-  };
-  auto extract = [&](int kk) {
-    const int t = blockIdx.x + kk * gridDim.x;
+  auto request = [&](int k) {   // start loading tile k of the CTA's sequence into this warp's slot
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t >= A.total_tiles) return;
     const ATile b = a_tile(g, A, t);
     const int HW = g.hw[b.l];
-    const size_t ga = (size_t)b.n * g.A + g.start[b.l] + b.hw0 + lane;
-    const bool in = lane < b.cnt;
-    const float thr_c = __ldcg(A.thr_out + b.n * 2), thr_b = __ldcg(A.thr_out + b.n * 2 + 1);
-    const bool c = in && ws.t_m[ga] > thr_c, bx = in && ws.t_u[ga] > thr_b;   // strict (gfl_increment_erd.py:150,158)
-    if (in) A.sel_flags[ga] = (uint8_t)((c ? 1 : 0) | (bx ? 2 : 0));
-    const unsigned mc = __ballot_sync(0xffffffffu, c), mb = __ballot_sync(0xffffffffu, bx);
-    int base_c = 0, base_b = 0;
-    if (lane == 0) {
-      if (mc) base_c = atomicAdd(ws.stash_cnt + b.n * 2, __popc(mc));
-      if (mb) base_b = atomicAdd(ws.stash_cnt + b.n * 2 + 1, __popc(mb));
-      ws.stash_base[(size_t)b.n * A.tiles_per_img + b.sub] = make_int2(base_c, base_b);
-    }
-    base_c = __shfl_sync(0xffffffffu, base_c, 0);
-    base_b = __shfl_sync(0xffffffffu, base_b, 0);
-    // the selected anchors' rows: the whole warp copies one row at a time, all gathers of the tile in flight
-    const float* tc = A.t_cls.p[b.l] + (size_t)b.n * ori * HW + b.hw0;
-    const float* tb = A.t_box.p[b.l] + (size_t)b.n * kBoxCh * HW + b.hw0;
-    unsigned m = mc;
-    int rank = 0;
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1u;
-      float* dst = ws.stash_cls + ((size_t)b.n * cap + base_c + rank) * ori_pad;
-      for (int ch = lane; ch < ori; ch += 32) dst[ch] = __ldcg(tc + (size_t)ch * HW + j);
-      ++rank;
-    }
-    m = mb;
-    rank = 0;
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1u;
-      float* dst = ws.stash_box + ((size_t)b.n * cap + base_b + rank) * kBoxCh;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int ch = lane + 32 * i;
-        if (ch < kBoxCh) dst[ch] = __ldcg(tb + (size_t)ch * HW + j);
+    if (A.use_tma[b.l]) {
+      if (lane == 0) {
+        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(t_smem(full)),
+                     "r"((uint32_t)(rows * kAT * sizeof(float))) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+            ::"r"(t_smem(data)), "l"(&maps.t_cls[b.l]), "r"(b.hw0), "r"(b.n * ori), "r"(t_smem(full)), "l"(pol) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+            ::"r"(t_smem(data + (size_t)ori * kAT)), "l"(&maps.t_box[b.l]), "r"(b.hw0), "r"(b.n * kBoxCh), "r"(t_smem(full)), "l"(pol) : "memory");
       }
-      ++rank;
+    } else {
+      // rows of this level are not 16 B aligned (H*W % 4 != 0): 4-byte asynchronous copies, a warp-wide
+      // 128 B request per row; lanes past the level's end zero their column
+      const float* sc = A.t_cls.p[b.l] + (size_t)b.n * ori * HW + b.hw0 + lane;
+      const float* sb = A.t_box.p[b.l] + (size_t)b.n * kBoxCh * HW + b.hw0 + lane;
+      const bool in = lane < b.cnt;
+#pragma unroll 8
+      for (int r = 0; r < rows; ++r) {
+        const float* src = r < ori ? sc + (size_t)r * HW : sb + (size_t)(r - ori) * HW;
+        if (in) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(t_smem(data + r * kAT + lane)), "l"(src) : "memory");
+        else data[r * kAT + lane] = 0.f;
+      }
     }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(t_smem(full)) : "memory");
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(t_smem(full)) : "memory");
   };
 
-  int k = warp;
-  for (;; k += kAWarps) {
+  request(warp);
+  uint32_t ph = 0;
+  for (int k = warp;; k += W) {
     const int t = blockIdx.x + k * gridDim.x;
     if (t >= A.total_tiles) break;
-    const int slot = k % S;
-    const uint32_t ph = (uint32_t)(k / S) & 1u;
     const ATile b = a_tile(g, A, t);
-    const float* col = reinterpret_cast<const float*>(s_raw + (size_t)slot * A.stage_bytes) + lane;
-    t_wait(&s_full[slot], ph);
+    const float* col = data + lane;
+    const int tj = (k - warp) / W;
+    TTRACE(tj, 0);
+    t_wait(full, ph);
+    ph ^= 1u;
+    TTRACE(tj, 1);
     // ---- scan: one anchor per lane.  Lanes past the level's end hold zeros: computing on them
     // unconditionally keeps the loops free of predicates (their results are discarded).
     float best = col[0];
@@ -250,17 +179,18 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
       dist[sd] = __fdiv_rn(num, sum);                           // Integral (:40-54)
       u = fmaxf(u, mx);
     }
+    TTRACE(tj, 2);
+    // every lane has read the slot: refill it now, so the next tile's latency overlaps the publishing below
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the slot before the next bulk write
     __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(t_smem(&s_empty[slot])) : "memory");
+    request(k + W);
+    TTRACE(tj, 6);
     const bool in = lane < b.cnt;
+    const float m = sigmoid_ref(best);
+    const size_t ga = (size_t)b.n * g.A + g.start[b.l] + b.hw0 + lane;
+    // the tile's fp64 sums (the flags kernel that follows reduces them to the image's thresholds)
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     if (in) {
-      const float m = sigmoid_ref(best);
-      const size_t ga = (size_t)b.n * g.A + g.start[b.l] + b.hw0 + lane;
-      ws.t_m[ga] = m;
-      ws.t_arg[ga] = arg;
-      ws.t_u[ga] = u;
-      ws.t_dist[ga] = make_float4(dist[0], dist[1], dist[2], dist[3]);
       acc[0] = (double)m;
       acc[1] = (double)m * (double)m;
       acc[2] = (double)u;
@@ -272,53 +202,21 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
       const double v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
       __stcg(ws.ers_part + ((size_t)b.n * A.tiles_per_img + b.sub) * 4 + lane, v);
     }
-    // ---- the image's last tile computes its thresholds and opens the image for extraction
-    __threadfence();
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) last = atomicAdd(ws.img_cnt + b.n, 1) == A.tiles_per_img - 1;
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      __threadfence();
-      image_thresholds(g, ws, A, b.n, lane);
-      if (lane == 0) {
-        ws.img_cnt[b.n] = 0;                 // clean for the next launch
-        ws.stash_cnt[b.n * 2] = 0;
-        ws.stash_cnt[b.n * 2 + 1] = 0;
-      }
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ws.img_flag + b.n), "r"(epoch) : "memory");
+    if (in) {   // the per-anchor cache
+      ws.t_m[ga] = m;
+      ws.t_arg[ga] = arg;
+      ws.t_u[ga] = u;
+      ws.t_dist[ga] = make_float4(dist[0], dist[1], dist[2], dist[3]);
     }
-    // ---- extract what is ready, without blocking
-    while (k_extract <= k) {
-      const int te = blockIdx.x + k_extract * gridDim.x;
-      if (!flag_ready(te / A.tiles_per_img)) break;
-      extract(k_extract);
-      k_extract += kAWarps;
-    }
-  }
-  // ---- drain: the remaining tiles of this warp, now waiting for their thresholds
-  for (; k_extract < k; k_extract += kAWarps) {
-    const int te = blockIdx.x + k_extract * gridDim.x;
-    while (!flag_ready(te / A.tiles_per_img)) __nanosleep(200);
-    extract(k_extract);
-  }
-  // ---- the last warp of the grid to finish stamps the epoch (and leaves the ticket clean)
-  __threadfence();
-  __syncwarp();
-  if (lane == 0) {
-    const unsigned int total = gridDim.x * kAWarps;
-    if (atomicAdd(ws.teacher_done, 1u) == total - 1u) {
-      *ws.teacher_done = 0u;
-      *ws.teacher_epoch = epoch;
-      ws.stash_valid[0] = 1u;
-    }
+    TTRACE(tj, 7);
   }
 }
 
 // ----------------------------------------------------------------------------- host side
 bool tma_encode_rows(void* map, const void* base, int hw, long long rows_total, int box_rows, int box_cols);   // student.cu
+
+static unsigned long long* g_ttrace = nullptr;
+static int g_ttrace_warp = 0;
 
 static int t_env_int(const char* name, int dflt, int lo, int hi) {
   const char* e = getenv(name);
@@ -327,14 +225,13 @@ static int t_env_int(const char* name, int dflt, int lo, int hi) {
   return v < lo || v > hi ? dflt : v;
 }
 
-// returns the number of tiles per image (the ordered-list kernel does not need it any more; kept for symmetry)
-cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box, float* thr,
-                                uint8_t* sel_flags, cudaStream_t st) {
+cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box,
+                                int32_t* cls_count, int32_t* box_count, int* tiles_per_img, cudaStream_t st) {
   TeacherArgs A;
   A.t_cls = t_cls;
   A.t_box = t_box;
-  A.thr_out = thr;
-  A.sel_flags = sel_flags;
+  A.cls_count = cls_count;
+  A.box_count = box_count;
   int tiles = 0;
   for (int l = 0; l < kLevels; ++l) {
     A.lvl_tile_start[l] = tiles;
@@ -343,16 +240,16 @@ cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t
   A.lvl_tile_start[kLevels] = tiles;
   A.tiles_per_img = tiles;
   A.total_tiles = tiles * g.n_img;
+  if (tiles_per_img) *tiles_per_img = tiles;
   const int rows = g.ori + kBoxCh;
   A.stage_bytes = rows * kAT * (int)sizeof(float);   // a multiple of 128
-  int S = (220 * 1024) / A.stage_bytes;
-  static int want = t_env_int("ERD_TEACHER_STAGES", 12, 2, kAMaxStages);
-  if (S > want) S = want;
-  if (S > kAMaxStages) S = kAMaxStages;
-  if (S < 2) return cudaErrorInvalidValue;
+  int S = (224 * 1024) / A.stage_bytes;   // consumer warps == ring slots
+  if (S > kAMaxWarps) S = kAMaxWarps;
+  if (S < 4) return cudaErrorInvalidValue;   // ori_classes too large for this tiling
   A.stages = S;
-  static int l2_keep = t_env_int("ERD_TEACHER_L2", 1, 0, 1);
-  A.l2_keep = l2_keep;
+  A.l2_keep = 0;
+  A.trace = g_ttrace;
+  A.trace_warp = g_ttrace_warp;
   struct MapCache {
     const void* key[2 * kLevels];
     int hw[kLevels], n_img, ori;
@@ -392,8 +289,13 @@ cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t
     smem_set = smem;
   }
   const int grid = A.total_tiles < sms ? A.total_tiles : sms;
-  ERD_LAUNCH(kKErsScan, st, (teacher_pass_kernel<<<grid, kAThreads, smem, st>>>(g, ws, A, cache.maps)));
+  ERD_LAUNCH(kKErsScan, st, (teacher_pass_kernel<<<grid, 32 * S, smem, st>>>(g, ws, A, cache.maps)));
   return cudaGetLastError();
 }
 
 }  // namespace erd
+
+extern "C" void erd_teacher_trace(unsigned long long* p, int warp) {
+  erd::g_ttrace = p;
+  erd::g_ttrace_warp = warp;
+}

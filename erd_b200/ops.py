@@ -125,8 +125,6 @@ class Plan:
         arguments): pad them into the plan buffers and rebuild the per-anchor flags."""
         if len(cls_inds) != self.n or len(box_inds) != self.n:
             raise AssertionError('one index tensor per image expected')
-        N.check(N.load().erd_selection_replaced(C.byref(self.shape), self.ws.data_ptr(),
-                                                torch.cuda.current_stream().cuda_stream), 'erd_selection_replaced')
         self.sel_flags.zero_()
         for lst, inds, cnt, bit in ((cls_inds, self.cls_inds, self.cls_count, 1),
                                     (box_inds, self.box_inds, self.box_count, 2)):

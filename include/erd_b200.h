@@ -101,12 +101,6 @@ int erd_ers_select(const ErdShape* shape, const float* const* t_cls, const float
                    int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds, int32_t* box_count,
                    float* thr, uint8_t* sel_flags, void* ws, void* stream);
 
-/* Tell the library that the caller overwrote cls_inds / box_inds / their counts / sel_flags with a
- * selection of its own (the reference's loss_by_feat takes the index lists as arguments,
- * gfl_head_increment_erd.py:334-343): the teacher-row stash erd_ers_select built no longer matches
- * it, and erd_loss_fwd_bwd gathers the teacher rows from the tensors instead. */
-int erd_selection_replaced(const ErdShape* shape, void* ws, void* stream);
-
 /* Anchors, valid flags, ATSS assignment, pseudo sampling.
  * Replaces AnchorHead.get_anchors (dense_heads/anchor_head.py:164-199),
  * GFLHead.get_targets/_get_targets_single (dense_heads/gfl_head.py:504-679),

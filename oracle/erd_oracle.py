@@ -410,10 +410,15 @@ def loss_by_feat(t_cls: Sequence[Tensor], t_box: Sequence[Tensor], s_cls: Sequen
                  ori: int, dist_loss_weight: float, gt_bboxes: Sequence[Tensor],
                  gt_labels: Sequence[Tensor], pad_shapes: Sequence[Tuple[int, int]],
                  num_classes: int = 80, reg_max: int = 16, strides: Sequence[int] = STRIDES,
-                 world_size: int = 1, report: Optional[dict] = None):
-    """gfl_head_increment_erd.py:334-454.  ``world_size`` only documents that the two
-    avg factors are reduce_mean'd (dist_utils.py:59-65); on one process it is a no-op.
+                 reduce_mean=None, report: Optional[dict] = None):
+    """gfl_head_increment_erd.py:334-454.  ``reduce_mean``: the reference's
+    ``mmdet.utils.reduce_mean`` (dist_utils.py:59-65: ``t.clone().div_(world).all_reduce(SUM)``)
+    as a callable on 0-dim float tensors; None = not distributed (passthrough, :61-62).  It is
+    applied at the reference's two call sites (:390-391 and :406-407), which is how the
+    multi-rank tests feed this rank the world-averaged normalisers.
     Returns the reference's loss dict."""
+    if reduce_mean is None:
+        reduce_mean = lambda t: t
     n = s_cls[0].size(0)
     sizes = [tuple(t.shape[-2:]) for t in s_cls]
     assert len(sizes) == len(strides)                                             # :374
@@ -431,7 +436,8 @@ def loss_by_feat(t_cls: Sequence[Tensor], t_box: Sequence[Tensor], s_cls: Sequen
             report.setdefault('atss', []).append(rep_i)
             report.setdefault('gt_inds', []).append(per_img[-1]['gt_inds'])
     avg1 = float(sum(max(t['num_pos'], 1) for t in per_img))                      # gfl_head.py:548-549, sampling_result.py:96-100
-    avg1 = torch.tensor(avg1, dtype=torch.float).item()                           # :390-391
+    avg1_local = avg1
+    avg1 = reduce_mean(torch.tensor(avg1, dtype=torch.float)).item()              # :390-391
 
     def by_level(key):                                                            # misc.py:427-440
         stacked = torch.stack([t[key] for t in per_img], 0)
@@ -446,11 +452,13 @@ def loss_by_feat(t_cls: Sequence[Tensor], t_box: Sequence[Tensor], s_cls: Sequen
         a, b, c, wsum, sc = level_loss(anc_l[lv], s_cls[lv], s_box[lv], lab_l[lv], lw_l[lv], tgt_l[lv],
                                        s, num_classes, ori, avg1, reg_max)
         l_cls.append(a); l_bbox.append(b); l_dfl.append(c); wsums.append(wsum); scores.append(sc)
-    avg2 = sum(wsums).clamp(min=1).item()                                         # :406-407
+    wsum_local = sum(wsums)
+    avg2 = reduce_mean(wsum_local.detach().clone()).clamp_(min=1).item()          # :406-407
     l_bbox = [x / avg2 for x in l_bbox]                                           # :408-409
     l_dfl = [x / avg2 for x in l_dfl]
     if report is not None:
         report['avg_factors'] = (avg1, avg2)
+        report['avg_local'] = (avg1_local, float(wsum_local))
         report['scores'] = scores
 
     anc = torch.cat(anc_l, dim=1)                                                 # :412
@@ -477,12 +485,13 @@ def total_loss(losses: dict) -> Tensor:
 
 
 def erd_step(t_cls, t_box, s_cls, s_box, gt_bboxes, gt_labels, pad_shapes, ori,
-             dist_loss_weight=1.0, num_classes=80, reg_max=16, report=None):
+             dist_loss_weight=1.0, num_classes=80, reg_max=16, report=None, reduce_mean=None):
     """ERS selection + loss_by_feat + backward: the unit the benchmark calls one step
     (gfl_increment_erd.py:202-220 minus the conv stacks).  Student tensors must be leaf
     tensors with requires_grad.  Returns (losses dict, cls_inds, box_inds)."""
     cls_inds, box_inds = sel_pos(t_cls, t_box, report)
     losses = loss_by_feat(t_cls, t_box, s_cls, s_box, cls_inds, box_inds, ori, dist_loss_weight,
-                          gt_bboxes, gt_labels, pad_shapes, num_classes, reg_max, report=report)
+                          gt_bboxes, gt_labels, pad_shapes, num_classes, reg_max, reduce_mean=reduce_mean,
+                          report=report)
     total_loss(losses).backward()
     return losses, cls_inds, box_inds

@@ -13,7 +13,7 @@ losses = torch.empty(p.num_losses, device='cuda')
 def step():
     path.prepare(p, b.t_cls, b.t_box, b.s_cls, b.s_box); path.reduce_avg(p)
     path.loss_fwd_bwd(p, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls, g_box, losses, 1.0)
-lib.erd_student_dev(int(os.environ.get('DEV', 0)), 5)
+lib.erd_student_dev(int(os.environ.get('DEV', 0)), int(os.environ.get('STAGES', 5)))
 for _ in range(3): step()
 torch.cuda.synchronize()
 tr = torch.zeros(64 * 16, dtype=torch.int64, device='cuda')
