@@ -28,8 +28,11 @@
 namespace erd {
 
 constexpr int kBT = 64;                    // anchors per tile
-constexpr int kBConsumers = 512;           // 16 consumer warps
-constexpr int kBGroups = kBConsumers / kBT;   // channel groups of the dense part: thread = (column, group)
+constexpr int kBConsumers = 512;           // 16 consumer warps ...
+constexpr int kBTeams = 4;                 // ... in 4 teams; tile k of the CTA is consumed by team k % 4
+constexpr int kBTeamWarps = kBConsumers / 32 / kBTeams;
+constexpr int kBTeamThreads = 32 * kBTeamWarps;
+constexpr int kBGroups = kBTeamThreads / kBT;   // channel groups of the dense part: thread = (column, group)
 constexpr int kBLoaders = 3;               // loader warps (tile k of the CTA is loaded by warp k % 3)
 constexpr int kBThreads = kBConsumers + 32 * (kBLoaders + 1);   // + the store warp
 constexpr int kStageItems = 12;            // positives per tile whose records are staged in the slot (more: read from global)
@@ -257,7 +260,7 @@ struct ConsumerCtx {
   float* tcol;                   // this warp's teacher-column staging buffer
   unsigned long long* tbar;      // ... and the barrier its fetches complete on
   unsigned long long pol_keep;
-  int tbox_off, lane, cwarp, col, q, oq, cq;
+  int tbox_off, lane, cwarp, twarp, col, q, oq, cq;   // cwarp: warp in the CTA, twarp: warp in its team
   float inv_avg1, avg2, inv_T;
 };
 
@@ -272,7 +275,8 @@ __device__ __forceinline__ void consume_tile(const ConsumerCtx& cc, const BTile&
   const StudentArgs& A = cc.A;
   const StudentMaps& maps = cc.maps;
   float* tcol = cc.tcol;
-  const int tbox_off = cc.tbox_off, lane = cc.lane, cwarp = cc.cwarp, col = cc.col, q = cc.q, oq = cc.oq, cq = cc.cq;
+  const int tbox_off = cc.tbox_off, lane = cc.lane, cwarp = cc.cwarp, twarp = cc.twarp, col = cc.col, q = cc.q, oq = cc.oq, cq = cc.cq;
+  (void)cwarp;
   const float inv_avg1 = cc.inv_avg1, avg2 = cc.avg2, inv_T = cc.inv_T;
   const int C = g.C, ori = g.ori, cn = g.cn;
   constexpr int bq = (kBoxCh + kBGroups - 1) / kBGroups;
@@ -299,7 +303,7 @@ __device__ __forceinline__ void consume_tile(const ConsumerCtx& cc, const BTile&
     const size_t ga0 = (size_t)b.n * g.A + g.start[b.l] + b.hw0;
     // this warp's first item of the tile: request its teacher column now, use it after the dense part
     const int n_items = (A.dev & 1) ? 0 : hd->n_items;
-    int it = (cwarp - k) & (kBConsumers / 32 - 1);
+    int it = (twarp - k / kBTeams) & (kBTeamWarps - 1);   // item i of the team's j-th tile goes to its warp (i + j) % 4
     bool fetched = false;
     if (it < n_items) fetched = fetch_teacher(it);
     // Where the tile lives: in the ring slot (logits in, gradients out, in place), or -- levels without a
@@ -362,7 +366,7 @@ __device__ __forceinline__ void consume_tile(const ConsumerCtx& cc, const BTile&
     // ------------------------------------------------------------ sparse items: one WARP per special column
     // Item i of tile k goes to warp (i + k) % 16.  Lane layout for the box rows: lane = side * 8 + b,
     // holding bins b, b + 8 (and 16 for b == 0) of its side; reductions over a side are 8-lane shuffles.
-    for (; it < n_items; it += kBConsumers / 32) {
+    for (; it < n_items; it += kBTeamWarps) {
       if (!fetched) fetched = fetch_teacher(it);   // a second item of this warp in the same tile (rare)
       const int icol = hd->item_col[it];
       const unsigned irole = hd->role[icol];
@@ -427,7 +431,7 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&s_full[s], 1 + 32);   // the loader's lane 0 (after arming the TMA bytes) + its 32 lanes' cp.async batches
-      mbar_init(&s_done[s], kBConsumers / 32);   // one arrival per consumer warp
+      mbar_init(&s_done[s], kBTeamWarps);        // one arrival per warp of the consuming team
       mbar_init(&s_empty[s], 1);
     }
     for (int w = 0; w < kBConsumers / 32; ++w) mbar_init(&s_tbar[w], 1);
@@ -584,8 +588,10 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
   // next slot.  Loss sums travel in registers and are flushed (warp shuffle + one fp64 atomic) when
   // the level / image of the CTA's tile sequence changes.
   const int ctid = threadIdx.x;            // 0 .. kBConsumers - 1
-  const int col = ctid & (kBT - 1), q = ctid / kBT;
   const int cwarp = ctid >> 5;
+  const int team = cwarp / kBTeamWarps, twarp = cwarp % kBTeamWarps;
+  const int ttid = ctid - team * kBTeamThreads;   // thread in the team
+  const int col = ttid & (kBT - 1), q = ttid / kBT;
   const int oq = (ori + kBGroups - 1) / kBGroups, cq = (cn + kBGroups - 1) / kBGroups;
   constexpr int bq = (kBoxCh + kBGroups - 1) / kBGroups;
   const float inv_avg1 = 1.0f / (float)((double)A.avg[0] + (double)kEps32);   // losses/utils.py:60-61
@@ -595,7 +601,7 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
   float* tcol = s_tcol + (size_t)cwarp * tcol_stride;   // this warp's teacher-column staging: [ori][4] | [68][4]
   uint32_t tphase = 0;
-  const ConsumerCtx cc{g, ws, A, maps, tcol, &s_tbar[cwarp], pol_keep, tbox_off, lane, cwarp, col, q, oq, cq, inv_avg1, avg2, inv_T};
+  const ConsumerCtx cc{g, ws, A, maps, tcol, &s_tbar[cwarp], pol_keep, tbox_off, lane, cwarp, twarp, col, q, oq, cq, inv_avg1, avg2, inv_T};
   int cur_img = -1, cur_lvl = -1;
   float dcls_part = 0.f;   // sum (x_s - x_t)^2 of the current image, this thread
   float qfl_part = 0.f;    // QFL loss sum of the current (image, level), this thread
@@ -608,12 +614,12 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
     qfl_part = 0.f;
     dcls_part = 0.f;
   };
-  int k = 0;
-  for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, ++k) {
+  for (int k = team;; k += kBTeams) {
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t >= A.total_tiles) break;
     const int slot = k % S;
     const uint32_t ph = (uint32_t)(k / S) & 1u;
     const BTile b = b_tile(g, A, t);
-    const int HW = g.hw[b.l];
     float* data = slot_data(slot);
     TileHeader* hd = slot_head(slot);
     if (b.n != cur_img || b.l != cur_lvl) {   // warp-uniform
@@ -622,16 +628,16 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
       cur_lvl = b.l;
     }
     mbar_wait_parity(&s_full[slot], ph);
-    if (cwarp == 0) TRACE(k, 2);
-    if (cwarp == 15) TRACE(k, 6);
+    if (twarp == 0) TRACE(k, 2);
+    if (twarp == 3) TRACE(k, 6);
     if (A.use_tma[b.l]) consume_tile<true>(cc, b, k, data, hd, qfl_part, dcls_part, tphase);
     else consume_tile<false>(cc, b, k, data, hd, qfl_part, dcls_part, tphase);
-    if (cwarp == 0) TRACE(k, 13);
+    if (twarp == 0) TRACE(k, 13);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> the TMA store
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_done[slot]);
-    if (cwarp == 0) TRACE(k, 3);
-    if (cwarp == 15) TRACE(k, 7);
+    if (twarp == 0) TRACE(k, 3);
+    if (twarp == 3) TRACE(k, 7);
   }
   flush();
   asm volatile("bar.sync 1, %0;" ::"n"(kBConsumers) : "memory");   // consumers only: every warp has flushed
@@ -710,16 +716,20 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
   A.total_tiles = tiles * g.n_img;
   const int rows = g.C + kBoxCh;
   A.stage_bytes = (int)(((size_t)rows * kBT * sizeof(float) + sizeof(TileHeader) + 127) & ~(size_t)127);
-  // (the ring must be at least as deep as there are loader warps: a loader may only ever be one
-  // phase ahead of a slot's empty barrier)
-  int want_stages = g_dev_stages >= kBLoaders ? g_dev_stages : env_int("ERD_STUDENT_STAGES", 5, kBLoaders, 8);
+  // (the ring must be at least as deep as there are loader warps and consumer teams: nobody may get
+  // more than one phase ahead of a slot's barriers)
+  int want_stages = g_dev_stages >= kBTeams ? g_dev_stages : env_int("ERD_STUDENT_STAGES", 5, kBTeams, 8);
   const size_t tail_bytes = (((size_t)(kLevels + g.n_img) * sizeof(double) + 127) & ~(size_t)127) +
                             (size_t)(kBConsumers / 32) * (((g.ori * 16 + 127) & ~127) + ((kBoxCh * 16 + 127) & ~127));   // loss sums + teacher-column staging
   const int max_smem = 227 * 1024 - 1024 - (int)tail_bytes;
   int S = max_smem / A.stage_bytes;
   if (S > want_stages) S = want_stages;
   if (S > 8) S = 8;
-  if (S < kBLoaders) return cudaErrorInvalidValue;   // num_classes too large for the smallest ring
+  // A team only waits on the full barriers of its own tiles, so a slot must always be consumed by the
+  // same team (S a multiple of the team count): a team that waited on a slot whose previous tile belongs
+  // to another team could run a whole phase ahead of it, and a parity wait cannot tell phase j+1 from j-1.
+  S -= S % kBTeams;
+  if (S < kBTeams) return cudaErrorInvalidValue;   // num_classes too large for the smallest ring
   A.stages = S;
   A.trace = g_trace;
   A.dev = g_dev_mask >= 0 ? g_dev_mask : env_int("ERD_STUDENT_DEV", 0, 0, 255);
