@@ -6,18 +6,25 @@
 // (dense_heads/gfl_head_increment_erd.py:142-322) and their autograd backward; closed forms in
 // loss_math.cuh.
 //
-// Structure (one CTA per SM, warp specialised):
-//   load warp   : per tile of 64 anchors, two 2-D TMA loads (cp.async.bulk.tensor) bring the
-//                 [C x 64] class tile and the [68 x 64] box tile of the student into a ring slot;
-//                 meanwhile the warp gathers the tile's per-anchor roles (assignment, ERS flags,
-//                 the positives' targets) into the slot's header.
-//   8 consumer  : transform the tile IN PLACE in shared memory (logits -> gradients).  Dense part:
-//   warps         thread = (anchor column, quarter of the channels), conflict free.  Sparse part:
-//                 one quad of lanes per ERS row / positive / box candidate of the tile.
-//   store warp  : two 2-D TMA stores write the slot to the gradient tensors; the slot returns to
-//                 the load warp once the TMA engine has read it.
+// Structure (one CTA per SM).  The CTA is four independent TEAMS, each its own
+// pipeline over every fourth tile of the CTA's sequence (a tile = 32 anchors x all channels):
+//   IO warp (1 per team)    double-buffers the team's two shared-memory slots.  Per tile: two 2-D TMA
+//                           loads (cp.async.bulk.tensor) bring the [C x 32] class tile and the [68 x 32]
+//                           box tile of the student; the per-anchor roles (assignment, ERS flags) go
+//                           into the slot's header, the positives' records and the teacher columns of
+//                           the tile's ERS anchors into its staging area (cp.async).  When the
+//                           consumers are done with a slot, two TMA stores write it to the gradient
+//                           tensors and the next load is issued.
+//   4 consumer warps        transform the tile IN PLACE (logits -> gradients).  Dense part: lane =
+//                           anchor column, warp = quarter of the channels, loads batched ahead of the
+//                           arithmetic.  Sparse part: one warp per special column (ERS row / positive /
+//                           box candidate) of the tile.
+// Teams never synchronise with each other, and inside a team the only synchronisation is the pair of
+// mbarriers per slot (full: IO -> consumers, done: consumers -> IO), always waited on in tile order,
+// so no barrier phase can be skipped.
 // Pyramid levels whose rows are not 16-byte aligned (H*W % 4 != 0: a few % of the anchors) cannot
-// have a tensor map; their tiles take the same path with plain loads / stores by the consumers.
+// have a tensor map: the IO warp moves their tiles with 4-byte cp.async copies / plain stores;
+// the consumers see no difference.
 #include <cuda.h>   // CUtensorMap types; the encoder itself is looked up through the runtime (below)
 
 #include <cstdio>
@@ -27,34 +34,37 @@
 
 namespace erd {
 
-constexpr int kBT = 64;                    // anchors per tile
-constexpr int kBConsumers = 512;           // 16 consumer warps ...
-constexpr int kBTeams = 4;                 // ... in 4 teams; tile k of the CTA is consumed by team k % 4
-constexpr int kBTeamWarps = kBConsumers / 32 / kBTeams;
-constexpr int kBTeamThreads = 32 * kBTeamWarps;
-constexpr int kBGroups = kBTeamThreads / kBT;   // channel groups of the dense part: thread = (column, group)
-constexpr int kBLoaders = 3;               // loader warps (tile k of the CTA is loaded by warp k % 3)
-constexpr int kBThreads = kBConsumers + 32 * (kBLoaders + 1);   // + the store warp
-constexpr int kStageItems = 12;            // positives per tile whose records are staged in the slot (more: read from global)
+constexpr int kBT = 32;                                   // anchors per tile: one per lane
+constexpr int kTeams = 4;                                 // independent pipelines per CTA
+constexpr int kTeamWarps = 4;                             // consumer warps per team
+constexpr int kConsumerWarps = kTeams * kTeamWarps;
+constexpr int kConsumers = 32 * kConsumerWarps;
+constexpr int kBThreads = kConsumers + 32 * kTeams;       // + one IO warp per team
+constexpr int kSlots = 2 * kTeams;                        // two slots per team
+constexpr int kStageItems = 12;                           // special columns per tile whose records / teacher columns are staged in the slot
+constexpr int kQflChunk = 5;                              // QFL elements a thread loads ahead of the arithmetic
+static_assert(kBoxCh % kTeamWarps == 0, "box rows are split evenly over the team's warps");
+constexpr int kBoxPerWarp = kBoxCh / kTeamWarps;
 
 constexpr unsigned kRoleValid = 1u, kRolePos = 2u, kRoleCls = 4u, kRoleCand = 8u;
 constexpr unsigned kRoleSpecial = kRolePos | kRoleCls | kRoleCand;
 
-// Header of a ring slot, behind the tile's logits.  `rec` is filled by asynchronous copies
-// (cp.async) that complete on the slot's full barrier.
+// Header of a slot, behind the tile's logits.  `rec` is filled by asynchronous copies (cp.async)
+// that complete on the slot's full barrier, like the teacher columns behind the header.
 struct __align__(32) TileHeader {
   PosRec rec[kStageItems];          // records of the tile's first positives (index: rec_of[item])
+  float kd[kBT];                    // weighted KL of the items that are box candidates (consumers -> IO warp)
+  int n, l, hw0, cnt;               // the tile: image, level, first anchor of the level, anchors
+  int n_items, cls_k, tma, pad0;    // cls_k: K_cls of the tile's image (class-response normaliser)
   unsigned char role[kBT];
   unsigned char item_col[kBT];      // special columns of the tile, ascending
   unsigned char col_item[kBT];      // column -> its item index
   unsigned char rec_of[kBT];        // item -> index into rec[], 255: not staged
-  float kd[kBT];                    // weighted KL of the items that are box candidates (consumers -> store warp)
-  int n_items, cls_k, pad0, pad1;   // cls_k: K_cls of the tile's image (class-response normaliser)
 };
 
 struct StudentArgs {
   Ptr5 t_cls, t_box;
-  MPtr5 g_cls, g_box;        // used by the non-TMA tiles
+  MPtr5 g_cls, g_box;        // used by the tiles of levels without a tensor map
   Ptr5 s_cls, s_box;
   const int32_t* gt_inds;
   const uint8_t* sel_flags;
@@ -63,16 +73,15 @@ struct StudentArgs {
   const float* upstream;
   const unsigned int* skip_flag;
   float dlw;
-  int tiles_per_img, total_tiles, stages, stage_bytes;
-  int dev;                           // TEMPORARY dev switches: 1 skip sparse, 2 skip dense, 4 skip stores
-  unsigned long long* trace;         // TEMPORARY: per-tile timestamps of CTA 0 [tile][8]
+  int tiles_per_img, total_tiles;
+  int slot_bytes, hdr_off, tst_off;  // slot layout: [rows x 32 logits][TileHeader][tstage_items x (ori + 68) teacher logits]
+  int tstage_items;                  // items per tile whose teacher column is staged (more: read from global)
   int lvl_tile_start[kLevels + 1];   // prefix of ceil(hw / kBT)
   int use_tma[kLevels];
 };
 
 struct __align__(64) StudentMaps {
-  CUtensorMap s_cls[kLevels], s_box[kLevels], g_cls[kLevels], g_box[kLevels];   // [C x 64] / [68 x 64] tiles
-  CUtensorMap t_cls[kLevels], t_box[kLevels];                                   // [ori x 4] / [68 x 4]: one anchor's teacher column
+  CUtensorMap s_cls[kLevels], s_box[kLevels], g_cls[kLevels], g_box[kLevels];   // [C x 32] / [68 x 32] tiles
 };
 
 struct BTile {
@@ -91,13 +100,6 @@ __device__ __forceinline__ BTile b_tile(const Geo& g, const StudentArgs& A, int 
   b.cnt = min(kBT, g.hw[b.l] - b.hw0);
   return b;
 }
-
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define TRACE(kk, slotid) do { if (A.trace && blockIdx.x == 0 && lane == 0) A.trace[(size_t)(kk) * 16 + (slotid)] = gtime(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -141,13 +143,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
 
 // Box rows of one special column (a positive and / or an ERS box candidate), by one whole warp, in
 // place in the tile.  lane = side * 8 + b holds bins b, b + 8 (b == 0: also 16) of its side.
+// `tb` / `tbs`: the teacher's box column of this anchor (staged in the slot: stride 1; global: stride H*W).
 __device__ __forceinline__ void item_box_rows(const Geo& g, const Workspace& ws, const StudentArgs& A, const BTile& b,
-                                              const float* box_in, float* box_out, int pitch, const TileHeader* hd, float* hd_kd, const float* tbox_staged,
-                                              const float* tbox_global, int HW, int it, int icol, int hwI, bool is_pos,
-                                              bool is_cand, float w_kd, float avg2, float inv_T, size_t ga0, int lane) {
+                                              float* box, const TileHeader* hd, float* hd_kd, const float* tb, size_t tbs,
+                                              int it, int icol, int hwI, bool is_pos, bool is_cand, float w_kd, float avg2,
+                                              float inv_T, size_t ga0, int lane) {
+  constexpr int pitch = kBT;
   const int side = lane >> 3, bb = lane & 7;
-  const float* brow_in = box_in + (size_t)(side * kBins) * pitch + icol;
-  float* brow = box_out + (size_t)(side * kBins) * pitch + icol;
+  const float* brow_in = box + (size_t)(side * kBins) * pitch + icol;
+  float* brow = box + (size_t)(side * kBins) * pitch + icol;
   int jb[3];
   bool ok[3];
   float zs[3], out[3];
@@ -164,7 +168,7 @@ __device__ __forceinline__ void item_box_rows(const Geo& g, const Workspace& ws,
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int ch = side * kBins + jb[i];
-      const float zt = !ok[i] ? -INFINITY : tbox_staged ? tbox_staged[ch * 4] : __ldg(tbox_global + (size_t)ch * HW);
+      const float zt = ok[i] ? tb[(size_t)ch * tbs] : -INFINITY;
       a[i] = zs[i] * inv_T;
       t[i] = zt * inv_T;
       ms = fmaxf(ms, a[i]);
@@ -256,157 +260,120 @@ struct ConsumerCtx {
   const Geo& g;
   const Workspace& ws;
   const StudentArgs& A;
-  const StudentMaps& maps;
-  float* tcol;                   // this warp's teacher-column staging buffer
-  unsigned long long* tbar;      // ... and the barrier its fetches complete on
-  unsigned long long pol_keep;
-  int tbox_off, lane, cwarp, twarp, col, q, oq, cq;   // cwarp: warp in the CTA, twarp: warp in its team
+  int lane, q, oq, cq;           // q: warp in its team = quarter of the channels
   float inv_avg1, avg2, inv_T;
 };
 
-// One tile, one consumer warp: the dense part of this warp's threads and the items of the tile that
-// fall to this warp.  RING: the tile is in the ring slot `data` (logits in, gradients out, in place);
-// else (level without a tensor map) it is read from / written to global memory directly.
-template <bool RING>
-__device__ __forceinline__ void consume_tile(const ConsumerCtx& cc, const BTile& b, int k, float* data, TileHeader* hd,
-                                             float& qfl_part, float& dcls_part, uint32_t& tphase) {
+// One tile, one consumer warp: the dense part of this warp's quarter of the channels and the items
+// of the tile that fall to this warp, in place in the slot.  `j`: index of the tile in the team's sequence.
+__device__ __forceinline__ void consume_tile(const ConsumerCtx& cc, int j, float* data, TileHeader* hd, const float* tst,
+                                             float& qfl_part, float& dcls_part) {
   const Geo& g = cc.g;
   const Workspace& ws = cc.ws;
   const StudentArgs& A = cc.A;
-  const StudentMaps& maps = cc.maps;
-  float* tcol = cc.tcol;
-  const int tbox_off = cc.tbox_off, lane = cc.lane, cwarp = cc.cwarp, twarp = cc.twarp, col = cc.col, q = cc.q, oq = cc.oq, cq = cc.cq;
-  (void)cwarp;
-  const float inv_avg1 = cc.inv_avg1, avg2 = cc.avg2, inv_T = cc.inv_T;
+  const int lane = cc.lane, q = cc.q;
   const int C = g.C, ori = g.ori, cn = g.cn;
-  constexpr int bq = (kBoxCh + kBGroups - 1) / kBGroups;
-  const int HW = g.hw[b.l];
-    // Start the asynchronous fetch of item `it`'s teacher column into this warp's staging buffer: two
-    // TMA loads of [rows x 4] boxes -- the aligned group of four columns holding the anchor (the lines
-    // were left in L2 by the teacher pass).  Returns true when a fetch is in flight or nothing needs fetching.
-    auto fetch_teacher = [&](int item) {
-      const int icol = hd->item_col[item];
-      const unsigned irole = hd->role[icol];
-      if (!RING || !(irole & (kRoleCls | kRoleCand))) return true;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the buffer before the bulk write
-      __syncwarp();
-      if (lane == 0) {
-        const int hwI = b.hw0 + icol;
-        const uint32_t bytes = ((irole & kRoleCls) ? (uint32_t)ori * 16u : 0u) + ((irole & kRoleCand) ? (uint32_t)kBoxCh * 16u : 0u);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(cc.tbar)), "r"(bytes) : "memory");
-        // (a box must start 16 B aligned in global memory: fetch the aligned group of four columns around the anchor)
-        if (irole & kRoleCls) tma_load_2d(tcol, &maps.t_cls[b.l], hwI & ~3, b.n * ori, cc.tbar, cc.pol_keep);
-        if (irole & kRoleCand) tma_load_2d(tcol + tbox_off, &maps.t_box[b.l], hwI & ~3, b.n * kBoxCh, cc.tbar, cc.pol_keep);
-      }
-      return true;
-    };
-    const size_t ga0 = (size_t)b.n * g.A + g.start[b.l] + b.hw0;
-    // this warp's first item of the tile: request its teacher column now, use it after the dense part
-    const int n_items = (A.dev & 1) ? 0 : hd->n_items;
-    int it = (twarp - k / kBTeams) & (kBTeamWarps - 1);   // item i of the team's j-th tile goes to its warp (i + j) % 4
-    bool fetched = false;
-    if (it < n_items) fetched = fetch_teacher(it);
-    // Where the tile lives: in the ring slot (logits in, gradients out, in place), or -- levels without a
-    // tensor map -- straight in global memory.  Everything below addresses rows through (pointer, pitch).
-    constexpr bool in_ring = RING;
-    const size_t goff_c = (size_t)b.n * C * HW + b.hw0, goff_b = (size_t)b.n * kBoxCh * HW + b.hw0;
-    const float* cls_in = in_ring ? data : A.s_cls.p[b.l] + goff_c;
-    float* cls_out = in_ring ? data : A.g_cls.p[b.l] + goff_c;
-    const float* box_in = in_ring ? data + (size_t)C * kBT : A.s_box.p[b.l] + goff_b;
-    float* box_out = in_ring ? data + (size_t)C * kBT : A.g_box.p[b.l] + goff_b;
-    const int pitch = RING ? kBT : HW;   // a compile-time stride in the ring
-    // Dense part and sparse items touch disjoint addresses of the tile (the dense part skips the
-    // rows a special column's item owns), so nothing orders them inside a tile.
-    // ------------------------------------------------------------ dense part
-    {
-      const unsigned role = hd->role[col];
-      const float lw = (role & kRoleValid) ? 1.0f : 0.0f;                // label_weights, gfl_head.py:650-655,663
-      const float gs = lw * (upstream_of(A.upstream, acc_cls(b.l)) * g.w_cls * inv_avg1);
-      int label = -1;
-      float score = 0.f;
-      if (role & kRolePos) {   // rare
-        const int ri = hd->rec_of[hd->col_item[col]];
-        const PosRec* rec = ri != 255 ? &hd->rec[ri] : ws.pos_rec + ga0 + col;
-        label = rec->label;
-        score = rec->score;
-      }
-      float loss = 0.f;
-      const int c0 = q * cq, c1 = min(c0 + cq, cn);
-      if (in_ring || col < b.cnt) {   // (columns past a level's end: zero-filled in the ring, absent in global memory)
-        const float* nin = cls_in + (size_t)ori * pitch + col;
-        float* nout = cls_out + (size_t)ori * pitch + col;
-        const bool own_label = label >= c0 && label < c1;    // a positive's label channel lies in this thread's share
-        const float x_label = own_label ? nin[(size_t)label * pitch] : 0.f;
-#pragma unroll 4
-        for (int c = c0; c < ((A.dev & 2) ? c0 : c1); ++c) {   // QFL, every element as a negative first: branch free (:260-261,317-320)
-          const QflTerm tn = qfl_neg(nin[(size_t)c * pitch]);
-          loss = fmaf(lw, tn.loss, loss);
-          nout[(size_t)c * pitch] = gs * tn.grad;
-        }
-        if (own_label) {   // ... then the label channel of the (rare) positive is redone with its soft target
-          const QflTerm tp = qfl_pos(x_label, score), tn = qfl_neg(x_label);
-          loss += lw * (tp.loss - tn.loss);
-          nout[(size_t)label * pitch] = gs * tp.grad;
-        }
-        qfl_part += loss;
-        // structural zeros: the old-class rows of columns without a class-response row or a box
-        // candidate's weight to read, the box rows of columns that are neither positive nor candidate
-        if (!(role & (kRoleCls | kRoleCand))) {
-          const int o0 = q * oq, o1 = min(o0 + oq, ori);
-          for (int c = o0; c < o1; ++c) cls_out[(size_t)c * pitch + col] = 0.f;
-        }
-        if (!(role & (kRolePos | kRoleCand))) {
-          float* brow = box_out + (size_t)(q * bq) * pitch + col;
+  BTile b;
+  b.n = hd->n;
+  b.l = hd->l;
+  b.hw0 = hd->hw0;
+  b.cnt = hd->cnt;
+  const size_t ga0 = (size_t)b.n * g.A + g.start[b.l] + b.hw0;
+  // Dense part and sparse items touch disjoint addresses of the tile (the dense part skips the
+  // rows a special column's item owns), so nothing orders them inside a tile.
+  // ------------------------------------------------------------ dense part: lane = column
+  {
+    const unsigned role = hd->role[lane];
+    const float lw = (role & kRoleValid) ? 1.0f : 0.0f;                // label_weights, gfl_head.py:650-655,663
+    const float gs = lw * (upstream_of(A.upstream, acc_cls(b.l)) * g.w_cls * cc.inv_avg1);
+    int label = -1;
+    float score = 0.f;
+    if (role & kRolePos) {   // rare
+      const int ri = hd->rec_of[hd->col_item[lane]];
+      const PosRec* rec = ri != 255 ? &hd->rec[ri] : ws.pos_rec + ga0 + lane;
+      label = rec->label;
+      score = rec->score;
+    }
+    float* ncol = data + (size_t)ori * kBT + lane;       // the new-class rows of this column
+    const int c0 = q * cc.cq, c1 = min(c0 + cc.cq, cn);
+    const bool own_label = label >= c0 && label < c1;    // a positive's label channel lies in this thread's share
+    const float x_label = own_label ? ncol[label * kBT] : 0.f;
+    float loss = 0.f;
+    for (int c = c0; c < c1; c += kQflChunk) {   // QFL, every element as a negative first: branch free (:260-261,317-320)
+      float x[kQflChunk];
 #pragma unroll
-          for (int j = 0; j < bq; ++j)
-            if (q * bq + j < kBoxCh) brow[(size_t)j * pitch] = 0.f;
-        }
+      for (int i = 0; i < kQflChunk; ++i) x[i] = c + i < c1 ? ncol[(c + i) * kBT] : -INFINITY;   // (-inf: loss 0, gradient 0)
+#pragma unroll
+      for (int i = 0; i < kQflChunk; ++i) {
+        const QflTerm tn = qfl_neg(x[i]);
+        loss += tn.loss;
+        x[i] = gs * tn.grad;
       }
+#pragma unroll
+      for (int i = 0; i < kQflChunk; ++i)
+        if (c + i < c1) ncol[(c + i) * kBT] = x[i];
     }
-    // ------------------------------------------------------------ sparse items: one WARP per special column
-    // Item i of tile k goes to warp (i + k) % 16.  Lane layout for the box rows: lane = side * 8 + b,
-    // holding bins b, b + 8 (and 16 for b == 0) of its side; reductions over a side are 8-lane shuffles.
-    for (; it < n_items; it += kBTeamWarps) {
-      if (!fetched) fetched = fetch_teacher(it);   // a second item of this warp in the same tile (rare)
-      const int icol = hd->item_col[it];
-      const unsigned irole = hd->role[icol];
-      const bool is_cls = (irole & kRoleCls) != 0u, is_cand = (irole & kRoleCand) != 0u, is_pos = (irole & kRolePos) != 0u;
-      const bool staged = in_ring;   // teacher column in this warp's staging buffer, else straight from global
-      const int hwI = b.hw0 + icol;
-      const float* tc_g = A.t_cls.p[b.l] + (size_t)b.n * ori * HW + hwI;
-      const float* tb_g = A.t_box.p[b.l] + (size_t)b.n * kBoxCh * HW + hwI;
-      if (staged && (is_cls || is_cand)) {
-        mbar_wait_parity(cc.tbar, tphase);
-        tphase ^= 1u;
-      }
-      fetched = false;
+    if (own_label) {   // ... then the label channel of the (rare) positive is redone with its soft target
+      const QflTerm tp = qfl_pos(x_label, score), tn = qfl_neg(x_label);
+      loss += tp.loss - tn.loss;
+      ncol[label * kBT] = gs * tp.grad;
+    }
+    qfl_part = fmaf(lw, loss, qfl_part);
+    // structural zeros: the old-class rows of columns without a class-response row or a box
+    // candidate's weight to read, the box rows of columns that are neither positive nor candidate
+    if (!(role & (kRoleCls | kRoleCand))) {
+      const int o0 = q * cc.oq, o1 = min(o0 + cc.oq, ori);
+      float* ocol = data + lane;
+#pragma unroll 5
+      for (int c = o0; c < o1; ++c) ocol[c * kBT] = 0.f;
+    }
+    if (!(role & (kRolePos | kRoleCand))) {
+      float* bcol = data + (size_t)(C + q * kBoxPerWarp) * kBT + lane;
+#pragma unroll
+      for (int r = 0; r < kBoxPerWarp; ++r) bcol[r * kBT] = 0.f;
+    }
+  }
+  // ------------------------------------------------------------ sparse items: one WARP per special column
+  // Item i of the team's tile j goes to its warp (i + j) % 4.  Lane layout for the box rows: lane = side * 8 + b,
+  // holding bins b, b + 8 (and 16 for b == 0) of its side; reductions over a side are 8-lane shuffles.
+  const int n_items = hd->n_items;
+  for (int it = (q - j) & (kTeamWarps - 1); it < n_items; it += kTeamWarps) {
+    const int icol = hd->item_col[it];
+    const unsigned irole = hd->role[icol];
+    const bool is_cls = (irole & kRoleCls) != 0u, is_cand = (irole & kRoleCand) != 0u, is_pos = (irole & kRolePos) != 0u;
+    const int hwI = b.hw0 + icol;
+    // the teacher's column of this anchor: staged behind the header by the IO warp, or (more items in the tile
+    // than the staging area holds) straight from global memory
+    const bool staged = it < A.tstage_items;
+    const int HW = g.hw[b.l];
+    const float* tc = staged ? tst + (size_t)it * (ori + kBoxCh) : A.t_cls.p[b.l] + (size_t)b.n * ori * HW + hwI;
+    const float* tb = staged ? tc + ori : A.t_box.p[b.l] + (size_t)b.n * kBoxCh * HW + hwI;
+    const size_t ts = staged ? 1 : (size_t)HW;
+    float* box = data + (size_t)C * kBT;
+    if (is_cls || is_cand) {
       // old-class rows of the column: lane owns channels lane, lane + 32, ...
-      if (is_cls || is_cand) {
-        const float kc = (float)hd->cls_k * (float)ori;
-        const float scale_dc = upstream_of(A.upstream, acc_dcls(b.n)) * A.dlw * 2.0f / kc;
-        float mx_old = -INFINITY;
-        for (int c = lane; c < ori; c += 32) {
-          const float xs = cls_in[(size_t)c * pitch + icol];
-          mx_old = fmaxf(mx_old, xs);
-          float gr = 0.f;
-          if (is_cls) {   // class-response L2 (:181-186,324-332): g = 2 (x_s - x_t) / (K ori)
-            const float xt = staged ? tcol[c * 4 + (hwI & 3)] : __ldg(tc_g + (size_t)c * HW);
-            const float df = xs - xt;
-            dcls_part = fmaf(df, df, dcls_part);
-            gr = scale_dc * df;
-          }
-          cls_out[(size_t)c * pitch + icol] = gr;
+      const float kc = (float)hd->cls_k * (float)ori;
+      const float scale_dc = upstream_of(A.upstream, acc_dcls(b.n)) * A.dlw * 2.0f / kc;
+      float mx_old = -INFINITY;
+      for (int c = lane; c < ori; c += 32) {
+        const float xs = data[c * kBT + icol];
+        mx_old = fmaxf(mx_old, xs);
+        float gr = 0.f;
+        if (is_cls) {   // class-response L2 (:181-186,324-332): g = 2 (x_s - x_t) / (K ori)
+          const float df = xs - tc[(size_t)c * ts];
+          dcls_part = fmaf(df, df, dcls_part);
+          gr = scale_dc * df;
         }
-        if (is_pos || is_cand) {
-          const float w_kd = sigmoid_ref(warp_max(mx_old));                                      // :217-218
-          item_box_rows(g, ws, A, b, box_in, box_out, pitch, hd, hd->kd, staged ? tcol + tbox_off + (hwI & 3) : nullptr, tb_g, HW, it, icol, hwI, is_pos, is_cand,
-                        w_kd, avg2, inv_T, ga0, lane);
-        }
-      } else {
-        item_box_rows(g, ws, A, b, box_in, box_out, pitch, hd, hd->kd, nullptr, tb_g, HW, it, icol, hwI, is_pos, false, 0.f, avg2, inv_T,
-                      ga0, lane);
+        data[c * kBT + icol] = gr;
       }
+      if (is_pos || is_cand) {
+        const float w_kd = sigmoid_ref(warp_max(mx_old));                                      // :217-218
+        item_box_rows(g, ws, A, b, box, hd, hd->kd, tb, ts, it, icol, hwI, is_pos, is_cand, w_kd, cc.avg2, cc.inv_T, ga0, lane);
+      }
+    } else {
+      item_box_rows(g, ws, A, b, box, hd, hd->kd, tb, ts, it, icol, hwI, is_pos, false, 0.f, cc.avg2, cc.inv_T, ga0, lane);
     }
+  }
 }
 
 // ----------------------------------------------------------------------------- the kernel
@@ -414,194 +381,169 @@ __global__ void __launch_bounds__(kBThreads, 1)
 student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ StudentMaps maps) {
   if (A.skip_flag && *A.skip_flag == 0u) return;
   extern __shared__ __align__(128) unsigned char s_raw[];
-  __shared__ __align__(8) unsigned long long s_full[8], s_done[8], s_empty[8];
-  // loss sums of this CTA: [kLevels] QFL + [n_img] class-response squares, behind the ring (flushed once, at the end:
+  __shared__ __align__(8) unsigned long long s_full[kSlots], s_done[kSlots];
+  // loss sums of this CTA: [kLevels] QFL + [n_img] class-response squares, behind the slots (flushed once, at the end:
   // a global atomic in front of a tile's release-arrive would hold the slot for a full memory round trip)
-  double* s_loss = reinterpret_cast<double*>(s_raw + (size_t)A.stages * A.stage_bytes);
-  const int S = A.stages;
+  double* s_loss = reinterpret_cast<double*>(s_raw + (size_t)kSlots * A.slot_bytes);
   const int C = g.C, ori = g.ori, cn = g.cn;
   const int rows = C + kBoxCh;
-  // per consumer warp: a staging buffer for one anchor's teacher column ([ori + 68 rows][4 floats], filled by
-  // two TMA loads of [rows x 4] boxes whose first column is the anchor) and the barrier those loads complete on
-  const int tbox_off = ((ori * 16 + 127) & ~127) / 4;                  // floats: the box part starts 128 B aligned (TMA destination)
-  const int tcol_stride = tbox_off + ((kBoxCh * 16 + 127) & ~127) / 4;   // floats per warp
-  float* s_tcol = reinterpret_cast<float*>(s_raw + (size_t)A.stages * A.stage_bytes + (((size_t)(kLevels + g.n_img) * sizeof(double) + 127) & ~(size_t)127));
-  __shared__ __align__(8) unsigned long long s_tbar[kBConsumers / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&s_full[s], 1 + 32);   // the loader's lane 0 (after arming the TMA bytes) + its 32 lanes' cp.async batches
-      mbar_init(&s_done[s], kBTeamWarps);        // one arrival per warp of the consuming team
-      mbar_init(&s_empty[s], 1);
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&s_full[s], 1 + 32);        // the IO warp's lane 0 (after arming the TMA bytes) + its 32 lanes' cp.async batches
+      mbar_init(&s_done[s], kTeamWarps);    // one arrival per consumer warp of the team
     }
-    for (int w = 0; w < kBConsumers / 32; ++w) mbar_init(&s_tbar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < kLevels + g.n_img; i += kBThreads) s_loss[i] = 0.0;
   __syncthreads();
-  auto slot_data = [&](int s) { return reinterpret_cast<float*>(s_raw + (size_t)s * A.stage_bytes); };
-  auto slot_head = [&](int s) {
-    return reinterpret_cast<TileHeader*>(s_raw + (size_t)s * A.stage_bytes + (size_t)rows * kBT * sizeof(float));
-  };
-  if (warp >= kBConsumers / 32 && warp < kBConsumers / 32 + kBLoaders) {
-    // ================================================================== loader warps
-    // Everything a loader does per tile is asynchronous (TMA, cp.async) except the tile's roles,
-    // which it needs in registers to know what to fetch: those are requested one of ITS tiles ahead
-    // (three of the CTA's tiles), so their latency is off the path.
-    const int lw = warp - kBConsumers / 32;
-    unsigned long long pol_stream;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-    int gi[2] = {-1, -1};
-    unsigned fl[2] = {0u, 0u};
-    int kcls = 0;
-    auto fetch_roles = [&](int t) {
-      if (t >= A.total_tiles) return;
-      const BTile b = b_tile(g, A, t);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int col = lane + 32 * h;
-        const size_t ga = (size_t)b.n * g.A + g.start[b.l] + b.hw0 + col;
-        gi[h] = col < b.cnt ? A.gt_inds[ga] : -1;
-        fl[h] = col < b.cnt ? (unsigned)A.sel_flags[ga] : 0u;
-      }
-      kcls = A.cls_count[b.n];
-    };
-    fetch_roles(blockIdx.x + lw * gridDim.x);
-    for (int k = lw; ; k += kBLoaders) {
-      const int t = blockIdx.x + k * gridDim.x;
-      if (t >= A.total_tiles) break;
-      const int slot = k % S;
-      const uint32_t ph = (uint32_t)(k / S) & 1u;
-      const BTile b = b_tile(g, A, t);
-      const int HW = g.hw[b.l];
-      mbar_wait_parity(&s_empty[slot], ph ^ 1u);   // first pass over the ring: passes at once
-      TRACE(k, 0);
-      float* data = slot_data(slot);
-      TileHeader* hd = slot_head(slot);
-      if (A.use_tma[b.l]) {
-        if (lane == 0) {
-          mbar_expect_tx(&s_full[slot], (uint32_t)(rows * kBT * sizeof(float)));
-          tma_load_2d(data, &maps.s_cls[b.l], b.hw0, b.n * C, &s_full[slot], pol_stream);
-          tma_load_2d(data + (size_t)C * kBT, &maps.s_box[b.l], b.hw0, b.n * kBoxCh, &s_full[slot], pol_stream);
-        }
-      }
-      // (tiles of levels without a tensor map -- rows not 16 B aligned -- never enter the ring: the
-      // consumers read and write global memory directly; the slot only carries the header)
-      TRACE(k, 8);
-      // the roles requested one iteration ago
-      const int cgi[2] = {gi[0], gi[1]};
-      const unsigned cfl[2] = {fl[0], fl[1]};
-      const int ckcls = kcls;
-      unsigned role[2];
-      int item[2];
-      int n_pos = 0;
-      int n_items = 0;
-      if (cgi[0] == 12345678 && cfl[1] == 99u) n_items = 1;   // (touch the registers: wait for the loads)
-      TRACE(k, 9);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int col = lane + 32 * h;
-        role[h] = (cgi[h] >= 0 ? kRoleValid : 0u) | (cgi[h] > 0 ? kRolePos : 0u) | ((cfl[h] & 1u) ? kRoleCls : 0u) |
-                  ((cfl[h] & 2u) ? kRoleCand : 0u);
-        const bool special = (role[h] & kRoleSpecial) != 0u;
-        const unsigned m = __ballot_sync(0xffffffffu, special);
-        item[h] = special ? n_items + __popc(m & ((1u << lane) - 1u)) : 255;
-        n_items += __popc(m);
-        hd->role[col] = (unsigned char)role[h];
-        hd->col_item[col] = (unsigned char)item[h];
-        if (special) hd->item_col[item[h]] = (unsigned char)col;
-      }
-      // (second sweep, all lanes converged: the positives' staging indices)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int col = lane + 32 * h;
-        const bool pos = (role[h] & kRolePos) != 0u;
-        const unsigned mp = __ballot_sync(0xffffffffu, pos);
-        const int ri = n_pos + __popc(mp & ((1u << lane) - 1u));
-        n_pos += __popc(mp);
-        if (pos) {
-          hd->rec_of[item[h]] = (unsigned char)(ri < kStageItems ? ri : 255);
-          if (ri < kStageItems) {
-            const PosRec* src = ws.pos_rec + (size_t)b.n * g.A + g.start[b.l] + b.hw0 + col;
-            cp_async_16(reinterpret_cast<char*>(&hd->rec[ri]), reinterpret_cast<const char*>(src));
-            cp_async_16(reinterpret_cast<char*>(&hd->rec[ri]) + 16, reinterpret_cast<const char*>(src) + 16);
-          }
-        }
-      }
-      if (lane == 0) {
-        hd->n_items = n_items;
-        hd->cls_k = ckcls;
-      }
-      TRACE(k, 11);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_full[slot]);   // releases the header written by all lanes
-      cp_async_arrive(&s_full[slot]);   // every lane: its copies (possibly none) count towards the slot
-      TRACE(k, 1);
-      // Request the next tile's roles only now: a release-arrive waits for every load the thread has
-      // in flight, so loads issued earlier would hold back this tile's full barrier by their latency.
-      fetch_roles(blockIdx.x + (k + kBLoaders) * gridDim.x);
-    }
-    return;
-  }
 
-  if (warp == kBConsumers / 32 + kBLoaders) {
-    // ================================================================== store warp
+  if (warp >= kConsumerWarps) {
+    // ================================================================== IO warp of team `team`
+    const int team = warp - kConsumerWarps;
     unsigned long long pol_stream;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-    int k = 0;
-    for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, ++k) {
-      const int slot = k % S;
-      const uint32_t ph = (uint32_t)(k / S) & 1u;
-      const BTile b = b_tile(g, A, t);
-      mbar_wait_parity(&s_done[slot], ph);
-      TRACE(k, 4);
-      const float* data = slot_data(slot);
-      {   // the candidates' weighted KL values of this tile -> ws.kd_loss (read by the take-back pass)
-        const TileHeader* hd = slot_head(slot);
-        const int n_items = hd->n_items;
-        const size_t ga0 = (size_t)b.n * g.A + g.start[b.l] + b.hw0;
-        for (int it = lane; it < n_items; it += 32) {
-          const int icol = hd->item_col[it];
-          if (hd->role[icol] & kRoleCand) ws.kd_loss[ga0 + icol] = hd->kd[it];
-        }
+    // Tile jj of the team is done: write the slot to the gradient tensors; returns when the slot may be overwritten.
+    auto drain = [&](int jj) {
+      const int s = team * 2 + (jj & 1);
+      mbar_wait_parity(&s_done[s], (uint32_t)(jj >> 1) & 1u);
+      const unsigned char* base = s_raw + (size_t)s * A.slot_bytes;
+      const float* data = reinterpret_cast<const float*>(base);
+      const TileHeader* hd = reinterpret_cast<const TileHeader*>(base + A.hdr_off);
+      const int n = hd->n, l = hd->l, hw0 = hd->hw0, cnt = hd->cnt, n_items = hd->n_items;
+      const size_t ga0 = (size_t)n * g.A + g.start[l] + hw0;
+      // the candidates' weighted KL values of this tile -> ws.kd_loss (read by the take-back pass)
+      for (int it = lane; it < n_items; it += 32) {
+        const int icol = hd->item_col[it];
+        if (hd->role[icol] & kRoleCand) ws.kd_loss[ga0 + icol] = hd->kd[it];
       }
-      if (A.use_tma[b.l]) {
-        if (lane == 0 && !(A.dev & 4)) {
-          tma_store_2d(&maps.g_cls[b.l], b.hw0, b.n * C, data, pol_stream);
-          tma_store_2d(&maps.g_box[b.l], b.hw0, b.n * kBoxCh, data + (size_t)C * kBT, pol_stream);
+      if (A.use_tma[l]) {
+        if (lane == 0) {
+          tma_store_2d(&maps.g_cls[l], hw0, n * C, data, pol_stream);
+          tma_store_2d(&maps.g_box[l], hw0, n * kBoxCh, data + (size_t)C * kBT, pol_stream);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the engine has read the slot
         }
+      } else if (lane < cnt) {   // rows of this level are not 16 B aligned: plain stores, 128 B per row and warp
+        const int HW = g.hw[l];
+        float* gc = A.g_cls.p[l] + (size_t)n * C * HW + hw0 + lane;
+#pragma unroll 8
+        for (int r = 0; r < C; ++r) __stcs(gc + (size_t)r * HW, data[r * kBT + lane]);
+        float* gb = A.g_box.p[l] + (size_t)n * kBoxCh * HW + hw0 + lane;
+#pragma unroll 4
+        for (int r = 0; r < kBoxCh; ++r) __stcs(gb + (size_t)r * HW, data[(C + r) * kBT + lane]);
       }
       __syncwarp();
-      TRACE(k, 5);
-      // (relaxed: the slot's reads are complete -- consumed by the stores / the bulk group; nothing to publish)
-      if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&s_empty[slot])) : "memory");
+    };
+    int j = 0;
+    for (;; ++j) {
+      const int t = blockIdx.x + (team + kTeams * j) * gridDim.x;
+      if (t >= A.total_tiles) break;
+      const BTile b = b_tile(g, A, t);
+      const int HW = g.hw[b.l];
+      // the tile's roles: requested before the slot is drained, so their latency hides behind the store
+      const bool in = lane < b.cnt;
+      const size_t ga = (size_t)b.n * g.A + g.start[b.l] + b.hw0 + lane;
+      const int gi = in ? A.gt_inds[ga] : -1;
+      const unsigned fl = in ? (unsigned)A.sel_flags[ga] : 0u;
+      const int kcls = A.cls_count[b.n];
+      if (j >= 2) drain(j - 2);
+      const int s = team * 2 + (j & 1);
+      unsigned char* base = s_raw + (size_t)s * A.slot_bytes;
+      float* data = reinterpret_cast<float*>(base);
+      TileHeader* hd = reinterpret_cast<TileHeader*>(base + A.hdr_off);
+      float* tst = reinterpret_cast<float*>(base + A.tst_off);
+      unsigned long long* full = &s_full[s];
+      const bool tma = A.use_tma[b.l] != 0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this warp's generic reads of the slot (drain) before the bulk writes
+      if (tma) {
+        if (lane == 0) {
+          mbar_expect_tx(full, (uint32_t)(rows * kBT * sizeof(float)));
+          tma_load_2d(data, &maps.s_cls[b.l], b.hw0, b.n * C, full, pol_stream);
+          tma_load_2d(data + (size_t)C * kBT, &maps.s_box[b.l], b.hw0, b.n * kBoxCh, full, pol_stream);
+        }
+      } else {
+        // rows not 16 B aligned: 4-byte asynchronous copies, a warp-wide 128 B request per row; lanes past
+        // the level's end zero their column
+        const float* sc = A.s_cls.p[b.l] + (size_t)b.n * C * HW + b.hw0 + lane;
+        const float* sb = A.s_box.p[b.l] + (size_t)b.n * kBoxCh * HW + b.hw0 + lane;
+#pragma unroll 8
+        for (int r = 0; r < C; ++r) {
+          if (in) cp_async_4(data + r * kBT + lane, sc + (size_t)r * HW);
+          else data[r * kBT + lane] = 0.f;
+        }
+#pragma unroll 4
+        for (int r = 0; r < kBoxCh; ++r) {
+          if (in) cp_async_4(data + (C + r) * kBT + lane, sb + (size_t)r * HW);
+          else data[(C + r) * kBT + lane] = 0.f;
+        }
+      }
+      // header: roles, the list of special columns, the positives' records
+      const unsigned role = (gi >= 0 ? kRoleValid : 0u) | (gi > 0 ? kRolePos : 0u) | ((fl & 1u) ? kRoleCls : 0u) |
+                            ((fl & 2u) ? kRoleCand : 0u);
+      const bool special = (role & kRoleSpecial) != 0u;
+      const unsigned lt = (1u << lane) - 1u;
+      const unsigned m = __ballot_sync(0xffffffffu, special);
+      const int item = special ? __popc(m & lt) : 255;
+      hd->role[lane] = (unsigned char)role;
+      hd->col_item[lane] = (unsigned char)item;
+      if (special) hd->item_col[item] = (unsigned char)lane;
+      const bool pos = (role & kRolePos) != 0u;
+      const unsigned mp = __ballot_sync(0xffffffffu, pos);
+      if (pos) {
+        const int ri = __popc(mp & lt);
+        hd->rec_of[item] = (unsigned char)(ri < kStageItems ? ri : 255);
+        if (ri < kStageItems) {
+          const PosRec* src = ws.pos_rec + ga;
+          cp_async_16(reinterpret_cast<char*>(&hd->rec[ri]), reinterpret_cast<const char*>(src));
+          cp_async_16(reinterpret_cast<char*>(&hd->rec[ri]) + 16, reinterpret_cast<const char*>(src) + 16);
+        }
+      }
+      if (lane == 0) {
+        hd->n = b.n;
+        hd->l = b.l;
+        hd->hw0 = b.hw0;
+        hd->cnt = b.cnt;
+        hd->n_items = __popc(m);
+        hd->cls_k = kcls;
+        hd->tma = tma ? 1 : 0;
+      }
+      // the teacher's columns of the tile's first items (the lines were left in L2 by the teacher pass, or come from DRAM)
+      unsigned mm = m;
+      for (int it = 0; mm != 0u && it < A.tstage_items; ++it) {   // warp-uniform
+        const int icol = __ffs(mm) - 1;
+        mm &= mm - 1u;
+        const unsigned irole = __shfl_sync(0xffffffffu, role, icol);
+        float* dst = tst + (size_t)it * (ori + kBoxCh);
+        if (irole & kRoleCls) {
+          const float* src = A.t_cls.p[b.l] + (size_t)b.n * ori * HW + b.hw0 + icol;
+          for (int c = lane; c < ori; c += 32) cp_async_4(dst + c, src + (size_t)c * HW);
+        }
+        if (irole & kRoleCand) {
+          const float* src = A.t_box.p[b.l] + (size_t)b.n * kBoxCh * HW + b.hw0 + icol;
+          for (int r = lane; r < kBoxCh; r += 32) cp_async_4(dst + ori + r, src + (size_t)r * HW);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full);   // releases the header written by all lanes
+      cp_async_arrive(full);              // every lane: its copies (possibly none) count towards the slot
     }
+    if (j >= 2) drain(j - 2);
+    if (j >= 1) drain(j - 1);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     return;
   }
 
   // ==================================================================== consumers
-  // The consumer warps never synchronise with each other: inside a tile the dense part and the
-  // items own disjoint addresses, and a warp that is done with its share of a tile moves on to the
-  // next slot.  Loss sums travel in registers and are flushed (warp shuffle + one fp64 atomic) when
-  // the level / image of the CTA's tile sequence changes.
-  const int ctid = threadIdx.x;            // 0 .. kBConsumers - 1
-  const int cwarp = ctid >> 5;
-  const int team = cwarp / kBTeamWarps, twarp = cwarp % kBTeamWarps;
-  const int ttid = ctid - team * kBTeamThreads;   // thread in the team
-  const int col = ttid & (kBT - 1), q = ttid / kBT;
-  const int oq = (ori + kBGroups - 1) / kBGroups, cq = (cn + kBGroups - 1) / kBGroups;
-  constexpr int bq = (kBoxCh + kBGroups - 1) / kBGroups;
+  // The consumer warps of a team never synchronise with each other: inside a tile the dense part and
+  // the items own disjoint addresses, and a warp that is done with its share of a tile moves on to the
+  // team's next slot.  Loss sums travel in registers and are flushed (warp shuffle + one shared-memory
+  // fp64 atomic) when the level / image of the team's tile sequence changes.
+  const int team = warp / kTeamWarps, q = warp % kTeamWarps;
   const float inv_avg1 = 1.0f / (float)((double)A.avg[0] + (double)kEps32);   // losses/utils.py:60-61
   const float avg2 = fmaxf(A.avg[1], 1.0f);                                   // :407 clamp_(min=1)
-  const float inv_T = 1.0f / g.T;
-  unsigned long long pol_keep;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-  float* tcol = s_tcol + (size_t)cwarp * tcol_stride;   // this warp's teacher-column staging: [ori][4] | [68][4]
-  uint32_t tphase = 0;
-  const ConsumerCtx cc{g, ws, A, maps, tcol, &s_tbar[cwarp], pol_keep, tbox_off, lane, cwarp, twarp, col, q, oq, cq, inv_avg1, avg2, inv_T};
+  const ConsumerCtx cc{g, ws, A, lane, q, (ori + kTeamWarps - 1) / kTeamWarps, (cn + kTeamWarps - 1) / kTeamWarps,
+                       inv_avg1, avg2, 1.0f / g.T};
   int cur_img = -1, cur_lvl = -1;
   float dcls_part = 0.f;   // sum (x_s - x_t)^2 of the current image, this thread
   float qfl_part = 0.f;    // QFL loss sum of the current (image, level), this thread
@@ -614,34 +556,29 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
     qfl_part = 0.f;
     dcls_part = 0.f;
   };
-  for (int k = team;; k += kBTeams) {
-    const int t = blockIdx.x + k * gridDim.x;
+  for (int j = 0;; ++j) {
+    const int t = blockIdx.x + (team + kTeams * j) * gridDim.x;
     if (t >= A.total_tiles) break;
-    const int slot = k % S;
-    const uint32_t ph = (uint32_t)(k / S) & 1u;
-    const BTile b = b_tile(g, A, t);
-    float* data = slot_data(slot);
-    TileHeader* hd = slot_head(slot);
-    if (b.n != cur_img || b.l != cur_lvl) {   // warp-uniform
+    const int s = team * 2 + (j & 1);
+    unsigned char* base = s_raw + (size_t)s * A.slot_bytes;
+    float* data = reinterpret_cast<float*>(base);
+    TileHeader* hd = reinterpret_cast<TileHeader*>(base + A.hdr_off);
+    const float* tst = reinterpret_cast<const float*>(base + A.tst_off);
+    mbar_wait_parity(&s_full[s], (uint32_t)(j >> 1) & 1u);
+    const int n = hd->n, l = hd->l;
+    if (n != cur_img || l != cur_lvl) {   // warp-uniform
       flush();
-      cur_img = b.n;
-      cur_lvl = b.l;
+      cur_img = n;
+      cur_lvl = l;
     }
-    mbar_wait_parity(&s_full[slot], ph);
-    if (twarp == 0) TRACE(k, 2);
-    if (twarp == 3) TRACE(k, 6);
-    if (A.use_tma[b.l]) consume_tile<true>(cc, b, k, data, hd, qfl_part, dcls_part, tphase);
-    else consume_tile<false>(cc, b, k, data, hd, qfl_part, dcls_part, tphase);
-    if (twarp == 0) TRACE(k, 13);
+    consume_tile(cc, j, data, hd, tst, qfl_part, dcls_part);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> the TMA store
     __syncwarp();
-    if (lane == 0) mbar_arrive(&s_done[slot]);
-    if (twarp == 0) TRACE(k, 3);
-    if (twarp == 3) TRACE(k, 7);
+    if (lane == 0) mbar_arrive(&s_done[s]);
   }
   flush();
-  asm volatile("bar.sync 1, %0;" ::"n"(kBConsumers) : "memory");   // consumers only: every warp has flushed
-  for (int i = ctid; i < kLevels + g.n_img; i += kBConsumers)
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");   // consumers only: every warp has flushed
+  for (int i = threadIdx.x; i < kLevels + g.n_img; i += kConsumers)
     if (s_loss[i] != 0.0) atomicAdd(ws.loss_acc + (i < kLevels ? acc_cls(i) : acc_dcls(i - kLevels)), s_loss[i]);
 }
 
@@ -681,16 +618,6 @@ bool tma_encode_rows(void* map, const void* base, int hw, long long rows_total, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int g_dev_mask = -1, g_dev_stages = -1;
-static unsigned long long* g_trace = nullptr;   // TEMPORARY tuning hooks (erd_student_dev)
-
-static int env_int(const char* name, int dflt, int lo, int hi) {
-  const char* e = getenv(name);
-  if (!e) return dflt;
-  const int v = atoi(e);
-  return v < lo || v > hi ? dflt : v;
-}
-
 cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st) {
   StudentArgs A;
   A.t_cls = a.t_cls;
@@ -714,63 +641,53 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
   A.lvl_tile_start[kLevels] = tiles;
   A.tiles_per_img = tiles;
   A.total_tiles = tiles * g.n_img;
+  // slot layout: [rows x 32 logits][TileHeader][tstage_items x (ori + 68) teacher logits]; eight slots and the
+  // loss sums must fit the 227 KB a CTA may have -- the teacher staging takes what is left, up to kStageItems
   const int rows = g.C + kBoxCh;
-  A.stage_bytes = (int)(((size_t)rows * kBT * sizeof(float) + sizeof(TileHeader) + 127) & ~(size_t)127);
-  // (the ring must be at least as deep as there are loader warps and consumer teams: nobody may get
-  // more than one phase ahead of a slot's barriers)
-  int want_stages = g_dev_stages >= kBTeams ? g_dev_stages : env_int("ERD_STUDENT_STAGES", 5, kBTeams, 8);
-  const size_t tail_bytes = (((size_t)(kLevels + g.n_img) * sizeof(double) + 127) & ~(size_t)127) +
-                            (size_t)(kBConsumers / 32) * (((g.ori * 16 + 127) & ~127) + ((kBoxCh * 16 + 127) & ~127));   // loss sums + teacher-column staging
-  const int max_smem = 227 * 1024 - 1024 - (int)tail_bytes;
-  int S = max_smem / A.stage_bytes;
-  if (S > want_stages) S = want_stages;
-  if (S > 8) S = 8;
-  // A team only waits on the full barriers of its own tiles, so a slot must always be consumed by the
-  // same team (S a multiple of the team count): a team that waited on a slot whose previous tile belongs
-  // to another team could run a whole phase ahead of it, and a parity wait cannot tell phase j+1 from j-1.
-  S -= S % kBTeams;
-  if (S < kBTeams) return cudaErrorInvalidValue;   // num_classes too large for the smallest ring
-  A.stages = S;
-  A.trace = g_trace;
-  A.dev = g_dev_mask >= 0 ? g_dev_mask : env_int("ERD_STUDENT_DEV", 0, 0, 255);
+  const size_t data_bytes = (size_t)rows * kBT * sizeof(float);   // a multiple of 128
+  const size_t tcol_bytes = (size_t)(g.ori + kBoxCh) * sizeof(float);
+  const size_t tail_bytes = ((size_t)(kLevels + g.n_img) * sizeof(double) + 127) & ~(size_t)127;
+  const size_t budget = (size_t)227 * 1024 - 1024 - tail_bytes;
+  const size_t fixed = data_bytes + sizeof(TileHeader);
+  if (fixed * kSlots > budget) return cudaErrorInvalidValue;   // num_classes too large for this tiling
+  size_t stage = ((budget / kSlots) & ~(size_t)127) - fixed;
+  int tstage = (int)(stage / tcol_bytes);
+  if (tstage > kStageItems) tstage = kStageItems;
+  A.tstage_items = tstage;
+  A.hdr_off = (int)data_bytes;
+  A.tst_off = (int)fixed;
+  A.slot_bytes = (int)((fixed + (size_t)tstage * tcol_bytes + 127) & ~(size_t)127);
   // tensor maps, cached on the pointers they were built for (the training loop reuses its buffers)
   struct MapCache {
-    const void* key[6 * kLevels];
-    int hw[kLevels], n_img, C, ori;
+    const void* key[4 * kLevels];
+    int hw[kLevels], n_img, C;
     int use_tma[kLevels];
     StudentMaps maps;
     bool valid = false;
   };
   static thread_local MapCache cache;
-  const void* key[6 * kLevels];
+  const void* key[4 * kLevels];
   for (int l = 0; l < kLevels; ++l) {
     key[l] = a.s_cls.p[l];
     key[kLevels + l] = a.s_box.p[l];
     key[2 * kLevels + l] = a.g_cls.p[l];
     key[3 * kLevels + l] = a.g_box.p[l];
-    key[4 * kLevels + l] = a.t_cls.p[l];
-    key[5 * kLevels + l] = a.t_box.p[l];
   }
-  bool hit = cache.valid && cache.n_img == g.n_img && cache.C == g.C && cache.ori == g.ori;
-  for (int i = 0; hit && i < 6 * kLevels; ++i) hit = cache.key[i] == key[i];
+  bool hit = cache.valid && cache.n_img == g.n_img && cache.C == g.C;
+  for (int i = 0; hit && i < 4 * kLevels; ++i) hit = cache.key[i] == key[i];
   for (int l = 0; hit && l < kLevels; ++l) hit = cache.hw[l] == g.hw[l];
   if (!hit) {
-    static int allow_tma = env_int("ERD_STUDENT_TMA", 1, 0, 1);
     for (int l = 0; l < kLevels; ++l) {
       const long long rc = (long long)g.n_img * g.C, rb = (long long)g.n_img * kBoxCh;
-      cache.use_tma[l] = allow_tma && g.vec[l] &&
-                         tma_encode_rows(&cache.maps.s_cls[l], a.s_cls.p[l], g.hw[l], rc, g.C, kBT) &&
+      cache.use_tma[l] = g.vec[l] && tma_encode_rows(&cache.maps.s_cls[l], a.s_cls.p[l], g.hw[l], rc, g.C, kBT) &&
                          tma_encode_rows(&cache.maps.s_box[l], a.s_box.p[l], g.hw[l], rb, kBoxCh, kBT) &&
                          tma_encode_rows(&cache.maps.g_cls[l], a.g_cls.p[l], g.hw[l], rc, g.C, kBT) &&
-                         tma_encode_rows(&cache.maps.g_box[l], a.g_box.p[l], g.hw[l], rb, kBoxCh, kBT) &&
-                         tma_encode_rows(&cache.maps.t_cls[l], a.t_cls.p[l], g.hw[l], (long long)g.n_img * g.ori, g.ori, 4) &&
-                         tma_encode_rows(&cache.maps.t_box[l], a.t_box.p[l], g.hw[l], rb, kBoxCh, 4);
+                         tma_encode_rows(&cache.maps.g_box[l], a.g_box.p[l], g.hw[l], rb, kBoxCh, kBT);
       cache.hw[l] = g.hw[l];
     }
-    for (int i = 0; i < 6 * kLevels; ++i) cache.key[i] = key[i];
+    for (int i = 0; i < 4 * kLevels; ++i) cache.key[i] = key[i];
     cache.n_img = g.n_img;
     cache.C = g.C;
-    cache.ori = g.ori;
     cache.valid = true;
   }
   for (int l = 0; l < kLevels; ++l) A.use_tma[l] = cache.use_tma[l];
@@ -781,7 +698,7 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const size_t smem = (size_t)S * A.stage_bytes + tail_bytes;
+  const size_t smem = (size_t)kSlots * A.slot_bytes + tail_bytes;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(student_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -789,18 +706,7 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
   }
   const int grid = A.total_tiles < sms ? A.total_tiles : sms;
   ERD_LAUNCH(kKStudent, st, (student_pass_kernel<<<grid, kBThreads, smem, st>>>(g, ws, A, cache.maps)));
-  cudaError_t le = cudaGetLastError();
-  if (le != cudaSuccess)
-    fprintf(stderr, "student_pass launch failed: %s grid=%d threads=%d smem=%zu S=%d stage=%d tail=%zu params=%zu\n", cudaGetErrorString(le), grid,
-            kBThreads, smem, S, A.stage_bytes, tail_bytes, sizeof(Geo) + sizeof(Workspace) + sizeof(StudentArgs) + sizeof(StudentMaps));
-  return le;
+  return cudaGetLastError();
 }
 
 }  // namespace erd
-
-extern "C" void erd_student_trace(unsigned long long* p) { erd::g_trace = p; }
-
-extern "C" void erd_student_dev(int mask, int stages) {
-  erd::g_dev_mask = mask;
-  erd::g_dev_stages = stages;
-}

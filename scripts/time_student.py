@@ -6,19 +6,17 @@ from erd_b200.ops import ErdPath
 from erd_b200.synth import make_batch
 n = int(os.environ.get('IMGS', 16))
 hw = tuple(int(x) for x in os.environ.get('HW', '800x1333').split('x'))
-b = make_batch(n, hw, ori=40, seed=1234).to('cuda')
+b = make_batch(n, hw, ori=int(os.environ.get('ORI', 40)), seed=1234, mode=os.environ.get('MODE', 'gaussian')).to('cuda')
 print('image', hw, 'levels', b.shapes, 'anchors', b.anchors_per_image)
 path = ErdPath(); lib = N.load()
-p = path.plan(b.s_cls, 80, 40, 16); p.set_targets(b.gt_bboxes, b.gt_labels, b.pad_shapes)
+p = path.plan(b.s_cls, 80, b.ori, 16); p.set_targets(b.gt_bboxes, b.gt_labels, b.pad_shapes)
 g_cls = [torch.empty_like(t) for t in b.s_cls]; g_box = [torch.empty_like(t) for t in b.s_box]
 losses = torch.empty(p.num_losses, device='cuda')
 def step():
     path.prepare(p, b.t_cls, b.t_box, b.s_cls, b.s_box); path.reduce_avg(p)
     path.loss_fwd_bwd(p, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls, g_box, losses, 1.0)
 nk = lib.erd_profile_num_kernels(); names = [lib.erd_profile_kernel_name(i).decode() for i in range(nk)]
-variants = [tuple(int(x) for x in v.split(':')) for v in os.environ.get('VARIANTS', '0:5').split(',')]
-for mask, stages in variants:
-    lib.erd_student_dev(mask, stages)
+for rep in range(int(os.environ.get('REPS', 1))):
     for _ in range(5): step()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
@@ -37,4 +35,4 @@ for mask, stages in variants:
     torch.cuda.synchronize()
     lib.erd_profile_enable(0)
     tot, cnt = (C.c_float * nk)(), (C.c_int * nk)(); lib.erd_profile_collect(tot, cnt)
-    print(f'dev={mask} stages={stages} graph_step_ms={graph_ms:.4f}', {names[i]: round(1e3 * tot[i] / cnt[i], 1) for i in range(nk) if cnt[i]}, flush=True)
+    print(f'graph_step_ms={graph_ms:.4f}', {names[i]: round(1e3 * tot[i] / cnt[i], 1) for i in range(nk) if cnt[i]}, flush=True)
