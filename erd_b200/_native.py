@@ -11,7 +11,7 @@ import os
 from . import build as _build
 
 MAX_LEVELS = 5
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class ErdShape(C.Structure):
@@ -45,6 +45,7 @@ SIGNATURES = {
     'erd_last_error': [],
     'erd_sizes': [_SH, C.POINTER(ErdSizes)],
     'erd_workspace_init': [_SH, _P, _P],
+    'erd_workspace_field': [_SH, _P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_size_t)],
     'erd_create': [C.POINTER(_P)],
     'erd_destroy': [_P],
     'erd_ers_select': [_SH, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -81,6 +81,11 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->t_dist = (float4*)take(NA * 16);
   const size_t tiles32 = (size_t)g.A / 32 + kLevels;   // >= sum_l ceil(hw_l / 32)
   ws->ers_part = (double*)take((size_t)g.n_img * tiles32 * 4 * 8);
+  ws->t_stash = (float*)take((size_t)g.n_img * kStashRows * stash_pitch(g.ori) * 4);
+  ws->t_slot = (unsigned short*)take(NA * 2);
+  ws->pthr = (float*)take((size_t)g.n_img * 2 * 4);
+  ws->samp_acc = (double*)take((size_t)g.n_img * 5 * 8);
+  ws->samp_ticket = (unsigned int*)take((size_t)g.n_img * 4);
   ws->atss_key = (unsigned long long*)take(NA * 8);
   ws->pos_list = (int2*)take(NA * 8);
   ws->pos_counter = (int*)take((size_t)g.n_img * 4);
@@ -166,6 +171,22 @@ int erd_workspace_init(const ErdShape* shape, void* wsp, void* stream) {
   carve(g, wsp, &ws);
   cudaError_t e = cudaMemsetAsync(wsp, 0, ws.bytes, (cudaStream_t)stream);
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_workspace_init");
+}
+
+int erd_workspace_field(const ErdShape* shape, void* wsp, const char* name, void** ptr, size_t* bytes) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (!wsp || !name || !ptr || !bytes) return fail(ERD_ERR_NULL, "erd_workspace_field: NULL argument");
+  Workspace ws;
+  carve(g, wsp, &ws);
+  const size_t NA = (size_t)g.n_img * g.A;
+  if (!strcmp(name, "t_slot")) { *ptr = ws.t_slot; *bytes = NA * 2; }
+  else if (!strcmp(name, "pthr")) { *ptr = ws.pthr; *bytes = (size_t)g.n_img * 8; }
+  else if (!strcmp(name, "t_m")) { *ptr = ws.t_m; *bytes = NA * 4; }
+  else if (!strcmp(name, "t_u")) { *ptr = ws.t_u; *bytes = NA * 4; }
+  else return fail(ERD_ERR_BAD_SHAPE, "erd_workspace_field: unknown field");
+  return ERD_OK;
 }
 
 int erd_create(ErdContext** ctx) {

@@ -53,6 +53,15 @@ struct Workspace {
   float* t_u;                     // [N][A] teacher max raw box logit
   float4* t_dist;                 // [N][A] teacher softmax-integral distances (l,t,r,b), bin units
   double* ers_part;               // [N][tiles of 32 anchors][4] per-tile sums: m, m^2, u, u^2
+  // The stash: the teacher's logit column [ori + 68, padded to 4] of every anchor that clears the
+  // PROVISIONAL thresholds (estimated from a sample of the image before the streaming pass), written by
+  // the teacher pass while the tile is in shared memory, so that the student pass does not gather those
+  // columns from the NCHW tensors again (64 B of DRAM per 4 B used).  Region [n][cta][kStashPerCta].
+  float* t_stash;
+  unsigned short* t_slot;         // [N][A] stash row of the anchor + 1, 0: not stashed (read the tensors)
+  float* pthr;                    // [N][2] provisional thresholds (class response, box)
+  double* samp_acc;               // [N][5] sample sums m, m^2, u, u^2, count (zero between steps)
+  unsigned int* samp_ticket;      // [1] warps of the teacher pass that have finished the sampling phase (zero between steps)
   unsigned long long* atss_key;   // [N][A] packed (iou bits << 32 | ~gt) argmax table
   int2* pos_list;                 // [N][A] (anchor, global GT row) of the assigned anchors (unordered)
   int* pos_counter;               // [N] running length of pos_list (zero between steps)
@@ -71,6 +80,11 @@ struct Workspace {
   double* loss_acc;               // [3L + 2N]
   size_t bytes;
 };
+
+constexpr int kStashCtas = 160;        // the teacher pass runs on at most this many CTAs (one per SM)
+constexpr int kStashPerCta = 64;      // stash rows per (image, CTA); an anchor that does not fit is simply not stashed
+constexpr int kStashRows = kStashCtas * kStashPerCta;   // per image; < 65535 (t_slot is 16 bit)
+inline __host__ __device__ int stash_pitch(int ori) { return (ori + kBoxCh + 3) & ~3; }   // floats per stash row (16 B multiple)
 
 inline __host__ __device__ int nms_words(int sel_cap) { return (sel_cap + 63) / 64; }
 inline __host__ __device__ int nms_nz_words(int sel_cap) { return (nms_words(sel_cap) + 63) / 64; }

@@ -66,6 +66,18 @@ __global__ void __launch_bounds__(kFlagThreads) ers_flags_kernel(Geo g, Workspac
     __syncthreads();
   }
   const float thr_c = s_thr[0], thr_b = s_thr[1];
+  if (blockIdx.x == 0) {   // the teacher pass's sampling sums: publish its provisional thresholds (diagnostics), clean up
+    if (threadIdx.x < 2) {
+      const double* a = ws.samp_acc + n * 5;
+      const double cnt = a[4], s1 = a[threadIdx.x * 2], s2 = a[threadIdx.x * 2 + 1];
+      double var = (s2 - s1 * s1 / cnt) / (cnt - 1.0);
+      if (!(var > 0.0)) var = 0.0;
+      ws.pthr[n * 2 + threadIdx.x] = (float)(s1 / cnt + 1.7 * sqrt(var));
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) ws.samp_acc[n * 5 + threadIdx.x] = 0.0;
+    if (n == 0 && threadIdx.x == 0) *ws.samp_ticket = 0u;
+  }
   const int a0 = (blockIdx.x * kFlagThreads + threadIdx.x) * kFlagPer;
   const float* m = ws.t_m + (size_t)n * g.A;
   const float* u = ws.t_u + (size_t)n * g.A;

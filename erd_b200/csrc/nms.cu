@@ -12,6 +12,8 @@
 // off the critical path -- the ordering of the survivors by score that batched_nms returns.
 // Nothing before the resolve pass needs the boxes sorted: "i is visited before j" is evaluated
 // per pair as (score_i > score_j) or (equal scores and i earlier in the list).
+#include <cstdlib>
+
 #include "erd_common.cuh"
 
 namespace erd {
@@ -367,8 +369,16 @@ cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_ind
     cudaError_t e = cudaEventRecord(prepped, st);
     if (e != cudaSuccess) return e;
   }
+  // The chain runs beside the student pass on the few SMs that pass leaves free, so the grid is sized for
+  // those: each CTA loops over the image's tiles (K = 500 candidates are 36 tiles), and a launch of
+  // thousands of CTAs that mostly exit at once would queue behind each other there.
+  static const int mask_ctas = [] {
+    const char* e = getenv("ERD_NMS_MASK_CTAS");
+    const int v = e ? atoi(e) : 32;
+    return v < 1 ? 1 : v;
+  }();
   ERD_LAUNCH(kKNmsMask, st,
-             (nms_mask_kernel<<<dim3(256, g.n_img), kMaskThreads, 0, st>>>(g, ws, box_count, iou_thr)));
+             (nms_mask_kernel<<<dim3(mask_ctas, g.n_img), kMaskThreads, 0, st>>>(g, ws, box_count, iou_thr)));
   const size_t res_smem = sizeof(unsigned long long) * 4 * (size_t)nms_words(g.sel_cap);
   ERD_LAUNCH(kKNmsScan, st,
              (nms_resolve_kernel<<<g.n_img, kResThreads, res_smem, st>>>(g, ws, box_inds, box_count, keep,

@@ -42,6 +42,7 @@ constexpr int kConsumers = 32 * kConsumerWarps;
 constexpr int kBThreads = kConsumers + 32 * kTeams;       // + one IO warp per team
 constexpr int kSlots = 2 * kTeams;                        // two slots per team
 constexpr int kStageItems = 12;                           // special columns per tile whose records / teacher columns are staged in the slot
+constexpr int kStudentFreeSms = 24;                       // SMs left to the kernels that run beside this pass
 constexpr int kQflChunk = 5;                              // QFL elements a thread loads ahead of the arithmetic
 static_assert(kBoxCh % kTeamWarps == 0, "box rows are split evenly over the team's warps");
 constexpr int kBoxPerWarp = kBoxCh / kTeamWarps;
@@ -62,6 +63,8 @@ struct __align__(32) TileHeader {
   unsigned char rec_of[kBT];        // item -> index into rec[], 255: not staged
 };
 
+static_assert(sizeof(TileHeader) % 16 == 0, "the teacher staging behind the header is the target of 16-byte bulk copies");
+
 struct StudentArgs {
   Ptr5 t_cls, t_box;
   MPtr5 g_cls, g_box;        // used by the tiles of levels without a tensor map
@@ -74,8 +77,9 @@ struct StudentArgs {
   const unsigned int* skip_flag;
   float dlw;
   int tiles_per_img, total_tiles;
-  int slot_bytes, hdr_off, tst_off;  // slot layout: [rows x 32 logits][TileHeader][tstage_items x (ori + 68) teacher logits]
+  int slot_bytes, hdr_off, tst_off;  // slot layout: [rows x 32 logits][TileHeader][tstage_items x stash_pitch(ori) teacher logits]
   int tstage_items;                  // items per tile whose teacher column is staged (more: read from global)
+  int tcol_pitch;                    // floats per staged teacher column == per stash row (a multiple of 4)
   int lvl_tile_start[kLevels + 1];   // prefix of ceil(hw / kBT)
   int use_tma[kLevels];
 };
@@ -134,6 +138,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
       ::"r"(smem_addr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_addr(bar)), "l"(policy) : "memory");
+}
+// 1-D bulk copy global -> shared, completing on `bar` (addresses and size multiples of 16 B)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src,
                                              unsigned long long policy) {
@@ -346,7 +355,7 @@ __device__ __forceinline__ void consume_tile(const ConsumerCtx& cc, int j, float
     // than the staging area holds) straight from global memory
     const bool staged = it < A.tstage_items;
     const int HW = g.hw[b.l];
-    const float* tc = staged ? tst + (size_t)it * (ori + kBoxCh) : A.t_cls.p[b.l] + (size_t)b.n * ori * HW + hwI;
+    const float* tc = staged ? tst + (size_t)it * A.tcol_pitch : A.t_cls.p[b.l] + (size_t)b.n * ori * HW + hwI;
     const float* tb = staged ? tc + ori : A.t_box.p[b.l] + (size_t)b.n * kBoxCh * HW + hwI;
     const size_t ts = staged ? 1 : (size_t)HW;
     float* box = data + (size_t)C * kBT;
@@ -446,6 +455,7 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
       const size_t ga = (size_t)b.n * g.A + g.start[b.l] + b.hw0 + lane;
       const int gi = in ? A.gt_inds[ga] : -1;
       const unsigned fl = in ? (unsigned)A.sel_flags[ga] : 0u;
+      const unsigned srow = in ? (unsigned)ws.t_slot[ga] : 0u;   // the anchor's stash row + 1 (teacher pass), 0: none
       const int kcls = A.cls_count[b.n];
       if (j >= 2) drain(j - 2);
       const int s = team * 2 + (j & 1);
@@ -508,13 +518,25 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
         hd->cls_k = kcls;
         hd->tma = tma ? 1 : 0;
       }
-      // the teacher's columns of the tile's first items (the lines were left in L2 by the teacher pass, or come from DRAM)
+      // The teacher's columns of the tile's first items: one bulk copy of the anchor's stash row (written by
+      // the teacher pass while it had the tile in shared memory); an anchor the provisional thresholds missed
+      // is gathered from the NCHW tensors, 4 bytes per row.
       unsigned mm = m;
       for (int it = 0; mm != 0u && it < A.tstage_items; ++it) {   // warp-uniform
         const int icol = __ffs(mm) - 1;
         mm &= mm - 1u;
         const unsigned irole = __shfl_sync(0xffffffffu, role, icol);
-        float* dst = tst + (size_t)it * (ori + kBoxCh);
+        const unsigned irow = __shfl_sync(0xffffffffu, srow, icol);
+        float* dst = tst + (size_t)it * A.tcol_pitch;
+        if (!(irole & (kRoleCls | kRoleCand))) continue;
+        if (irow != 0u) {
+          if (lane == 0) {
+            const uint32_t bytes = (uint32_t)A.tcol_pitch * (uint32_t)sizeof(float);
+            mbar_expect_tx(full, bytes);
+            bulk_load(dst, ws.t_stash + ((size_t)b.n * kStashRows + (irow - 1u)) * A.tcol_pitch, bytes, full);
+          }
+          continue;
+        }
         if (irole & kRoleCls) {
           const float* src = A.t_cls.p[b.l] + (size_t)b.n * ori * HW + b.hw0 + icol;
           for (int c = lane; c < ori; c += 32) cp_async_4(dst + c, src + (size_t)c * HW);
@@ -641,11 +663,11 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
   A.lvl_tile_start[kLevels] = tiles;
   A.tiles_per_img = tiles;
   A.total_tiles = tiles * g.n_img;
-  // slot layout: [rows x 32 logits][TileHeader][tstage_items x (ori + 68) teacher logits]; eight slots and the
+  // slot layout: [rows x 32 logits][TileHeader][tstage_items x stash_pitch(ori) teacher logits]; eight slots and the
   // loss sums must fit the 227 KB a CTA may have -- the teacher staging takes what is left, up to kStageItems
   const int rows = g.C + kBoxCh;
   const size_t data_bytes = (size_t)rows * kBT * sizeof(float);   // a multiple of 128
-  const size_t tcol_bytes = (size_t)(g.ori + kBoxCh) * sizeof(float);
+  const size_t tcol_bytes = (size_t)stash_pitch(g.ori) * sizeof(float);   // a multiple of 16
   const size_t tail_bytes = ((size_t)(kLevels + g.n_img) * sizeof(double) + 127) & ~(size_t)127;
   const size_t budget = (size_t)227 * 1024 - 1024 - tail_bytes;
   const size_t fixed = data_bytes + sizeof(TileHeader);
@@ -654,6 +676,7 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
   int tstage = (int)(stage / tcol_bytes);
   if (tstage > kStageItems) tstage = kStageItems;
   A.tstage_items = tstage;
+  A.tcol_pitch = stash_pitch(g.ori);
   A.hdr_off = (int)data_bytes;
   A.tst_off = (int)fixed;
   A.slot_bytes = (int)((fixed + (size_t)tstage * tcol_bytes + 127) & ~(size_t)127);
@@ -704,7 +727,17 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
     if (e != cudaSuccess) return e;
     smem_set = smem;
   }
-  const int grid = A.total_tiles < sms ? A.total_tiles : sms;
+  // One CTA of this kernel fills an SM (registers, shared memory), so nothing else can share it.  The teacher-
+  // side NMS chain runs BESIDE this pass and is all latency: it gets a few SMs of its own, or it would only
+  // start when the first CTAs of this pass exit (measured: the whole chain then lands behind the pass).
+  static const int free_sms = [] {
+    const char* e = getenv("ERD_STUDENT_FREE_SMS");
+    const int v = e ? atoi(e) : kStudentFreeSms;
+    return v < 0 ? 0 : v;
+  }();
+  int grid = sms - free_sms;
+  if (grid < 1) grid = 1;
+  if (grid > A.total_tiles) grid = A.total_tiles;
   ERD_LAUNCH(kKStudent, st, (student_pass_kernel<<<grid, kBThreads, smem, st>>>(g, ws, A, cache.maps)));
   return cudaGetLastError();
 }

@@ -15,6 +15,17 @@
 // next.  Nothing synchronises the warps.  The loads carry an L2 evict_last hint: the student pass
 // comes back for the rows of the selected anchors, and 126 MB of L2 hold most of the teacher.
 // Levels whose rows are not 16-byte aligned come in as 4-byte cp.async copies.
+//
+// The stash.  The student pass needs the teacher's whole logit column of every ERS anchor (class-
+// response L2, box-distribution KL), which in NCHW costs a 64-byte DRAM access per 4-byte element.
+// The scan has that column in shared memory, but the thresholds that decide the selection only exist
+// once the whole image has been scanned.  So the kernel opens with a sampling phase: the warps first scan
+// every 16th tile of each image for m and u only, add up fp64 sums with atomics and the CTAs meet at a grid-wide
+// ticket (the grid is at most one CTA per SM, so all CTAs are resident or become so without depending on
+// anything this kernel produces); mean + 1.7 std of the sample are the PROVISIONAL thresholds, and the
+// scan copies the column of every anchor that clears them to a compact stash row.  The estimate only
+// decides what is stashed, never what is selected: an ERS anchor that was not stashed is read from
+// the tensors by the student pass as before, so results do not depend on the estimate.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -34,9 +45,8 @@ struct TeacherArgs {
   int tiles_per_img, total_tiles, stages, stage_bytes;
   int lvl_tile_start[kLevels + 1];   // prefix of ceil(hw / kAT)
   int use_tma[kLevels];
-  int l2_keep;
-  unsigned long long* trace;   // TEMPORARY: timestamps of one warp of CTA 0, [tile][8]
-  int trace_warp;
+  int stash_pitch;                   // floats per stash row
+  int sample_stride, samples_per_img;   // the sampling phase takes tiles 0, stride, 2 stride, ... of every image
 };
 
 struct __align__(64) TeacherMaps {
@@ -59,13 +69,6 @@ __device__ __forceinline__ ATile a_tile(const Geo& g, const TeacherArgs& A, int 
   return b;
 }
 
-__device__ __forceinline__ unsigned long long t_gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define TTRACE(j, id) do { if (A.trace && blockIdx.x == 0 && warp == (A.trace_warp) && lane == 0) A.trace[(size_t)(j) * 8 + (id)] = t_gtime(); } while (0)
-
 __device__ __forceinline__ uint32_t t_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void t_wait(unsigned long long* bar, uint32_t parity) {
   uint32_t done = 0;
@@ -74,10 +77,14 @@ __device__ __forceinline__ void t_wait(unsigned long long* bar, uint32_t parity)
                  : "=r"(done) : "r"(t_smem(bar)), "r"(parity) : "memory");
 }
 
+constexpr int kTeacherFreeSms = 8;      // SMs left to the kernels that run beside this pass
+constexpr float kSampleSigmas = 1.7f;   // provisional threshold = sample mean + this many sample std (the selection: mean + 2 std)
+
 __global__ void __launch_bounds__(kAMaxThreads, 1)
 teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ TeacherMaps maps) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ __align__(8) unsigned long long s_full[kAMaxWarps];
+  int* s_stash_cnt = reinterpret_cast<int*>(s_raw + (size_t)A.stages * A.stage_bytes);   // [n_img] stash rows this CTA has used
   // Every warp is its own pipeline over the tiles k = warp, warp + W, ... of the CTA's sequence, with
   // its own shared-memory slot: request the tile, scan it, publish its sums, wait for the image's
   // thresholds, extract the selected rows from the slot.  Warps only meet at the per-image flag.
@@ -91,6 +98,7 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
     for (int s = 0; s < W; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_smem(&s_full[s])), "r"(1 + 32));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < g.n_img; i += blockDim.x) s_stash_cnt[i] = 0;
   __syncthreads();
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < g.n_img; i += blockDim.x) {
@@ -102,10 +110,7 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
   float* data = reinterpret_cast<float*>(s_raw + (size_t)warp * A.stage_bytes);
   unsigned long long* full = &s_full[warp];
 
-  auto request = [&](int k) {   // start loading tile k of the CTA's sequence into this warp's slot
-    const int t = blockIdx.x + k * gridDim.x;
-    if (t >= A.total_tiles) return;
-    const ATile b = a_tile(g, A, t);
+  auto request_tile = [&](const ATile& b) {   // start loading a tile into this warp's slot
     const int HW = g.hw[b.l];
     if (A.use_tma[b.l]) {
       if (lane == 0) {
@@ -135,19 +140,77 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
     if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(t_smem(full)) : "memory");
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(t_smem(full)) : "memory");
   };
+  auto request = [&](int k) {   // tile k of the CTA's sequence
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t < A.total_tiles) request_tile(a_tile(g, A, t));
+  };
 
-  request(warp);
   uint32_t ph = 0;
+  // ---- sampling phase: m and u of every sample_stride-th tile of each image -> ws.samp_acc[n][5]
+  for (int si = blockIdx.x * W + warp; si < A.samples_per_img * g.n_img; si += gridDim.x * W) {
+    const int n = si / A.samples_per_img;
+    const int t = n * A.tiles_per_img + (si - n * A.samples_per_img) * A.sample_stride;
+    const ATile b = a_tile(g, A, t);
+    request_tile(b);
+    t_wait(full, ph);
+    ph ^= 1u;
+    const float* col = data + lane;
+    float best = -INFINITY, u = -INFINITY;
+#pragma unroll 8
+    for (int c = 0; c < ori; ++c) best = fmaxf(best, col[c * kAT]);
+#pragma unroll 17
+    for (int r = 0; r < kBoxCh; ++r) u = fmaxf(u, col[(ori + r) * kAT]);
+    const float m = sigmoid_ref(best);
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (lane < b.cnt) {
+      acc[0] = (double)m;
+      acc[1] = (double)m * (double)m;
+      acc[2] = (double)u;
+      acc[3] = (double)u * (double)u;
+      acc[4] = 1.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane < 5) {
+      const double v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : acc[4];
+      atomicAdd(ws.samp_acc + n * 5 + lane, v);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the slot before the next bulk write
+    __syncwarp();
+  }
+  __threadfence();   // this warp's sums before the CTA's ticket
+  __syncthreads();
+  request(warp);     // the first tile is on its way while the grid meets
+  if (threadIdx.x == 0) {   // one ticket and one poller per CTA: a counter every warp of the grid hammered would serialise in L2
+    atomicAdd(ws.samp_ticket, 1u);
+    unsigned int seen;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ws.samp_ticket) : "memory");
+      if (seen >= gridDim.x) break;
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  int thr_img = -1;
+  float pthr_c = INFINITY, pthr_b = INFINITY;
   for (int k = warp;; k += W) {
     const int t = blockIdx.x + k * gridDim.x;
     if (t >= A.total_tiles) break;
     const ATile b = a_tile(g, A, t);
     const float* col = data + lane;
-    const int tj = (k - warp) / W;
-    TTRACE(tj, 0);
+    if (b.n != thr_img) {   // provisional thresholds of this image (latency hidden behind the tile's)
+      const double v = lane < 5 ? __ldcg(ws.samp_acc + b.n * 5 + lane) : 0.0;
+      const double cnt = __shfl_sync(0xffffffffu, v, 4);
+      const double s1 = __shfl_sync(0xffffffffu, v, (lane & 1) * 2), s2 = __shfl_sync(0xffffffffu, v, (lane & 1) * 2 + 1);
+      double var = (s2 - s1 * s1 / cnt) / (cnt - 1.0);
+      if (!(var > 0.0)) var = 0.0;
+      const float th = (float)(s1 / cnt + (double)kSampleSigmas * sqrt(var));   // even lanes: class response, odd lanes: box
+      pthr_c = __shfl_sync(0xffffffffu, th, 0);
+      pthr_b = __shfl_sync(0xffffffffu, th, 1);
+      thr_img = b.n;
+    }
     t_wait(full, ph);
     ph ^= 1u;
-    TTRACE(tj, 1);
     // ---- scan: one anchor per lane.  Lanes past the level's end hold zeros: computing on them
     // unconditionally keeps the loops free of predicates (their results are discarded).
     float best = col[0];
@@ -179,15 +242,37 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
       dist[sd] = __fdiv_rn(num, sum);                           // Integral (:40-54)
       u = fmaxf(u, mx);
     }
-    TTRACE(tj, 2);
+    const bool in = lane < b.cnt;
+    const float m = sigmoid_ref(best);
+    const size_t ga = (size_t)b.n * g.A + g.start[b.l] + b.hw0 + lane;
+    // ---- stash: the columns that clear the provisional thresholds, while the tile is still in the slot
+    {
+      const bool want = in && (m > pthr_c || u > pthr_b);
+      unsigned wm = __ballot_sync(0xffffffffu, want);
+      unsigned short myslot = 0;
+      if (wm) {   // warp-uniform
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_stash_cnt[b.n], __popc(wm));   // shared memory: this CTA's region of the image
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int idx = base + __popc(wm & ((1u << lane) - 1u));
+        const bool ok = want && idx < kStashPerCta;
+        const int row = (int)blockIdx.x * kStashPerCta + idx;
+        if (ok) myslot = (unsigned short)(row + 1);
+        unsigned om = __ballot_sync(0xffffffffu, ok);
+        while (om) {
+          const int c = __ffs(om) - 1;
+          om &= om - 1u;
+          const int r0 = __shfl_sync(0xffffffffu, row, c);
+          float* dst = ws.t_stash + ((size_t)b.n * kStashRows + r0) * A.stash_pitch;
+          for (int r = lane; r < rows; r += 32) dst[r] = data[r * kAT + c];
+        }
+      }
+      if (in) ws.t_slot[ga] = myslot;
+    }
     // every lane has read the slot: refill it now, so the next tile's latency overlaps the publishing below
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the slot before the next bulk write
     __syncwarp();
     request(k + W);
-    TTRACE(tj, 6);
-    const bool in = lane < b.cnt;
-    const float m = sigmoid_ref(best);
-    const size_t ga = (size_t)b.n * g.A + g.start[b.l] + b.hw0 + lane;
     // the tile's fp64 sums (the flags kernel that follows reduces them to the image's thresholds)
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     if (in) {
@@ -208,22 +293,11 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
       ws.t_u[ga] = u;
       ws.t_dist[ga] = make_float4(dist[0], dist[1], dist[2], dist[3]);
     }
-    TTRACE(tj, 7);
   }
 }
 
 // ----------------------------------------------------------------------------- host side
 bool tma_encode_rows(void* map, const void* base, int hw, long long rows_total, int box_rows, int box_cols);   // student.cu
-
-static unsigned long long* g_ttrace = nullptr;
-static int g_ttrace_warp = 0;
-
-static int t_env_int(const char* name, int dflt, int lo, int hi) {
-  const char* e = getenv(name);
-  if (!e) return dflt;
-  const int v = atoi(e);
-  return v < lo || v > hi ? dflt : v;
-}
 
 cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box,
                                 int32_t* cls_count, int32_t* box_count, int* tiles_per_img, cudaStream_t st) {
@@ -243,13 +317,13 @@ cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t
   if (tiles_per_img) *tiles_per_img = tiles;
   const int rows = g.ori + kBoxCh;
   A.stage_bytes = rows * kAT * (int)sizeof(float);   // a multiple of 128
-  int S = (224 * 1024) / A.stage_bytes;   // consumer warps == ring slots
+  int S = (224 * 1024 - g.n_img * (int)sizeof(int)) / A.stage_bytes;   // consumer warps == ring slots
   if (S > kAMaxWarps) S = kAMaxWarps;
   if (S < 4) return cudaErrorInvalidValue;   // ori_classes too large for this tiling
   A.stages = S;
-  A.l2_keep = 0;
-  A.trace = g_ttrace;
-  A.trace_warp = g_ttrace_warp;
+  A.stash_pitch = stash_pitch(g.ori);
+  A.sample_stride = tiles / 8 < 1 ? 1 : (tiles / 8 > 16 ? 16 : tiles / 8);   // at least ~8 sample tiles per image
+  A.samples_per_img = (tiles + A.sample_stride - 1) / A.sample_stride;
   struct MapCache {
     const void* key[2 * kLevels];
     int hw[kLevels], n_img, ori;
@@ -282,20 +356,24 @@ cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const size_t smem = (size_t)S * A.stage_bytes;
+  const size_t smem = (size_t)S * A.stage_bytes + (size_t)g.n_img * sizeof(int);
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(teacher_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     smem_set = smem;
   }
-  const int grid = A.total_tiles < sms ? A.total_tiles : sms;
+  // (a CTA of this kernel fills its SM; the assignment chain that runs beside it gets a few SMs of its own)
+  static const int free_sms = [] {
+    const char* e = getenv("ERD_TEACHER_FREE_SMS");
+    const int v = e ? atoi(e) : kTeacherFreeSms;
+    return v < 0 ? 0 : v;
+  }();
+  int grid = sms - free_sms;
+  if (grid < 1) grid = 1;
+  if (grid > A.total_tiles) grid = A.total_tiles;
+  if (grid > kStashCtas) grid = kStashCtas;   // the stash is laid out per CTA
   ERD_LAUNCH(kKErsScan, st, (teacher_pass_kernel<<<grid, 32 * S, smem, st>>>(g, ws, A, cache.maps)));
   return cudaGetLastError();
 }
 
 }  // namespace erd
-
-extern "C" void erd_teacher_trace(unsigned long long* p, int warp) {
-  erd::g_ttrace = p;
-  erd::g_ttrace_warp = warp;
-}

@@ -92,6 +92,14 @@ class Plan:
     def pad_hw(self):
         return self.meta[self.n + 1:]
 
+    def workspace_field(self, name: str, dtype: torch.dtype) -> torch.Tensor:
+        """A named workspace array as a tensor view (tests / diagnostics; include/erd_b200.h)."""
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        N.check(N.load().erd_workspace_field(C.byref(self.shape), self.ws.data_ptr(), name.encode(), C.byref(ptr),
+                                             C.byref(nbytes)), 'erd_workspace_field')
+        off = ptr.value - self.ws.data_ptr()
+        return self.ws[off:off + nbytes.value].view(dtype)
+
     def set_targets(self, gt_bboxes: Sequence[torch.Tensor], gt_labels: Sequence[torch.Tensor],
                     pad_shapes: Sequence[Tuple[int, int]]):
         """Pack per-image GT into CSR form and upload offsets + pad shapes in one copy."""

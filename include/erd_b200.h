@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define ERD_MAX_LEVELS 5
-#define ERD_ABI_VERSION 3
+#define ERD_ABI_VERSION 4
 
 typedef enum ErdStatus {
   ERD_OK = 0,
@@ -209,6 +209,12 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
  * Word [erd_avg_exchange_bytes()/4 - 3] of the own buffer becomes 1 if a peer never arrived. */
 size_t erd_avg_exchange_bytes(void);
 int erd_avg_exchange(float* avg, void* const* peer_bufs, int32_t rank, int32_t world, void* stream);
+
+/* Introspection for tests and diagnostics: device address and size of a named workspace array
+ * ("t_slot": uint16 [N][A] stash row + 1 of each anchor; "pthr": float [N][2] provisional thresholds;
+ * "t_m", "t_u": float [N][A] the teacher cache the thresholds are taken over).  ERD_ERR_BAD_SHAPE for an
+ * unknown name.  No reference counterpart. */
+int erd_workspace_field(const ErdShape* shape, void* workspace, const char* name, void** ptr, size_t* bytes);
 
 /* Launch accounting and optional per-kernel timing (CUDA events on the launching stream).
  * No reference counterpart; bench.py reports roofline numbers from it. */

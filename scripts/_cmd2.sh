@@ -1,10 +1,7 @@
-mkdir -p gpurun_out/r2o
-export ITERS=6 HANG_S=40
-run() { tag=$1; shift; echo "== $tag"; env "$@" timeout 80 python scripts/_dbg.py 2>&1 | grep -v Warn | tail -${TAILN:-3} | tee gpurun_out/r2o/$tag.txt; }
-run gauss
-run trained MODE=trained
-run g1024 HW=1024x1024
-timeout 400 python -m pytest tests -m gpu -x -q --timeout=120 2>&1 | tail -12 | tee gpurun_out/r2o/pytest.txt
-timeout 80 python scripts/time_student.py 2>&1 | grep -v Warn | tee gpurun_out/r2o/time800.txt
-HW=1024x1024 timeout 80 python scripts/time_student.py 2>&1 | grep -v Warn | tee gpurun_out/r2o/time1024.txt
-MODE=trained timeout 80 python scripts/time_student.py 2>&1 | grep -v Warn | tee gpurun_out/r2o/time800_trained.txt
+mkdir -p gpurun_out/r2v
+export ITERS=4 HANG_S=40
+timeout 80 python scripts/_dbg.py 2>&1 | grep -v Warn | tail -1
+for sf in 0 24; do for tf in 0 8; do
+echo "student_free=$sf teacher_free=$tf"
+ERD_STUDENT_FREE_SMS=$sf ERD_TEACHER_FREE_SMS=$tf timeout 80 python scripts/time_student.py 2>&1 | grep graph_step
+done; done | tee gpurun_out/r2v/sweep.txt

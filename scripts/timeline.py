@@ -14,7 +14,7 @@ p = path.plan(b.s_cls, 80, 40, 16); p.set_targets(b.gt_bboxes, b.gt_labels, b.pa
 g_cls = [torch.empty_like(t) for t in b.s_cls]; g_box = [torch.empty_like(t) for t in b.s_box]
 losses = torch.empty(p.num_losses, device='cuda')
 def step():
-    path.prepare(p, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls=g_cls, g_box=g_box); path.reduce_avg(p)
+    path.prepare(p, b.t_cls, b.t_box, b.s_cls, b.s_box); path.reduce_avg(p)
     path.loss_fwd_bwd(p, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls, g_box, losses, 1.0)
 for _ in range(5): step()
 torch.cuda.synchronize()
