@@ -32,16 +32,35 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    # N ranks of a torchrun may get here at once: one builds (file lock), into a temporary file that is
+    # renamed over the library atomically, so nobody ever maps a half-written .so
+    import fcntl
+    lock = open(LIB_PATH + '.lock', 'w')
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not needs_build():   # another rank built it while we waited
+            return LIB_PATH
+        return _build_locked(verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(verbose: bool) -> str:
+    tmp = LIB_PATH + f'.tmp{os.getpid()}'
     cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
            '-shared', '-Xcompiler', '-fPIC', '--cudart', 'shared',
-           '-o', LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+           '-o', tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     cmd[1:1] = os.environ.get('ERD_EXTRA_NVCC', '').split()   # developer builds, e.g. -DERD_DEV_ABLATE
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(res.stderr)
     return LIB_PATH

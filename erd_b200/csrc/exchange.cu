@@ -6,6 +6,7 @@
 //   store (a0, a1) into slot[rank] of every peer's buffer, release-store the epoch behind it
 //   acquire-spin on the W slots of the own buffer until they carry this epoch
 //   sum a_r / W in rank order (identical bits on every rank)
+// A peer that does not arrive within the spin bound (minutes) turns both factors into NaN.
 // The epoch lives in device memory (the kernel increments it), so the launch is CUDA-graph
 // replayable; slots are double-buffered by epoch parity, which is enough because no rank can
 // finish step k+1 before every rank has contributed to it, i.e. has finished reading step k.
@@ -50,9 +51,12 @@ __global__ void __launch_bounds__(kMaxRanks) avg_exchange_kernel(float* __restri
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(&src->epoch) : "memory");
     } while (seen != e && ++spins < (1ll << 28));   // bounded: a lost peer must not hang the GPU
-    if (seen != e) ctr[1] = 1u;                      // status word: exchange timed out
-    s_v[t][0] = *reinterpret_cast<const volatile float*>(&src->a0);
-    s_v[t][1] = *reinterpret_cast<const volatile float*>(&src->a1);
+    // A peer that never arrived is FATAL, not silent: both factors become NaN, so every loss of the
+    // step is NaN (CheckInvalidLossHook / the caller's own check fires), and the status word says why.
+    const bool lost = seen != e;
+    if (lost) ctr[1] = 1u;
+    s_v[t][0] = lost ? __int_as_float(0x7fc00000) : *reinterpret_cast<const volatile float*>(&src->a0);
+    s_v[t][1] = lost ? __int_as_float(0x7fc00000) : *reinterpret_cast<const volatile float*>(&src->a1);
   }
   __syncthreads();
   if (t < 2) {

@@ -4,7 +4,9 @@
 Reference: ``GFLIncrementERD`` (mmdet/models/detectors/gfl_increment_erd.py:20-220).  Backbone,
 neck, teacher construction and checkpoint surgery (:67-122) are out of scope (SURVEY.md §8f);
 the student / teacher networks are injected as modules so that the same ``loss`` sequence
-(:202-220) runs: teacher forward, ``sel_pos``, student forward, ``bbox_head.loss``.
+(:202-220) runs: teacher forward, ``sel_pos``, student forward, ``bbox_head.loss``.  This is the
+STANDALONE mirror; inside a real mmdet use ``erd_b200/mmdet_plugin.py`` (subclasses of the reference's
+own classes, registered under their own names).
 """
 from __future__ import annotations
 
@@ -14,7 +16,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from .head import ErsSelection, GFLHeadIncrementERD
+from .head import ErsSelection, GFLHeadIncrementERD, fused_sel_pos
 
 
 class GFLIncrementERD(nn.Module):
@@ -36,14 +38,9 @@ class GFLIncrementERD(nn.Module):
         topk_bbox_inds, topk_bbox_preds); the index lists are lazily materialised views of the
         device-side selection, the two gathered-value lists -- which ``loss_by_feat`` never
         reads (:339-340) -- are gathered only on access."""
-        assert len(cls_scores) == len(bbox_preds)                                    # :180
         head = self.bbox_head
-        t_cls = [t[:, :self.ori_num_classes].detach().contiguous() for t in cls_scores]
-        t_box = [t.detach().contiguous() for t in bbox_preds]
-        plan = head.path.plan(t_cls, head.num_classes, self.ori_num_classes, head.reg_max)
-        head.path.ers_select(plan, t_cls, t_box)
-        gen = plan.ers_generation
-        cls_sel, box_sel = ErsSelection(plan, 'cls', gen), ErsSelection(plan, 'box', gen)
+        _, t_cls, t_box, cls_sel, box_sel = fused_sel_pos(head.path, head.num_classes, head.reg_max,
+                                                          self.ori_num_classes, cls_scores, bbox_preds)
         return (cls_sel, _LazyGather(cls_sel, t_cls), box_sel, _LazyGather(box_sel, t_box))
 
     def loss(self, batch_inputs: Tensor, batch_data_samples) -> dict:
@@ -75,10 +72,3 @@ class _LazyGather:
 
     def __getitem__(self, i):
         return self._materialise()[i]
-
-
-try:
-    from mmdet.registry import MODELS as _MODELS  # type: ignore
-    _MODELS.register_module(name='GFLIncrementERD', module=GFLIncrementERD, force=True)
-except Exception:
-    _MODELS = None

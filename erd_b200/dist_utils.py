@@ -33,7 +33,8 @@ class PeerAvgExchange:
     (``erd_avg_exchange``): every rank owns a small symmetric buffer all peers have mapped.
     Plumbing only: torch symmetric memory allocates and maps the buffers.  ``create`` returns
     None (the caller then keeps the NCCL all-reduce) when the process group is not initialised,
-    has one rank, spans more than one node, or symmetric memory cannot be set up."""
+    has one rank, spans more than one node, or symmetric memory cannot be set up.  A peer that
+    never arrives makes both factors NaN (every loss of the step is then NaN) and sets a status word."""
 
     def __init__(self, lib, buf, handle, rank: int, world_size: int):
         import ctypes as C
@@ -49,8 +50,17 @@ class PeerAvgExchange:
             return None
         if torch.device(device).type != 'cuda' or 'nccl' not in str(dist.get_backend()):
             return None
-        if int(os.environ.get('LOCAL_WORLD_SIZE', ws)) != ws:
-            return None                      # peer memory is a single-node mechanism
+        # peer memory is a single-node mechanism.  Launchers that do not export LOCAL_WORLD_SIZE
+        # (mmengine's slurm launcher) are asked directly: do all ranks report the same host?
+        if 'LOCAL_WORLD_SIZE' in os.environ:
+            if int(os.environ['LOCAL_WORLD_SIZE']) != ws:
+                return None
+        else:
+            import socket
+            hosts = [None] * ws
+            dist.all_gather_object(hosts, socket.gethostname())
+            if len(set(hosts)) != 1:
+                return None
         try:
             import torch.distributed._symmetric_memory as symm
             nbytes = int(lib.erd_avg_exchange_bytes())

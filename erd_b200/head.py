@@ -3,9 +3,11 @@ keys and ``loss`` / ``loss_by_feat`` signatures, backed by the sm_100a kernels.
 
 Reference: ``GFLHeadIncrementERD`` (mmdet/models/dense_heads/gfl_head_increment_erd.py:57-484)
 on top of ``GFLHead`` (dense_heads/gfl_head.py:65-230 for the conv stacks, which stay on
-PyTorch/cuDNN as the north star prescribes).  When a real ``mmdet`` is importable the class
-is also registered in its ``MODELS`` registry under the same name (force=True), so the
-``configs/gfl_increment`` files build it unchanged; it imports standalone otherwise.
+PyTorch/cuDNN as the north star prescribes).  This class is the STANDALONE mirror (no mmdet
+needed; flat conv towers).  Inside a real mmdet, ``erd_b200/mmdet_plugin.py`` subclasses the
+reference's own head instead and overrides only the hot-path methods with the functions below, so
+parameter names, ``predict`` and checkpoint surgery stay the reference's; nothing here replaces a
+registered reference class.
 """
 from __future__ import annotations
 
@@ -79,6 +81,62 @@ class _ErdLossFn(torch.autograd.Function):
             raise RuntimeError('erd_b200: backward with weighted loss terms after the plan was reused')
         grads = [g if ctx.needs_input_grad[6 + i] else None for i, g in enumerate(g_cls + g_box)]
         return (None, None, None, None, None, None, *grads)
+
+
+def fused_loss_by_feat(head, ori_outs, new_outs, ori_topk_cls_inds, ori_topk_bbox_inds, ori_num_classes,
+                       dist_loss_weight, batch_gt_instances, batch_img_metas) -> dict:
+    """The hot path behind ``loss_by_feat`` (gfl_head_increment_erd.py:334-454) for any head object that
+    carries ``path`` (ErdPath), ``num_classes``, ``reg_max`` and ``strides`` -- the standalone mirror
+    below or the subclass of the reference's head in ``mmdet_plugin.py``.  Returns
+    dict(loss_cls[5], loss_bbox[5], loss_dfl[5], loss_dist_cls[N], loss_dist_bbox[N]) of 0-dim
+    tensors attached to the autograd graph of ``new_outs``.  ``ori_topk_cls_scores``,
+    ``ori_topk_bbox_preds`` and ``model`` of the reference signature are unused there too."""
+    cls_scores, bbox_preds = new_outs
+    t_cls, t_box = ori_outs
+    assert len(cls_scores) == len(head.strides)                                  # :374
+    num_imgs = cls_scores[0].size(0)
+    assert len(batch_img_metas) == num_imgs and len(batch_gt_instances) == num_imgs   # gfl_head.py:517-518
+    s_cls = [t.contiguous() for t in cls_scores]
+    s_box = [t.contiguous() for t in bbox_preds]
+    t_cls = [t[:, :ori_num_classes].detach().contiguous() for t in t_cls]
+    t_box = [t.detach().contiguous() for t in t_box]
+    plan = head.path.plan(s_cls, head.num_classes, int(ori_num_classes), head.reg_max,
+                          max((int(g.bboxes.shape[0]) for g in batch_gt_instances), default=0))
+    ers_done = adopt_selection(head.path, plan, t_cls, t_box, ori_topk_cls_inds, ori_topk_bbox_inds)
+    plan.set_targets([g.bboxes for g in batch_gt_instances], [g.labels for g in batch_gt_instances],
+                     [m['pad_shape'][:2] for m in batch_img_metas])
+    vec = _ErdLossFn.apply(head, plan, t_cls, t_box, float(dist_loss_weight), ers_done, *s_cls, *s_box)
+    L = len(head.strides)
+    parts = vec.split([L, L, L, num_imgs, num_imgs])
+    return dict(loss_cls=list(parts[0].unbind()), loss_bbox=list(parts[1].unbind()),
+                loss_dfl=list(parts[2].unbind()), loss_dist_cls=list(parts[3].unbind()),
+                loss_dist_bbox=list(parts[4].unbind()))
+
+
+def adopt_selection(path: ErdPath, plan: Plan, t_cls, t_box, cls_inds, box_inds) -> bool:
+    """True when the plan already holds ``sel_pos`` results for these teacher tensors.
+    Foreign index lists (plain tensors) are honoured: the teacher cache is rebuilt and the
+    given rows are loaded into the plan."""
+    if (isinstance(cls_inds, ErsSelection) and isinstance(box_inds, ErsSelection)
+            and cls_inds.plan is plan and cls_inds.generation == plan.ers_generation
+            and box_inds.generation == plan.ers_generation):
+        return True
+    path.ers_select(plan, t_cls, t_box)
+    plan.ers_generation += 1
+    plan.load_selection(cls_inds, box_inds)
+    return True
+
+
+def fused_sel_pos(path: ErdPath, num_classes: int, reg_max: int, ori_num_classes: int, cls_scores, bbox_preds):
+    """``GFLIncrementERD.sel_pos`` (gfl_increment_erd.py:165-200) on the device.  Returns the plan, the
+    teacher tensors as the kernels read them, and the two lazily materialised index lists."""
+    assert len(cls_scores) == len(bbox_preds)                                    # :180
+    t_cls = [t[:, :ori_num_classes].detach().contiguous() for t in cls_scores]
+    t_box = [t.detach().contiguous() for t in bbox_preds]
+    plan = path.plan(t_cls, num_classes, ori_num_classes, reg_max)
+    path.ers_select(plan, t_cls, t_box)
+    gen = plan.ers_generation
+    return plan, t_cls, t_box, ErsSelection(plan, 'cls', gen), ErsSelection(plan, 'box', gen)
 
 
 def _cfg_get(cfg, key, default=None):
@@ -167,43 +225,9 @@ class GFLHeadIncrementERD(nn.Module):
     def loss_by_feat(self, ori_outs, new_outs, ori_topk_cls_inds, ori_topk_cls_scores, ori_topk_bbox_inds,
                      ori_topk_bbox_preds, ori_num_classes, dist_loss_weight, model, batch_gt_instances,
                      batch_img_metas, batch_gt_instances_ignore=None) -> dict:
-        """Same contract as gfl_head_increment_erd.py:334-454: returns
-        dict(loss_cls[5], loss_bbox[5], loss_dfl[5], loss_dist_cls[N], loss_dist_bbox[N]) of 0-dim
-        tensors attached to the autograd graph of ``new_outs``.  ``ori_topk_cls_scores``,
-        ``ori_topk_bbox_preds`` and ``model`` are unused, as in the reference."""
-        cls_scores, bbox_preds = new_outs
-        t_cls, t_box = ori_outs
-        assert len(cls_scores) == len(self.strides)                                  # :374
-        num_imgs = cls_scores[0].size(0)
-        assert len(batch_img_metas) == num_imgs and len(batch_gt_instances) == num_imgs   # gfl_head.py:517-518
-        s_cls = [t.contiguous() for t in cls_scores]
-        s_box = [t.contiguous() for t in bbox_preds]
-        t_cls = [t[:, :ori_num_classes].detach().contiguous() for t in t_cls]
-        t_box = [t.detach().contiguous() for t in t_box]
-        plan = self.path.plan(s_cls, self.num_classes, int(ori_num_classes), self.reg_max,
-                              max((int(g.bboxes.shape[0]) for g in batch_gt_instances), default=0))
-        ers_done = self._adopt_selection(plan, t_cls, t_box, ori_topk_cls_inds, ori_topk_bbox_inds)
-        plan.set_targets([g.bboxes for g in batch_gt_instances], [g.labels for g in batch_gt_instances],
-                         [m['pad_shape'][:2] for m in batch_img_metas])
-        vec = _ErdLossFn.apply(self, plan, t_cls, t_box, float(dist_loss_weight), ers_done, *s_cls, *s_box)
-        L = len(self.strides)
-        parts = vec.split([L, L, L, num_imgs, num_imgs])
-        return dict(loss_cls=list(parts[0].unbind()), loss_bbox=list(parts[1].unbind()),
-                    loss_dfl=list(parts[2].unbind()), loss_dist_cls=list(parts[3].unbind()),
-                    loss_dist_bbox=list(parts[4].unbind()))
-
-    def _adopt_selection(self, plan: Plan, t_cls, t_box, cls_inds, box_inds) -> bool:
-        """True when the plan already holds ``sel_pos`` results for these teacher tensors.
-        Foreign index lists (plain tensors) are honoured: the teacher cache is rebuilt and the
-        given rows are loaded into the plan."""
-        if (isinstance(cls_inds, ErsSelection) and isinstance(box_inds, ErsSelection)
-                and cls_inds.plan is plan and cls_inds.generation == plan.ers_generation
-                and box_inds.generation == plan.ers_generation):
-            return True
-        self.path.ers_select(plan, t_cls, t_box)
-        plan.ers_generation += 1
-        plan.load_selection(cls_inds, box_inds)
-        return True
+        """Same contract as gfl_head_increment_erd.py:334-454 (see ``fused_loss_by_feat``)."""
+        return fused_loss_by_feat(self, ori_outs, new_outs, ori_topk_cls_inds, ori_topk_bbox_inds, ori_num_classes,
+                                  dist_loss_weight, batch_gt_instances, batch_img_metas)
 
     def loss(self, ori_outs, new_outs, batch_data_samples, topk_cls_inds, topk_cls_scores, topk_bbox_inds,
              topk_bbox_preds, ori_num_classes, dist_loss_weight, model) -> dict:
@@ -226,10 +250,3 @@ def parse_losses(losses: dict) -> Tensor:
         if 'loss' in k:
             total = total + (v.mean() if isinstance(v, Tensor) else sum(x.mean() for x in v))
     return total
-
-
-try:  # register into a real mmdet when there is one
-    from mmdet.registry import MODELS as _MODELS  # type: ignore
-    _MODELS.register_module(name='GFLHeadIncrementERD', module=GFLHeadIncrementERD, force=True)
-except Exception:  # mmdet absent (this image) or incompatible: standalone use
-    _MODELS = None

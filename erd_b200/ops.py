@@ -74,7 +74,11 @@ class Plan:
         self.sel_flags = torch.zeros(n, self.A, dtype=torch.uint8, device=device)
         self.avg = torch.zeros(2, dtype=torch.float32, device=device)
         self.meta = torch.zeros(3 * n + 1, **i32)            # gt_offsets (n+1) | pad_hw (2n)
-        self.meta_host = torch.zeros(3 * n + 1, dtype=torch.int32).pin_memory()
+        # pinned staging for `meta`, rotated: a host that runs ahead of the GPU must not rewrite a buffer
+        # whose asynchronous copy has not run yet (each buffer is re-used only after its copy's event)
+        self._meta_hosts = [torch.zeros(3 * n + 1, dtype=torch.int32).pin_memory() for _ in range(3)]
+        self._meta_events = [None, None, None]
+        self._meta_turn = 0
         self.gt_boxes = torch.zeros(1, 4, dtype=torch.float32, device=device)
         self.gt_labels = torch.zeros(1, dtype=torch.int64, device=device)
         self.ers_generation = 0      # bumped every time the ERS buffers are rewritten
@@ -106,9 +110,14 @@ class Plan:
         n = self.n
         if not (len(gt_bboxes) == len(gt_labels) == len(pad_shapes) == n):
             raise AssertionError('gt / meta list lengths must equal the batch size')   # gfl_head.py:518
+        turn = self._meta_turn
+        self._meta_turn = (turn + 1) % len(self._meta_hosts)
+        if self._meta_events[turn] is not None:
+            self._meta_events[turn].synchronize()
+        meta_host = self._meta_hosts[turn]
         off = 0
         for i in range(n):
-            self.meta_host[i] = off
+            meta_host[i] = off
             off += int(gt_bboxes[i].shape[0])
             if int(gt_bboxes[i].shape[0]) > self.max_gt:
                 raise ValueError(f'image {i} has {int(gt_bboxes[i].shape[0])} GT boxes, plan capacity is {self.max_gt}')
@@ -116,10 +125,13 @@ class Plan:
             if ph < 1 or pw < 1:
                 # reference: ValueError when an image has no valid anchor (gfl_head.py:613-617)
                 raise ValueError('There is no valid anchor inside the image boundary.')
-            self.meta_host[n + 1 + 2 * i] = ph
-            self.meta_host[n + 2 + 2 * i] = pw
-        self.meta_host[n] = off
-        self.meta.copy_(self.meta_host, non_blocking=True)
+            meta_host[n + 1 + 2 * i] = ph
+            meta_host[n + 2 + 2 * i] = pw
+        meta_host[n] = off
+        self.meta.copy_(meta_host, non_blocking=True)
+        ev = self._meta_events[turn] or torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._meta_events[turn] = ev
         self.shape.total_gt = off
         if off > 0:
             self.gt_boxes = torch.cat([b.reshape(-1, 4) for b in gt_bboxes]).to(
@@ -158,6 +170,7 @@ class ErdPath:
         self.weights = tuple(float(w) for w in loss_weights) + (float(kd_T),)
         self.strides, self.anchor_scale, self.nms_iou_thr = tuple(strides), float(anchor_scale), float(nms_iou_thr)
         self._plans: Dict[tuple, Plan] = {}
+        self.max_plans = 8
         self._cap: Dict[tuple, int] = {}
         self._ctx: Dict[int, C.c_void_p] = {}
 
@@ -187,9 +200,15 @@ class ErdPath:
         self._cap[base + (t0.device,)] = cap
         key = base + (cap,)
         full = key + (t0.device,)
-        if full not in self._plans:
-            self._plans[full] = Plan(key, t0.device)
-        return self._plans[full]
+        plan = self._plans.pop(full, None)
+        if plan is None:
+            plan = Plan(key, t0.device)
+            # Resize(keep_ratio) + pad_size_divisor yield many padded batch geometries and capacity doublings
+            # supersede plans: keep the most recently used few (a plan is ~140 MB of workspace at 16 images)
+            while len(self._plans) >= self.max_plans:
+                self._plans.pop(next(iter(self._plans)))
+        self._plans[full] = plan   # most recently used last
+        return plan
 
     # ---- individual stages (used by the parity tests and by sel_pos) -----------------
     def ers_select(self, p: Plan, t_cls, t_box):

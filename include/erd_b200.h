@@ -206,7 +206,8 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
  * peer_bufs[r]: rank r's exchange buffer of erd_avg_exchange_bytes() bytes as mapped into THIS
  * process (the host maps them, e.g. with torch symmetric memory or CUDA IPC), zeroed once by
  * its owner before the first call.  Collective: every rank calls it once per step.
- * Word [erd_avg_exchange_bytes()/4 - 3] of the own buffer becomes 1 if a peer never arrived. */
+ * A peer that never arrives (spin bound: minutes) is fatal, not silent: avg[0..1] become NaN, so every loss
+ * of the step is NaN, and word [erd_avg_exchange_bytes()/4 - 3] of the own buffer becomes 1. */
 size_t erd_avg_exchange_bytes(void);
 int erd_avg_exchange(float* avg, void* const* peer_bufs, int32_t rank, int32_t world, void* stream);
 
