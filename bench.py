@@ -28,25 +28,40 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'anchors_per_sec_gfl_erd_loss_fwd_bwd'
 UNIT = 'anchors/s'
-IMG_HW = (800, 1333)
-IMGS_PER_GPU = 16
-ORI, NUM_CLASSES, REG_MAX = 40, 80, 16
-# compulsory fp32 traffic per anchor, fwd+bwd, 40+40 split
-# per dense kernel: ers_scan reads teacher cls + box; qfl_sweep reads the student's
-# new-class logits and writes their gradients; zero_fill writes the old-class and the box gradients (their
-# non-zero rows -- ERS rows, positives, box candidates -- are written over it by small list-driven kernels,
-# which are also the only readers of the student's old-class and box logits)
-CN = NUM_CLASSES - ORI
-BYTES_PER_ANCHOR = {'path': 1616, 'ers_scan': 4 * (ORI + 68), 'student_pass': 8 * (NUM_CLASSES + 68)}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload (16 images), from
-# profiles/r1c_traffic.csv.  Kernels that only write (zero_fill) or write as much as they read (qfl_sweep)
-# show less than their algorithmic bytes: dirty lines still sit in the 126 MB L2 when the kernel ends and
-# are written back during the next one.
-# per-launch duration of the same kernels run one at a time (ncu launch list, cold cache, serialised):
-# profiles/r1d_launches.csv.  Inside the step they overlap each other and the latency chains, so the live
-# per-kernel durations bench.py measures are longer; both are reported.
-NCU_ALONE_US = {}
-NCU_TRAFFIC_BYTES = {}
+NUM_CLASSES, REG_MAX = 80, 16
+# --config: the BASELINE.json configurations that fit one GPU (configs[1] is the one the metric is quoted on
+# and the default; the others are reported in DESIGN.md section 5)
+CONFIGS = {
+    'cfg1': dict(hw=(800, 1333), ori=40, imgs=16, num_gt=None, mode='gaussian',
+                 name='GFL R50-FPN 40+40 ERD loss fwd+bwd, {n} img/GPU 800x1333, 80-class head, reg_max=16 '
+                      '(BASELINE.json configs[1])'),
+    'cfg4_70_10': dict(hw=(800, 1333), ori=70, imgs=16, num_gt=None, mode='gaussian',
+                       name='70+10 split ERD loss fwd+bwd, {n} img/GPU 800x1333, 80-class head, 70 old classes distilled '
+                            '(BASELINE.json configs[3])'),
+    'cfg5_dense': dict(hw=(1600, 1600), ori=40, imgs=8, num_gt=100, mode='trained',
+                       name='dense scene 40+40 ERD loss fwd+bwd, {n} img/GPU 1600x1600, 100 GT boxes/image, planted-object '
+                            'teacher (BASELINE.json configs[4])'),
+    'trained': dict(hw=(800, 1333), ori=40, imgs=16, num_gt=None, mode='trained',
+                    name='40+40 ERD loss fwd+bwd, {n} img/GPU 800x1333, planted-object teacher (NMS-heavy mode of '
+                         'SURVEY.md 8(d))'),
+}
+CFG = CONFIGS['cfg1']
+
+
+def bytes_per_anchor(ori):
+    """compulsory fp32 traffic per anchor, fwd+bwd.  teacher pass: reads the
+    teacher's old-class logits and box distributions once; student pass: reads every student logit once and
+    writes every gradient element once."""
+    teacher, student = 4 * (ori + 68), 8 * (NUM_CLASSES + 68)
+    return {'path': teacher + student, 'ers_scan': teacher, 'student_pass': student}
+
+
+# Per-launch figures of the two dense kernels run one at a time under ncu at the default workload (cfg1, 16
+# images): duration from profiles/r2_launches.csv (cold cache, serialised), DRAM bytes (dram__bytes_read.sum +
+# dram__bytes_write.sum) from the --set full captures in profiles/r2_ncu_full_student_teacher.csv.  A kernel
+# that writes shows less than its algorithmic bytes: dirty lines still sit in the 126 MB L2 when it ends.
+NCU_ALONE_US = {'ers_scan': 43.4, 'student_pass': 87.9}
+NCU_TRAFFIC_BYTES = {'ers_scan': 169.6e6, 'student_pass': 396.5e6}
 
 
 def parse():
@@ -55,7 +70,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--imgs', type=int, default=IMGS_PER_GPU)
+    ap.add_argument('--config', default='cfg1', choices=sorted(CONFIGS))
+    ap.add_argument('--imgs', type=int, default=0, help='images per GPU (default: the config\'s)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -63,7 +79,8 @@ def parse():
 
 def make_inputs(n_imgs, seed):
     from erd_b200.synth import make_batch
-    return make_batch(n_imgs, IMG_HW, ori=ORI, num_classes=NUM_CLASSES, reg_max=REG_MAX, seed=seed)
+    return make_batch(n_imgs, CFG['hw'], ori=CFG['ori'], num_classes=NUM_CLASSES, reg_max=REG_MAX, seed=seed,
+                      num_gt=CFG['num_gt'], mode=CFG['mode'], gt_size_pow=2.0 if CFG['num_gt'] else 1.0)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -113,12 +130,14 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def time_cpu_oracle(n_imgs, iters, warmup, seed=1234):
-    """The oracle port (torch CPU, all host threads) on a bounded sample of the workload."""
+def time_cpu_oracle(n_imgs, iters, warmup, seed=1234, budget_s=None):
+    """The oracle port (torch CPU, all host threads) on n_imgs images of the workload per step.
+    ``budget_s``: stop timing early (after at least one step) when the run would exceed it."""
     from oracle import erd_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     b = make_inputs(n_imgs, seed)
     times = []
+    t_start = time.perf_counter()
     for it in range(warmup + iters):
         s_cls = [t.clone().requires_grad_() for t in b.s_cls]
         s_box = [t.clone().requires_grad_() for t in b.s_box]
@@ -128,28 +147,34 @@ def time_cpu_oracle(n_imgs, iters, warmup, seed=1234):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+        if budget_s is not None and times and time.perf_counter() - t_start + dt > budget_s:
+            break
     anchors = n_imgs * b.anchors_per_image
     return anchors, times, torch.get_num_threads()
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path (the oracle port: the reference itself is Python on
+    mmcv/mmengine and cannot travel to the GPU box) on the SAME workload as our arm: all images of the config
+    per step, the steps and warm-up the driver asked for, every host core.  Rank 0 only."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    n_sample = min(2, args.imgs)
-    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
-    anchors, times, cores = time_cpu_oracle(n_sample, steps, warm)
-    ms = 1e3 * sum(times) / len(times)
-    val = anchors / (sum(times) / len(times))
+    n = args.imgs
+    anchors, times, cores = time_cpu_oracle(n, args.steps, args.warmup, budget_s=420.0)
+    steps = len(times)
+    ms = 1e3 * sum(times) / steps
+    val = anchors / (sum(times) / steps)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
-        'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'GFL R50-FPN 40+40 ERD loss fwd+bwd, {args.imgs} img/GPU 800x1333, 80-class head, '
-                               f'reg_max=16', 'sample': f'{n_sample} of {args.imgs} images per step'},
+        'config': {'workload': CFG['name'].format(n=n), 'images_per_step': n,
+                   'note': 'one CPU process on rank 0 (the whole host), not one per GPU'
+                           + ('' if steps == args.steps else f'; stopped after {steps} of {args.steps} steps (time budget)')},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': f'{n_sample} images x 22400 anchors per step, {steps} steps, torch CPU oracle port '
-                                   f'(reference is Python and cannot travel to the GPU box)'},
+                         'sample': f'{n} images x {anchors // n} anchors per step, {steps} steps after {args.warmup} '
+                                   f'warm-up, torch-CPU oracle port on {cores} threads'},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -186,7 +211,9 @@ def run_ours(args):
     host = make_inputs(n, 1234 + rank)
     A = host.anchors_per_image
     b = host.to(dev)
-    plan = path.plan(b.s_cls, NUM_CLASSES, ORI, REG_MAX)
+    ORI = CFG['ori']
+    BYTES_PER_ANCHOR = bytes_per_anchor(ORI)
+    plan = path.plan(b.s_cls, NUM_CLASSES, ORI, REG_MAX, max((int(x.shape[0]) for x in b.gt_bboxes), default=0))
     plan.set_targets(b.gt_bboxes, b.gt_labels, b.pad_shapes)
     g_cls = [torch.empty_like(t) for t in b.s_cls]
     g_box = [torch.empty_like(t) for t in b.s_box]
@@ -272,6 +299,52 @@ def run_ours(args):
     lib.erd_profile_enable(0)
     kern = collect()
 
+    # ---- the same step through the plugin API with DEVICE-resident inputs: sel_pos + loss_by_feat + backward
+    # (what a training loop pays per iteration on top of the conv stacks; eager launches, autograd included)
+    api = None
+    if not args.no_e2e:
+        det_a = GFLIncrementERD(head, ORI)
+        gts_a = [type('GT', (), dict(bboxes=x, labels=y))() for x, y in zip(b.gt_bboxes, b.gt_labels)]
+        metas_a = [dict(img_shape=i, pad_shape=p) for i, p in zip(host.img_shapes, host.pad_shapes)]
+        sc = [t.clone().requires_grad_() for t in b.s_cls]
+        sb = [t.clone().requires_grad_() for t in b.s_box]
+
+        def api_step():
+            for t in sc + sb:
+                t.grad = None
+            sel = det_a.sel_pos(b.t_cls, b.t_box)
+            out = head.loss_by_feat((b.t_cls, b.t_box), (sc, sb), sel[0], sel[1], sel[2], sel[3], ORI, 1.0, None,
+                                    gts_a, metas_a)
+            parse_losses(out).backward()
+        for _ in range(3):
+            api_step()
+        ms_api = timed(api_step, args.steps) / args.steps
+        api = {'ms_per_step': ms_api, 'value': world * n * A / (ms_api * 1e-3), 'unit': UNIT,
+               'api': 'GFLIncrementERD.sel_pos + GFLHeadIncrementERD.loss_by_feat + backward, inputs resident in HBM, '
+                      'eager launches (no CUDA graph), CUDA events'}
+
+    # ---- multi-rank check (N > 1): the reduced avg factors every rank holds must be the mean of the ranks'
+    # local factors as reduce_mean computes it (t / W summed in rank order), bit for bit on every rank
+    multi = None
+    if world > 1:
+        path.prepare(plan, b.t_cls, b.t_box, b.s_cls, b.s_box)
+        local = plan.avg.clone()
+        path.reduce_avg(plan)
+        path.loss_fwd_bwd(plan, b.t_cls, b.t_box, b.s_cls, b.s_box, g_cls, g_box, losses, 1.0)
+        torch.cuda.synchronize()
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        want = torch.zeros_like(local)
+        for t in gathered:
+            want += t / world
+        ok = bool(torch.equal(plan.avg, want)) and bool(torch.isfinite(losses).all())
+        okt = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        multi = {'avg_factors_equal_mean_of_ranks_bitwise': bool(int(okt.item())),
+                 'local_avg_rank0': [float(x) for x in local.tolist()], 'reduced_avg': [float(x) for x in plan.avg.tolist()]}
+        if not int(okt.item()):
+            raise SystemExit(f'rank {rank}: reduced avg factors {plan.avg.tolist()} != mean of ranks {want.tolist()}')
+
     # ---- e2e: the reference-facing plugin API with HOST buffers (pinned), H2D of every head
     # output and D2H of the loss vector inside the timed region, autograd backward included.
     e2e = None
@@ -336,19 +409,18 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'GFL R50-FPN 40+40 ERD loss fwd+bwd, {n} img/GPU 800x1333, 80-class head, '
-                                   f'reg_max=16 (BASELINE.json configs[1])', 'anchors_per_image': A,
+            'config': {'workload': CFG['name'].format(n=n), 'name': args.config, 'anchors_per_image': A,
                        'images_per_gpu': n, 'parallelism': f'dp{world} over images', 'collective': collective,
-                       'l2': 'inputs+grads 579 MB per step > 126 MB L2, no flush needed'},
+                       'l2': f'inputs+grads {n * A * BYTES_PER_ANCHOR["path"] / 1e6:.0f} MB per step > 126 MB L2, no flush needed'},
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': (achieved / peak) if achieved else None,
-                         'traffic': NCU_TRAFFIC_BYTES.get(dom) if n == IMGS_PER_GPU else None,
-                         'traffic_source': 'profiles/r1c_traffic.csv (ncu, per launch, bytes)',
+                         'traffic': NCU_TRAFFIC_BYTES.get(dom) if (args.config == 'cfg1' and n == CONFIGS['cfg1']['imgs']) else None,
+                         'traffic_source': 'profiles/r2_ncu_full_student_teacher.csv (ncu --set full, per launch, bytes)',
                          'kernel_alone': ({'us': NCU_ALONE_US[dom],
                                            'achieved_gbs': round(n * A * BYTES_PER_ANCHOR[dom] / (NCU_ALONE_US[dom] * 1e-6) / 1e9, 1),
                                            'frac': round(n * A * BYTES_PER_ANCHOR[dom] / (NCU_ALONE_US[dom] * 1e-6) / 1e9 / peak, 3),
-                                           'source': 'profiles/r1d_launches.csv (ncu launch list, kernel run alone)'}
-                                          if n == IMGS_PER_GPU and dom in NCU_ALONE_US else None),
+                                           'source': 'profiles/r2_ncu_full_student_teacher.csv (ncu, kernel run alone, cold cache)'}
+                                          if (args.config == 'cfg1' and n == CONFIGS['cfg1']['imgs']) and dom in NCU_ALONE_US else None),
                          'peak_source': 'measured' if peaks else 'fallback',
                          'algorithmic_bytes_per_anchor': BYTES_PER_ANCHOR[dom],
                          'path_bytes_per_anchor': BYTES_PER_ANCHOR['path'],
@@ -361,13 +433,15 @@ def run_ours(args):
                          'kernel_ms_breakdown_pass': {k: round(v, 5) for k, v in kern.items() if v}},
             'launch_mode': {'value_from': 'cuda_graph_replay' if ms_graph is not None else 'eager',
                             'ms_per_step_eager': ms_eager / args.steps, 'graph_error': graph_err},
-            'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e,
+            'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'api_device_resident': api,
+            'multi_rank_check': multi,
         }
         if not args.no_cpu_baseline and world == 1:
-            anchors, times, cores = time_cpu_oracle(2, 5, 2)
+            anchors, times, cores = time_cpu_oracle(n, 10, 2, budget_s=25.0)
             line['cpu_baseline'] = {'value': anchors / (sum(times) / len(times)), 'unit': UNIT, 'cores': cores,
-                                    'kind': 'port', 'sample': '2 images x 22400 anchors per step, 5 steps, '
-                                                              'torch-CPU oracle port of the reference'}
+                                    'kind': 'port', 'sample': f'{n} images x {A} anchors per step (the whole workload), '
+                                                              f'{len(times)} steps after 2 warm-up, torch-CPU oracle port '
+                                                              f'of the reference on {cores} threads'}
         print(json.dumps(line), flush=True)
     if world > 1:
         # NCCL teardown with a captured graph alive can block; everything is printed, so leave
@@ -382,6 +456,9 @@ def run_ours(args):
 
 if __name__ == '__main__':
     a = parse()
+    CFG = CONFIGS[a.config]
+    if a.imgs <= 0:
+        a.imgs = CFG['imgs']
     if a.impl == 'reference':
         run_reference(a)
     else:

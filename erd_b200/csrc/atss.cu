@@ -56,6 +56,9 @@ __global__ void __launch_bounds__(kCandThreads) atss_candidates_kernel(Geo g, Wo
                                                                         const int32_t* __restrict__ gt_offsets,
                                                                         const int32_t* __restrict__ pad_hw) {
   const int gid = blockIdx.x;
+  // the grid covers shape.total_gt rows, which may be a fixed capacity (a CUDA graph of the step then stays
+  // valid from batch to batch); the rows in use are gt_offsets[N]
+  if (gid >= gt_offsets[g.n_img]) return;
   const int lane = threadIdx.x & 31, l = threadIdx.x >> 5;
   __shared__ int s_img, s_first, s_pad[2];
   __shared__ int s_idx[kLevels * kTopK];

@@ -548,7 +548,14 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(full);   // releases the header written by all lanes
+#ifndef ERD_RACECHECK
       cp_async_arrive(full);              // every lane: its copies (possibly none) count towards the slot
+#else
+      // compute-sanitizer racecheck tracks cp.async only through wait_group: this build (scripts/sanitize.sh)
+      // completes the copies synchronously so that the tool can check everything else about the slot protocol
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      mbar_arrive(full);
+#endif
     }
     if (j >= 2) drain(j - 2);
     if (j >= 1) drain(j - 1);

@@ -154,6 +154,7 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
     request_tile(b);
     t_wait(full, ph);
     ph ^= 1u;
+    asm volatile("cp.async.wait_all;" ::: "memory");
     const float* col = data + lane;
     float best = -INFINITY, u = -INFINITY;
 #pragma unroll 8
@@ -211,6 +212,9 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
     }
     t_wait(full, ph);
     ph ^= 1u;
+    // (the copies of an unaligned level are complete here -- they arrived on the barrier; the wait is free and
+    // tells tools that track cp.async only through wait_group, compute-sanitizer racecheck, as much)
+    asm volatile("cp.async.wait_all;" ::: "memory");
     // ---- scan: one anchor per lane.  Lanes past the level's end hold zeros: computing on them
     // unconditionally keeps the loops free of predicates (their results are discarded).
     float best = col[0];

@@ -48,7 +48,6 @@ class Plan:
         for l in range(min(len(shapes), N.MAX_LEVELS)):
             self.shape.level_h[l], self.shape.level_w[l] = shapes[l]
             self.shape.stride[l] = strides[l]
-        self.shape.total_gt = 0
         self.shape.anchor_scale = scale
         (self.shape.loss_weight_cls, self.shape.loss_weight_bbox, self.shape.loss_weight_dfl,
          self.shape.loss_weight_ld, self.shape.kd_temperature) = weights
@@ -79,8 +78,11 @@ class Plan:
         self._meta_hosts = [torch.zeros(3 * n + 1, dtype=torch.int32).pin_memory() for _ in range(3)]
         self._meta_events = [None, None, None]
         self._meta_turn = 0
-        self.gt_boxes = torch.zeros(1, 4, dtype=torch.float32, device=device)
-        self.gt_labels = torch.zeros(1, dtype=torch.int64, device=device)
+        # fixed-capacity GT buffers (n * max_gt rows): addresses and launch geometry never change, so a CUDA graph
+        # captured over the step stays valid when the next batch's GT is loaded
+        self.gt_boxes = torch.zeros(n * max_gt, 4, dtype=torch.float32, device=device)
+        self.gt_labels = torch.zeros(n * max_gt, dtype=torch.int64, device=device)
+        self.shape.total_gt = n * max_gt
         self.ers_generation = 0      # bumped every time the ERS buffers are rewritten
         self.bufs = N.ErdStepBuffers(
             self.cls_inds.data_ptr(), self.cls_count.data_ptr(), self.box_inds.data_ptr(),
@@ -115,29 +117,28 @@ class Plan:
         if self._meta_events[turn] is not None:
             self._meta_events[turn].synchronize()
         meta_host = self._meta_hosts[turn]
-        off = 0
+        counts = [int(b.shape[0]) for b in gt_bboxes]
+        vals, off = [], 0
+        for c in counts:                       # CSR offsets
+            vals.append(off)
+            off += c
+        vals.append(off)
         for i in range(n):
-            meta_host[i] = off
-            off += int(gt_bboxes[i].shape[0])
-            if int(gt_bboxes[i].shape[0]) > self.max_gt:
-                raise ValueError(f'image {i} has {int(gt_bboxes[i].shape[0])} GT boxes, plan capacity is {self.max_gt}')
+            if counts[i] > self.max_gt:
+                raise ValueError(f'image {i} has {counts[i]} GT boxes, plan capacity is {self.max_gt}')
             ph, pw = int(pad_shapes[i][0]), int(pad_shapes[i][1])
             if ph < 1 or pw < 1:
                 # reference: ValueError when an image has no valid anchor (gfl_head.py:613-617)
                 raise ValueError('There is no valid anchor inside the image boundary.')
-            meta_host[n + 1 + 2 * i] = ph
-            meta_host[n + 2 + 2 * i] = pw
-        meta_host[n] = off
+            vals += [ph, pw]
+        meta_host.copy_(torch.tensor(vals, dtype=torch.int32))   # one host-side copy instead of 3n element writes
         self.meta.copy_(meta_host, non_blocking=True)
         ev = self._meta_events[turn] or torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self._meta_events[turn] = ev
-        self.shape.total_gt = off
         if off > 0:
-            self.gt_boxes = torch.cat([b.reshape(-1, 4) for b in gt_bboxes]).to(
-                device=self.device, dtype=torch.float32).contiguous()
-            self.gt_labels = torch.cat([l.reshape(-1) for l in gt_labels]).to(
-                device=self.device, dtype=torch.int64).contiguous()
+            self.gt_boxes[:off].copy_(torch.cat([b.reshape(-1, 4) for b in gt_bboxes]), non_blocking=True)
+            self.gt_labels[:off].copy_(torch.cat([l.reshape(-1) for l in gt_labels]), non_blocking=True)
 
 
     def load_selection(self, cls_inds: Sequence[torch.Tensor], box_inds: Sequence[torch.Tensor]):

@@ -51,7 +51,8 @@ typedef struct ErdShape {
   int32_t level_h[ERD_MAX_LEVELS];    /* feature-map heights                                */
   int32_t level_w[ERD_MAX_LEVELS];    /* feature-map widths                                 */
   int32_t stride[ERD_MAX_LEVELS];     /* 8,16,32,64,128 (square strides)                    */
-  int32_t total_gt;                   /* number of rows of gt_boxes (sum over images)       */
+  int32_t total_gt;                   /* rows of gt_boxes a launch may cover: gt_offsets[N] of them are in use, so a
+                                       * fixed capacity works too (and keeps a captured CUDA graph valid)        */
   float anchor_scale;                 /* octave_base_scale * 2**0 = 8                       */
   float loss_weight_cls;              /* QualityFocalLoss loss_weight (1.0), beta fixed at 2 */
   float loss_weight_bbox;             /* GIoULoss loss_weight (2.0), eps 1e-6               */

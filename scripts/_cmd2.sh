@@ -1,7 +1,4 @@
-mkdir -p gpurun_out/r2v
-export ITERS=4 HANG_S=40
-timeout 80 python scripts/_dbg.py 2>&1 | grep -v Warn | tail -1
-for sf in 0 24; do for tf in 0 8; do
-echo "student_free=$sf teacher_free=$tf"
-ERD_STUDENT_FREE_SMS=$sf ERD_TEACHER_FREE_SMS=$tf timeout 80 python scripts/time_student.py 2>&1 | grep graph_step
-done; done | tee gpurun_out/r2v/sweep.txt
+mkdir -p gpurun_out/r2x
+timeout 120 python scripts/profile_api.py 2>&1 | grep -v Warn | cut -c1-150 | tee gpurun_out/r2x/profile_api.txt | head -60
+timeout 600 compute-sanitizer --tool racecheck --print-limit 400 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2x/racecheck_full.txt 2>&1
+grep "SUMMARY\|smoke ok" gpurun_out/r2x/racecheck_full.txt

@@ -55,10 +55,16 @@ def test_atss_random_many_gt(seed):
     path = ErdPath()
     batch = make_batch(3, (800, 1333), ori=40, seed=200 + seed, num_gt=(20, 60), gt_size_pow=2.5)
     for i, (g_cuda, g_or, np_c, np_o, rep) in enumerate(_atss_both(batch, path)):
-        if rep.get('topk_boundary_ties'):
-            pytest.skip('random input produced an exact distance tie (reference order is arbitrary there)')
-        assert torch.equal(g_cuda, g_or), f'image {i}: margin {rep.get("min_thr_margin")}'
-        assert np_c == np_o
+        if torch.equal(g_cuda, g_or):
+            assert np_c == np_o
+            continue
+        # never skipped: a difference is acceptable only where the reference itself is arbitrary -- an exact
+        # distance tie at the k-th candidate (torch.topk order) -- and only at anchors of the tied GTs
+        ties = rep.get('topk_boundary_ties')
+        assert ties, f'image {i}: assignment differs without a top-k tie (IoU-threshold margin {rep.get("min_thr_margin")})'
+        diff = (g_cuda != g_or).nonzero().squeeze(1)
+        print(f'image {i}: {diff.numel()} anchors differ; top-k boundary ties in the oracle: {ties[:4]}')
+        assert diff.numel() <= 2 * len(ties)
 
 
 def test_nms_dense_boxes_against_oracle_and_torchvision():
@@ -175,3 +181,40 @@ def test_every_call_sequence_gives_the_same_bits(mode):
     for a, r in zip(gc + gb, ref_gc + ref_gb):
         assert not a.isnan().any()              # every element written
         assert torch.equal(a, r)                # gradients do not depend on the launch order
+
+
+def test_cuda_graph_of_the_step_survives_new_targets():
+    """A CUDA graph captured over prepare + loss with one batch's GT must stay valid when the next batch's GT
+    (different boxes, different count) is loaded into the plan: GT buffers and launch geometry are fixed-capacity."""
+    path = ErdPath()
+    a = make_batch(3, (512, 640), ori=40, seed=61, num_gt=[2, 9, 4]).to('cuda')
+    b2 = make_batch(3, (512, 640), ori=40, seed=62, num_gt=[7, 0, 11]).to('cuda')
+    p = path.plan(a.s_cls, a.num_classes, a.ori, a.reg_max, 16)
+    g_cls = [torch.empty_like(t) for t in a.s_cls]
+    g_box = [torch.empty_like(t) for t in a.s_box]
+    losses = torch.empty(p.num_losses, device='cuda')
+
+    def step():
+        path.prepare(p, a.t_cls, a.t_box, a.s_cls, a.s_box)
+        path.loss_fwd_bwd(p, a.t_cls, a.t_box, a.s_cls, a.s_box, g_cls, g_box, losses, 1.0)
+    p.set_targets(a.gt_bboxes, a.gt_labels, a.pad_shapes)
+    step()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    p.set_targets(b2.gt_bboxes, b2.gt_labels, b2.pad_shapes)   # new GT, same tensors otherwise
+    graph.replay()
+    torch.cuda.synchronize()
+    got = (losses.clone(), p.gt_inds.clone(), [t.clone() for t in g_cls + g_box])
+    step()                                                     # the same thing launched eagerly
+    torch.cuda.synchronize()
+    assert torch.equal(got[1], p.gt_inds) and int((p.gt_inds > 0).sum()) > 0
+    assert torch.equal(got[0], losses)
+    for x, y in zip(got[2], g_cls + g_box):
+        assert torch.equal(x, y)
