@@ -1,4 +1,4 @@
-mkdir -p gpurun_out/r2x
-timeout 120 python scripts/profile_api.py 2>&1 | grep -v Warn | cut -c1-150 | tee gpurun_out/r2x/profile_api.txt | head -60
-timeout 600 compute-sanitizer --tool racecheck --print-limit 400 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2x/racecheck_full.txt 2>&1
-grep "SUMMARY\|smoke ok" gpurun_out/r2x/racecheck_full.txt
+mkdir -p gpurun_out/r2y
+timeout 900 python -m pytest tests -m gpu -x -q --timeout=400 2>&1 | grep -v Warn | tail -5 | tee gpurun_out/r2y/pytest.txt
+timeout 120 python scripts/profile_api.py 2>&1 | grep -v Warn | head -3 | tee gpurun_out/r2y/profile_api.txt
+bash scripts/sanitize.sh gpurun_out/r2y/sanitizer
