@@ -30,6 +30,11 @@ class ErdSizes(C.Structure):
                 ('workspace_bytes', C.c_size_t)]
 
 
+class ErdPredictConfig(C.Structure):
+    _fields_ = [('nms_pre', C.c_int32), ('max_per_img', C.c_int32), ('score_thr', C.c_float),
+                ('iou_threshold', C.c_float), ('min_bbox_size', C.c_float)]
+
+
 class ErdStepBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('cls_inds', 'cls_count', 'box_inds', 'box_count', 'thr',
                                            'sel_flags', 'gt_inds', 'num_pos', 'keep', 'keep_count', 'avg')]
@@ -45,6 +50,8 @@ SIGNATURES = {
     'erd_last_error': [],
     'erd_sizes': [_SH, C.POINTER(ErdSizes)],
     'erd_workspace_init': [_SH, _P, _P],
+    'erd_predict_workspace_bytes': [_SH, C.POINTER(ErdPredictConfig), C.POINTER(C.c_size_t)],
+    'erd_predict': [_SH, C.POINTER(ErdPredictConfig), PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P],
     'erd_workspace_field': [_SH, _P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_size_t)],
     'erd_create': [C.POINTER(_P)],
     'erd_destroy': [_P],

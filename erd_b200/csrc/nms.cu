@@ -361,14 +361,11 @@ __global__ void __launch_bounds__(kSortThreads) nms_order_kernel(Geo g, Workspac
   for (int r = threadIdx.x; r < M; r += kSortThreads) out[r] = (int)(unsigned int)(s_key[r] & 0xffffffffull);
 }
 
-cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_inds, const int32_t* box_count,
-                       const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count, uint8_t* sel_flags,
-                       cudaStream_t st, cudaEvent_t prepped, cudaEvent_t resolved) {
-  ERD_LAUNCH(kKNmsSort, st, (nms_prep_kernel<<<g.n_img, kPrepThreads, 0, st>>>(g, ws, box_inds, box_count, pad_hw)));
-  if (prepped) {   // lets the caller start DRAM-heavy work only after the latency-bound gathers
-    cudaError_t e = cudaEventRecord(prepped, st);
-    if (e != cudaSuccess) return e;
-  }
+// mask -> resolve -> order over boxes / scores already in ws.nms_box / ws.nms_score with clean predecessor rows
+// (the loss path's nms_prep or the inference path's merge kernel put them there)
+cudaError_t launch_nms_prepared(const Geo& g, const Workspace& ws, const int32_t* box_inds, const int32_t* box_count,
+                                float iou_thr, int32_t* keep, int32_t* keep_count, uint8_t* sel_flags, cudaStream_t st,
+                                cudaEvent_t resolved) {
   // The chain runs beside the student pass on the few SMs that pass leaves free, so the grid is sized for
   // those: each CTA loops over the image's tiles (K = 500 candidates are 36 tiles), and a launch of
   // thousands of CTAs that mostly exit at once would queue behind each other there.
@@ -399,6 +396,17 @@ cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_ind
   if (sort_smem > 200 * 1024) return cudaErrorInvalidValue;
   ERD_LAUNCH(kKNmsOrder, st, (nms_order_kernel<<<g.n_img, kSortThreads, sort_smem, st>>>(g, ws, keep, keep_count)));
   return cudaGetLastError();
+}
+
+cudaError_t launch_nms(const Geo& g, const Workspace& ws, const int32_t* box_inds, const int32_t* box_count,
+                       const int32_t* pad_hw, float iou_thr, int32_t* keep, int32_t* keep_count, uint8_t* sel_flags,
+                       cudaStream_t st, cudaEvent_t prepped, cudaEvent_t resolved) {
+  ERD_LAUNCH(kKNmsSort, st, (nms_prep_kernel<<<g.n_img, kPrepThreads, 0, st>>>(g, ws, box_inds, box_count, pad_hw)));
+  if (prepped) {   // lets the caller start DRAM-heavy work only after the latency-bound gathers
+    cudaError_t e = cudaEventRecord(prepped, st);
+    if (e != cudaSuccess) return e;
+  }
+  return launch_nms_prepared(g, ws, box_inds, box_count, iou_thr, keep, keep_count, sel_flags, st, resolved);
 }
 
 }  // namespace erd

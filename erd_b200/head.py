@@ -229,6 +229,25 @@ class GFLHeadIncrementERD(nn.Module):
         return fused_loss_by_feat(self, ori_outs, new_outs, ori_topk_cls_inds, ori_topk_bbox_inds, ori_num_classes,
                                   dist_loss_weight, batch_gt_instances, batch_img_metas)
 
+    def predict_by_feat(self, cls_scores, bbox_preds, score_factors=None, batch_img_metas=None, cfg=None,
+                        rescale: bool = False, with_nms: bool = True):
+        """base_dense_head.py:197-296 over gfl_head.py:408-502 on the device (``erd_predict``).  Returns one
+        object per image with ``bboxes`` (M,4), ``scores`` (M,), ``labels`` (M,) -- the fields of the reference's
+        InstanceData."""
+        from types import SimpleNamespace
+        from .predict import ErdPredictor
+        if not with_nms or score_factors is not None:
+            raise ValueError('erd_b200 fuses the with_nms=True path of the GFL head (no score_factors)')
+        cfg = cfg if cfg is not None else (self.test_cfg or {})
+        key = (int(cfg.get('nms_pre', 1000)), int(cfg.get('max_per_img', 100)), float(cfg.get('score_thr', 0.05)),
+               float(dict(cfg.get('nms', {})).get('iou_threshold', 0.6)), float(cfg.get('min_bbox_size', 0)))
+        if getattr(self, '_predictor_key', None) != key:
+            self._predictor, self._predictor_key = ErdPredictor(self.strides, *key), key
+        scales = [m['scale_factor'] for m in batch_img_metas] if rescale else None
+        out = self._predictor.predict_by_feat(cls_scores, bbox_preds, [m['img_shape'][:2] for m in batch_img_metas],
+                                              scales, self.reg_max)
+        return [SimpleNamespace(**d) for d in out]
+
     def loss(self, ori_outs, new_outs, batch_data_samples, topk_cls_inds, topk_cls_scores, topk_bbox_inds,
              topk_bbox_preds, ori_num_classes, dist_loss_weight, model) -> dict:
         """gfl_head_increment_erd.py:457-484 (unpack_gt_instances, models/utils/misc.py:89)."""

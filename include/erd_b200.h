@@ -212,6 +212,27 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
 size_t erd_avg_exchange_bytes(void);
 int erd_avg_exchange(float* avg, void* const* peer_bufs, int32_t rank, int32_t world, void* stream);
 
+/* --- inference post-process (next row of the scope table) ---------------------------
+ * Replaces GFLHead._predict_by_feat_single (mmdet/models/dense_heads/gfl_head.py:408-502) with
+ * filter_scores_and_topk (mmdet/models/utils/misc.py:308-354) and BaseDenseHead._bbox_post_process
+ * (mmdet/models/dense_heads/base_dense_head.py:424-486), with_nms=True, for a whole batch.
+ * cls_scores[l] (N, num_classes, H_l, W_l) logits and bbox_preds[l] (N, 4*(reg_max+1), H_l, W_l), fp32 NCHW as the
+ * head emits them; img_hw (N,2) int32 = img_meta['img_shape'][:2] (clamp limits); inv_scale (N,2) fp32 =
+ * 1 / scale_factor (w, h) for rescale=True, or NULL.  Outputs: dets (N, max_per_img, 5) = x1, y1, x2, y2, score in
+ * descending score order, labels (N, max_per_img) int32 (-1 beyond the count), num_dets (N,) int32.
+ * ErdShape: num_imgs, num_levels, num_classes, reg_max, level_h/w, stride are read.  nms_pre <= 3276. */
+typedef struct ErdPredictConfig {
+  int32_t nms_pre;        /* test_cfg.nms_pre: candidates kept per level (1000)   */
+  int32_t max_per_img;    /* test_cfg.max_per_img (100)                           */
+  float score_thr;        /* test_cfg.score_thr (0.05), strict >                  */
+  float iou_threshold;    /* test_cfg.nms.iou_threshold (0.6), class-aware NMS    */
+  float min_bbox_size;    /* test_cfg.min_bbox_size (0); < 0: no size filter      */
+} ErdPredictConfig;
+int erd_predict_workspace_bytes(const ErdShape* shape, const ErdPredictConfig* cfg, size_t* bytes);
+int erd_predict(const ErdShape* shape, const ErdPredictConfig* cfg, const float* const* cls_scores,
+                const float* const* bbox_preds, const int32_t* img_hw, const float* inv_scale, float* dets,
+                int32_t* labels, int32_t* num_dets, void* workspace, void* stream);
+
 /* Introspection for tests and diagnostics: device address and size of a named workspace array
  * ("t_slot": uint16 [N][A] stash row + 1 of each anchor; "pthr": float [N][2] provisional thresholds;
  * "t_m", "t_u": float [N][A] the teacher cache the thresholds are taken over).  ERD_ERR_BAD_SHAPE for an
