@@ -77,7 +77,7 @@ __device__ __forceinline__ void t_wait(unsigned long long* bar, uint32_t parity)
                  : "=r"(done) : "r"(t_smem(bar)), "r"(parity) : "memory");
 }
 
-constexpr int kTeacherFreeSms = 8;      // SMs left to the kernels that run beside this pass
+constexpr int kTeacherFreeSms = 24;     // SMs left to the kernels that run beside this pass
 constexpr float kSampleSigmas = 1.7f;   // provisional threshold = sample mean + this many sample std (the selection: mean + 2 std)
 
 __global__ void __launch_bounds__(kAMaxThreads, 1)
