@@ -85,6 +85,7 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ __align__(8) unsigned long long s_full[kAMaxWarps];
   int* s_stash_cnt = reinterpret_cast<int*>(s_raw + (size_t)A.stages * A.stage_bytes);   // [n_img] stash rows this CTA has used
+  double* s_samp = reinterpret_cast<double*>(s_raw + (size_t)A.stages * A.stage_bytes + (((size_t)g.n_img * sizeof(int) + 7) & ~(size_t)7));   // [n_img][5] sample sums
   // Every warp is its own pipeline over the tiles k = warp, warp + W, ... of the CTA's sequence, with
   // its own shared-memory slot: request the tile, scan it, publish its sums, wait for the image's
   // thresholds, extract the selected rows from the slot.  Warps only meet at the per-image flag.
@@ -99,6 +100,7 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < g.n_img; i += blockDim.x) s_stash_cnt[i] = 0;
+  for (int i = threadIdx.x; i < g.n_img * 5; i += blockDim.x) s_samp[i] = 0.0;
   __syncthreads();
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < g.n_img; i += blockDim.x) {
@@ -172,14 +174,19 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
     }
 #pragma unroll
     for (int i = 0; i < 5; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane < 5) {
+    if (lane < 5) {   // first into shared memory: the CTA's samples belong to one or two images
       const double v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : acc[4];
-      atomicAdd(ws.samp_acc + n * 5 + lane, v);
+      atomicAdd(&s_samp[n * 5 + lane], v);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the slot before the next bulk write
     __syncwarp();
   }
-  __threadfence();   // this warp's sums before the CTA's ticket
+  __syncthreads();
+  // one global atomic per (image, component) this CTA sampled: 88 same-address fp64 atomics per image would
+  // serialise in L2 and every warp's fence would wait for the chain
+  for (int i = threadIdx.x; i < g.n_img * 5; i += blockDim.x)
+    if (s_samp[i] != 0.0) atomicAdd(ws.samp_acc + i, s_samp[i]);
+  __threadfence();   // the sums before the CTA's ticket
   __syncthreads();
   request(warp);     // the first tile is on its way while the grid meets
   if (threadIdx.x == 0) {   // one ticket and one poller per CTA: a counter every warp of the grid hammered would serialise in L2
@@ -321,7 +328,8 @@ cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t
   if (tiles_per_img) *tiles_per_img = tiles;
   const int rows = g.ori + kBoxCh;
   A.stage_bytes = rows * kAT * (int)sizeof(float);   // a multiple of 128
-  int S = (224 * 1024 - g.n_img * (int)sizeof(int)) / A.stage_bytes;   // consumer warps == ring slots
+  const int tail_bytes = ((g.n_img * (int)sizeof(int) + 7) & ~7) + g.n_img * 5 * (int)sizeof(double);   // stash counters + sample sums
+  int S = (224 * 1024 - tail_bytes) / A.stage_bytes;   // consumer warps == ring slots
   if (S > kAMaxWarps) S = kAMaxWarps;
   if (S < 4) return cudaErrorInvalidValue;   // ori_classes too large for this tiling
   A.stages = S;
@@ -360,7 +368,7 @@ cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const size_t smem = (size_t)S * A.stage_bytes + (size_t)g.n_img * sizeof(int);
+  const size_t smem = (size_t)S * A.stage_bytes + (size_t)tail_bytes;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(teacher_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

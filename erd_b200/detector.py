@@ -2,7 +2,8 @@
 ``sel_pos`` (Elastic Response Selection) and the ``loss`` glue.
 
 Reference: ``GFLIncrementERD`` (mmdet/models/detectors/gfl_increment_erd.py:20-220).  Backbone,
-neck, teacher construction and checkpoint surgery (:67-122) are out of scope (SURVEY.md §8f);
+neck and teacher construction from a config (:95-122) are out of scope; the checkpoint
+surgery that seeds the student from the teacher (:67-93) is ``load_checkpoint_for_new_model``;
 the student / teacher networks are injected as modules so that the same ``loss`` sequence
 (:202-220) runs: teacher forward, ``sel_pos``, student forward, ``bbox_head.loss``.  This is the
 STANDALONE mirror; inside a real mmdet use ``erd_b200/mmdet_plugin.py`` (subclasses of the reference's
@@ -32,6 +33,34 @@ class GFLIncrementERD(nn.Module):
         if ori_model is not None:
             for p in ori_model.parameters():    # :115-116
                 p.requires_grad = False
+
+    def load_checkpoint_for_new_model(self, checkpoint, strict: bool = True):
+        """gfl_increment_erd.py:67-93 (`_load_checkpoint_for_new_model`): initialise the student from the teacher's
+        checkpoint -- a state dict, a ``{'state_dict': ...}`` checkpoint or a file of either -- whose classification
+        conv has ``ori_num_classes`` outputs: the rows of the new classes keep the student's own initialisation
+        (``gfl_cls.weight/bias[ori_num_classes:]`` are appended to the checkpoint's).  Keys are matched against this
+        module (``bbox_head.*`` and, when the student body is a module, ``extract_feat.*``); a ``module.`` prefix is
+        stripped as the reference does.  Returns torch's (missing, unexpected) key report."""
+        from collections import OrderedDict
+        if isinstance(checkpoint, (str, bytes)):
+            checkpoint = torch.load(checkpoint, map_location='cpu')
+        if isinstance(checkpoint, OrderedDict):
+            state = checkpoint
+        elif isinstance(checkpoint, dict) and 'state_dict' in checkpoint:
+            state = checkpoint['state_dict']
+        else:
+            raise RuntimeError('No state_dict found in checkpoint')                                       # :75-77
+        if list(state.keys())[0].startswith('module.'):                                                   # :79-81
+            state = {k[7:]: v for k, v in state.items()}
+        state = dict(state)
+        head = self.bbox_head
+        for name, own in (('bbox_head.gfl_cls.weight', head.gfl_cls.weight), ('bbox_head.gfl_cls.bias', head.gfl_cls.bias)):
+            old = state[name]
+            if old.shape[0] != self.ori_num_classes:
+                raise RuntimeError(f'{name}: checkpoint has {old.shape[0]} classes, ori_num_classes is {self.ori_num_classes}')
+            added = own.detach()[self.ori_num_classes:].to(old)                                            # :83-84
+            state[name] = torch.cat((old, added), dim=0)                                                  # :85-88
+        return self.load_state_dict(state, strict=strict)
 
     def sel_pos(self, cls_scores: Sequence[Tensor], bbox_preds: Sequence[Tensor]):
         """gfl_increment_erd.py:165-200.  Returns (topk_cls_inds, topk_cls_scores,

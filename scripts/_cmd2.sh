@@ -1,3 +1,6 @@
-mkdir -p gpurun_out/r3b
-for tf in 20 24 28 36; do for sf in 20 24 28; do echo "teacher_free=$tf student_free=$sf"; ERD_TEACHER_FREE_SMS=$tf ERD_STUDENT_FREE_SMS=$sf REPS=2 timeout 80 python scripts/time_student.py 2>&1 | grep graph_step | cut -c1-120; done; done | tee gpurun_out/r3b/sweep.txt
-SHIFT=0.5 timeout 200 python scripts/time_predict.py 2>&1 | grep -v Warn | tee gpurun_out/r3b/time_predict_few.txt
+mkdir -p gpurun_out/r3f
+export ITERS=4 HANG_S=40
+timeout 80 python scripts/_dbg.py 2>&1 | grep -v Warn | tail -1
+timeout 80 python scripts/stash_stats.py 2>&1 | grep -v Warn | tail -1
+REPS=3 timeout 80 python scripts/time_student.py 2>&1 | grep graph_step | tee gpurun_out/r3f/time800.txt
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:teacher_pass -s 3 -c 1 -o gpurun_out/r3f/teacher -f python scripts/time_student.py > gpurun_out/r3f/ncu.log 2>&1

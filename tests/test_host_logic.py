@@ -110,3 +110,28 @@ def test_peer_exchange_declines_without_a_process_group():
     from erd_b200.dist_utils import PeerAvgExchange
     import torch
     assert PeerAvgExchange.create(None, torch.device('cpu')) is None
+
+
+def test_checkpoint_surgery_expands_the_cls_head():
+    """gfl_increment_erd.py:67-93: the teacher checkpoint (40-class cls conv) seeds the 80-class student; the 40 new
+    rows keep the student's own initialisation; a 'module.' prefix (DDP checkpoint) is stripped."""
+    import torch
+    from collections import OrderedDict
+    from erd_b200.detector import GFLIncrementERD
+    from erd_b200.head import GFLHeadIncrementERD
+    torch.manual_seed(0)
+    teacher_head = GFLHeadIncrementERD(40, 16, stacked_convs=1, feat_channels=16,
+                                       norm_cfg=dict(type='GN', num_groups=4, requires_grad=True))
+    student_head = GFLHeadIncrementERD(80, 16, stacked_convs=1, feat_channels=16,
+                                       norm_cfg=dict(type='GN', num_groups=4, requires_grad=True))
+    det = GFLIncrementERD(student_head, 40)
+    own_w, own_b = student_head.gfl_cls.weight.detach().clone(), student_head.gfl_cls.bias.detach().clone()
+    ckpt = dict(state_dict=OrderedDict(('module.bbox_head.' + k, v.clone()) for k, v in teacher_head.state_dict().items()))
+    missing, unexpected = det.load_checkpoint_for_new_model(ckpt, strict=True)
+    assert not missing and not unexpected
+    assert torch.equal(student_head.gfl_cls.weight[:40], teacher_head.gfl_cls.weight)
+    assert torch.equal(student_head.gfl_cls.bias[:40], teacher_head.gfl_cls.bias)
+    assert torch.equal(student_head.gfl_cls.weight[40:], own_w[40:]) and torch.equal(student_head.gfl_cls.bias[40:], own_b[40:])
+    assert torch.equal(student_head.gfl_reg.weight, teacher_head.gfl_reg.weight)
+    with pytest.raises(RuntimeError):
+        det.load_checkpoint_for_new_model(dict(weights=1))
