@@ -83,9 +83,7 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->ers_part = (double*)take((size_t)g.n_img * tiles32 * 4 * 8);
   ws->t_stash = (float*)take((size_t)g.n_img * kStashRows * stash_pitch(g.ori) * 4);
   ws->t_slot = (unsigned short*)take(NA * 2);
-  ws->pthr = (float*)take((size_t)g.n_img * 2 * 4);
-  ws->samp_acc = (double*)take((size_t)g.n_img * 5 * 8);
-  ws->samp_ticket = (unsigned int*)take((size_t)g.n_img * 4);
+  ws->pthr_state = (unsigned int*)take(4 * 4);
   ws->atss_key = (unsigned long long*)take(NA * 8);
   ws->pos_list = (int2*)take(NA * 8);
   ws->pos_counter = (int*)take((size_t)g.n_img * 4);
@@ -182,7 +180,7 @@ int erd_workspace_field(const ErdShape* shape, void* wsp, const char* name, void
   carve(g, wsp, &ws);
   const size_t NA = (size_t)g.n_img * g.A;
   if (!strcmp(name, "t_slot")) { *ptr = ws.t_slot; *bytes = NA * 2; }
-  else if (!strcmp(name, "pthr")) { *ptr = ws.pthr; *bytes = (size_t)g.n_img * 8; }
+  else if (!strcmp(name, "pthr_state")) { *ptr = ws.pthr_state; *bytes = 16; }
   else if (!strcmp(name, "t_m")) { *ptr = ws.t_m; *bytes = NA * 4; }
   else if (!strcmp(name, "t_u")) { *ptr = ws.t_u; *bytes = NA * 4; }
   else return fail(ERD_ERR_BAD_SHAPE, "erd_workspace_field: unknown field");

@@ -54,14 +54,13 @@ struct Workspace {
   float4* t_dist;                 // [N][A] teacher softmax-integral distances (l,t,r,b), bin units
   double* ers_part;               // [N][tiles of 32 anchors][4] per-tile sums: m, m^2, u, u^2
   // The stash: the teacher's logit column [ori + 68, padded to 4] of every anchor that clears the
-  // PROVISIONAL thresholds (estimated from a sample of the image before the streaming pass), written by
+  // PROVISIONAL thresholds (the lowest mean + 1.7 std any image of the PREVIOUS call had), written by
   // the teacher pass while the tile is in shared memory, so that the student pass does not gather those
   // columns from the NCHW tensors again (64 B of DRAM per 4 B used).  Region [n][cta][kStashPerCta].
   float* t_stash;
   unsigned short* t_slot;         // [N][A] stash row of the anchor + 1, 0: not stashed (read the tensors)
-  float* pthr;                    // [N][2] provisional thresholds (class response, box)
-  double* samp_acc;               // [N][5] sample sums m, m^2, u, u^2, count (zero between steps)
-  unsigned int* samp_ticket;      // [1] warps of the teacher pass that have finished the sampling phase (zero between steps)
+  unsigned int* pthr_state;       // [4] provisional thresholds as ~ordered_bits(float), 0 = none yet: [0..1] in use by the
+                                  // teacher pass (class response, box), [2..3] being collected by the flags kernel
   unsigned long long* atss_key;   // [N][A] packed (iou bits << 32 | ~gt) argmax table
   int2* pos_list;                 // [N][A] (anchor, global GT row) of the assigned anchors (unordered)
   int* pos_counter;               // [N] running length of pos_list (zero between steps)
@@ -126,6 +125,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// float <-> unsigned int whose unsigned order is the floats' order
+__device__ __forceinline__ unsigned int ordered_bits(float x) {
+  const unsigned int u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -61,23 +61,16 @@ __global__ void __launch_bounds__(kFlagThreads) ers_flags_kernel(Geo g, Workspac
       if (var < 0.0) var = 0.0;
       const float t = __fadd_rn((float)mean, __fmul_rn(2.0f, (float)sqrt(var)));
       s_thr[threadIdx.x] = t;
-      if (blockIdx.x == 0) thr_out[n * 2 + threadIdx.x] = t;
+      if (blockIdx.x == 0) {
+        thr_out[n * 2 + threadIdx.x] = t;
+        // what the NEXT call's teacher pass stashes by: the lowest mean + 1.7 std over this call's images
+        // (kept as ~ordered_bits, so 0 = nothing yet and "lowest" is an atomicMax)
+        atomicMax(ws.pthr_state + 2 + threadIdx.x, ~ordered_bits((float)(mean + 1.7 * sqrt(var))));
+      }
     }
     __syncthreads();
   }
   const float thr_c = s_thr[0], thr_b = s_thr[1];
-  if (blockIdx.x == 0) {   // the teacher pass's sampling sums: publish its provisional thresholds (diagnostics), clean up
-    if (threadIdx.x < 2) {
-      const double* a = ws.samp_acc + n * 5;
-      const double cnt = a[4], s1 = a[threadIdx.x * 2], s2 = a[threadIdx.x * 2 + 1];
-      double var = (s2 - s1 * s1 / cnt) / (cnt - 1.0);
-      if (!(var > 0.0)) var = 0.0;
-      ws.pthr[n * 2 + threadIdx.x] = (float)(s1 / cnt + 1.7 * sqrt(var));
-    }
-    __syncthreads();
-    if (threadIdx.x < 5) ws.samp_acc[n * 5 + threadIdx.x] = 0.0;
-    if (n == 0 && threadIdx.x == 0) *ws.samp_ticket = 0u;
-  }
   const int a0 = (blockIdx.x * kFlagThreads + threadIdx.x) * kFlagPer;
   const float* m = ws.t_m + (size_t)n * g.A;
   const float* u = ws.t_u + (size_t)n * g.A;
@@ -110,6 +103,16 @@ __global__ void __launch_bounds__(kFlagThreads) ers_flags_kernel(Geo g, Workspac
     for (int w = 0; w < kFlagThreads / 32; ++w) { tc += s_c[w]; tb += s_b[w]; }
     if (tc) atomicAdd(cls_count + n, tc);
     if (tb) atomicAdd(box_count + n, tb);
+    // the grid's last block hands the collected provisional thresholds to the next call and starts a new collection
+    __threadfence();
+    if (atomicAdd(ws.counters + 4, 1u) == gridDim.x * gridDim.y - 1) {
+      __threadfence();
+      for (int i = 0; i < 2; ++i) {
+        ws.pthr_state[i] = ((volatile unsigned int*)ws.pthr_state)[2 + i];
+        ws.pthr_state[2 + i] = 0u;
+      }
+      ws.counters[4] = 0u;
+    }
   }
 }
 

@@ -58,14 +58,6 @@ struct PredictArgs {
   int lvl_tile_start[kLevels + 1];
 };
 
-__device__ __forceinline__ unsigned int ordered_bits(float x) {
-  const unsigned int u = __float_as_uint(x);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float from_ordered_bits(unsigned int k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
 // ----------------------------------------------------------------------------- collect
 constexpr int kCollectThreads = 128;
 

@@ -19,11 +19,12 @@
 // The stash.  The student pass needs the teacher's whole logit column of every ERS anchor (class-
 // response L2, box-distribution KL), which in NCHW costs a 64-byte DRAM access per 4-byte element.
 // The scan has that column in shared memory, but the thresholds that decide the selection only exist
-// once the whole image has been scanned.  So the kernel opens with a sampling phase: the warps first scan
-// every 16th tile of each image for m and u only, add up fp64 sums with atomics and the CTAs meet at a grid-wide
-// ticket (the grid is at most one CTA per SM, so all CTAs are resident or become so without depending on
-// anything this kernel produces); mean + 1.7 std of the sample are the PROVISIONAL thresholds, and the
-// scan copies the column of every anchor that clears them to a compact stash row.  The estimate only
+// once the whole image has been scanned.  So the stash works with PROVISIONAL thresholds: the lowest
+// mean + 1.7 std (the selection is mean + 2 std) any image of the PREVIOUS call had, which the flags kernel
+// leaves behind -- the teacher is frozen and consecutive batches are drawn from the same data, so the
+// estimate is good, and it costs nothing (a sampling pass over this call's images in front of the scan was
+// measured: +12..15 us on the critical path for the same hit rate).  The scan copies the column of every
+// anchor that clears them to a compact stash row.  The estimate only
 // decides what is stashed, never what is selected: an ERS anchor that was not stashed is read from
 // the tensors by the student pass as before, so results do not depend on the estimate.
 #include <cuda.h>
@@ -46,7 +47,6 @@ struct TeacherArgs {
   int lvl_tile_start[kLevels + 1];   // prefix of ceil(hw / kAT)
   int use_tma[kLevels];
   int stash_pitch;                   // floats per stash row
-  int sample_stride, samples_per_img;   // the sampling phase takes tiles 0, stride, 2 stride, ... of every image
 };
 
 struct __align__(64) TeacherMaps {
@@ -78,14 +78,12 @@ __device__ __forceinline__ void t_wait(unsigned long long* bar, uint32_t parity)
 }
 
 constexpr int kTeacherFreeSms = 24;     // SMs left to the kernels that run beside this pass
-constexpr float kSampleSigmas = 1.7f;   // provisional threshold = sample mean + this many sample std (the selection: mean + 2 std)
 
 __global__ void __launch_bounds__(kAMaxThreads, 1)
 teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ TeacherMaps maps) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ __align__(8) unsigned long long s_full[kAMaxWarps];
   int* s_stash_cnt = reinterpret_cast<int*>(s_raw + (size_t)A.stages * A.stage_bytes);   // [n_img] stash rows this CTA has used
-  double* s_samp = reinterpret_cast<double*>(s_raw + (size_t)A.stages * A.stage_bytes + (((size_t)g.n_img * sizeof(int) + 7) & ~(size_t)7));   // [n_img][5] sample sums
   // Every warp is its own pipeline over the tiles k = warp, warp + W, ... of the CTA's sequence, with
   // its own shared-memory slot: request the tile, scan it, publish its sums, wait for the image's
   // thresholds, extract the selected rows from the slot.  Warps only meet at the per-image flag.
@@ -100,7 +98,6 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < g.n_img; i += blockDim.x) s_stash_cnt[i] = 0;
-  for (int i = threadIdx.x; i < g.n_img * 5; i += blockDim.x) s_samp[i] = 0.0;
   __syncthreads();
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < g.n_img; i += blockDim.x) {
@@ -148,75 +145,16 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
   };
 
   uint32_t ph = 0;
-  // ---- sampling phase: m and u of every sample_stride-th tile of each image -> ws.samp_acc[n][5]
-  for (int si = blockIdx.x * W + warp; si < A.samples_per_img * g.n_img; si += gridDim.x * W) {
-    const int n = si / A.samples_per_img;
-    const int t = n * A.tiles_per_img + (si - n * A.samples_per_img) * A.sample_stride;
-    const ATile b = a_tile(g, A, t);
-    request_tile(b);
-    t_wait(full, ph);
-    ph ^= 1u;
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    const float* col = data + lane;
-    float best = -INFINITY, u = -INFINITY;
-#pragma unroll 8
-    for (int c = 0; c < ori; ++c) best = fmaxf(best, col[c * kAT]);
-#pragma unroll 17
-    for (int r = 0; r < kBoxCh; ++r) u = fmaxf(u, col[(ori + r) * kAT]);
-    const float m = sigmoid_ref(best);
-    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    if (lane < b.cnt) {
-      acc[0] = (double)m;
-      acc[1] = (double)m * (double)m;
-      acc[2] = (double)u;
-      acc[3] = (double)u * (double)u;
-      acc[4] = 1.0;
-    }
-#pragma unroll
-    for (int i = 0; i < 5; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane < 5) {   // first into shared memory: the CTA's samples belong to one or two images
-      const double v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : acc[4];
-      atomicAdd(&s_samp[n * 5 + lane], v);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the slot before the next bulk write
-    __syncwarp();
-  }
-  __syncthreads();
-  // one global atomic per (image, component) this CTA sampled: 88 same-address fp64 atomics per image would
-  // serialise in L2 and every warp's fence would wait for the chain
-  for (int i = threadIdx.x; i < g.n_img * 5; i += blockDim.x)
-    if (s_samp[i] != 0.0) atomicAdd(ws.samp_acc + i, s_samp[i]);
-  __threadfence();   // the sums before the CTA's ticket
-  __syncthreads();
-  request(warp);     // the first tile is on its way while the grid meets
-  if (threadIdx.x == 0) {   // one ticket and one poller per CTA: a counter every warp of the grid hammered would serialise in L2
-    atomicAdd(ws.samp_ticket, 1u);
-    unsigned int seen;
-    for (;;) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ws.samp_ticket) : "memory");
-      if (seen >= gridDim.x) break;
-      __nanosleep(64);
-    }
-  }
-  __syncthreads();
-  int thr_img = -1;
-  float pthr_c = INFINITY, pthr_b = INFINITY;
+  request(warp);
+  // provisional thresholds left behind by the previous call's flags kernel (0: none yet -> nothing is stashed)
+  const unsigned int pc_bits = __ldg(ws.pthr_state), pb_bits = __ldg(ws.pthr_state + 1);
+  const float pthr_c = pc_bits ? from_ordered_bits(~pc_bits) : INFINITY;
+  const float pthr_b = pb_bits ? from_ordered_bits(~pb_bits) : INFINITY;
   for (int k = warp;; k += W) {
     const int t = blockIdx.x + k * gridDim.x;
     if (t >= A.total_tiles) break;
     const ATile b = a_tile(g, A, t);
     const float* col = data + lane;
-    if (b.n != thr_img) {   // provisional thresholds of this image (latency hidden behind the tile's)
-      const double v = lane < 5 ? __ldcg(ws.samp_acc + b.n * 5 + lane) : 0.0;
-      const double cnt = __shfl_sync(0xffffffffu, v, 4);
-      const double s1 = __shfl_sync(0xffffffffu, v, (lane & 1) * 2), s2 = __shfl_sync(0xffffffffu, v, (lane & 1) * 2 + 1);
-      double var = (s2 - s1 * s1 / cnt) / (cnt - 1.0);
-      if (!(var > 0.0)) var = 0.0;
-      const float th = (float)(s1 / cnt + (double)kSampleSigmas * sqrt(var));   // even lanes: class response, odd lanes: box
-      pthr_c = __shfl_sync(0xffffffffu, th, 0);
-      pthr_b = __shfl_sync(0xffffffffu, th, 1);
-      thr_img = b.n;
-    }
     t_wait(full, ph);
     ph ^= 1u;
     // (the copies of an unaligned level are complete here -- they arrived on the barrier; the wait is free and
@@ -328,14 +266,12 @@ cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t
   if (tiles_per_img) *tiles_per_img = tiles;
   const int rows = g.ori + kBoxCh;
   A.stage_bytes = rows * kAT * (int)sizeof(float);   // a multiple of 128
-  const int tail_bytes = ((g.n_img * (int)sizeof(int) + 7) & ~7) + g.n_img * 5 * (int)sizeof(double);   // stash counters + sample sums
+  const int tail_bytes = (g.n_img * (int)sizeof(int) + 7) & ~7;   // stash counters
   int S = (224 * 1024 - tail_bytes) / A.stage_bytes;   // consumer warps == ring slots
   if (S > kAMaxWarps) S = kAMaxWarps;
   if (S < 4) return cudaErrorInvalidValue;   // ori_classes too large for this tiling
   A.stages = S;
   A.stash_pitch = stash_pitch(g.ori);
-  A.sample_stride = tiles / 8 < 1 ? 1 : (tiles / 8 > 16 ? 16 : tiles / 8);   // at least ~8 sample tiles per image
-  A.samples_per_img = (tiles + A.sample_stride - 1) / A.sample_stride;
   struct MapCache {
     const void* key[2 * kLevels];
     int hw[kLevels], n_img, ori;

@@ -234,7 +234,8 @@ int erd_predict(const ErdShape* shape, const ErdPredictConfig* cfg, const float*
                 int32_t* labels, int32_t* num_dets, void* workspace, void* stream);
 
 /* Introspection for tests and diagnostics: device address and size of a named workspace array
- * ("t_slot": uint16 [N][A] stash row + 1 of each anchor; "pthr": float [N][2] provisional thresholds;
+ * ("t_slot": uint16 [N][A] stash row + 1 of each anchor; "pthr_state": uint32 [4] provisional thresholds as
+ * ~ordered bits, 0 = none;
  * "t_m", "t_u": float [N][A] the teacher cache the thresholds are taken over).  ERD_ERR_BAD_SHAPE for an
  * unknown name.  No reference counterpart. */
 int erd_workspace_field(const ErdShape* shape, void* workspace, const char* name, void** ptr, size_t* bytes);
