@@ -57,11 +57,12 @@ def bytes_per_anchor(ori):
 
 
 # Per-launch figures of the two dense kernels run one at a time under ncu at the default workload (cfg1, 16
-# images): duration from profiles/r2_launches.csv (cold cache, serialised), DRAM bytes (dram__bytes_read.sum +
-# dram__bytes_write.sum) from the --set full captures in profiles/r2_ncu_full_student_teacher.csv.  A kernel
+# images, each on the 124 SMs it gets inside the step): duration and DRAM bytes (dram__bytes_read.sum +
+# dram__bytes_write.sum) from the --set full captures in profiles/r2_ncu_full_student_teacher.csv; the launch list
+# of a whole bench run is profiles/r2_launches.csv.  A kernel
 # that writes shows less than its algorithmic bytes: dirty lines still sit in the 126 MB L2 when it ends.
-NCU_ALONE_US = {'ers_scan': 43.4, 'student_pass': 87.9}
-NCU_TRAFFIC_BYTES = {'ers_scan': 169.6e6, 'student_pass': 396.5e6}
+NCU_ALONE_US = {'ers_scan': 48.7, 'student_pass': 97.1}
+NCU_TRAFFIC_BYTES = {'ers_scan': 171.5e6, 'student_pass': 396.5e6}
 
 
 def parse():

@@ -11,7 +11,7 @@ import os
 from . import build as _build
 
 MAX_LEVELS = 5
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class ErdShape(C.Structure):
@@ -65,6 +65,7 @@ SIGNATURES = {
                          C.POINTER(ErdStepBuffers), _P, _P, C.c_uint32],
     'erd_avg_exchange_bytes': [],
     'erd_avg_exchange': [_P, C.POINTER(_P), _I, _I, _P],
+    'erd_context_set_exchange': [_P, C.POINTER(_P), _I, _I],
     'erd_profile_enable': [C.c_uint],
     'erd_launch_count': [],
     'erd_profile_num_kernels': [],

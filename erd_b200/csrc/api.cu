@@ -139,6 +139,8 @@ struct ErdContext {
   cudaStream_t side;             // teacher chain: ERS scan + select -> NMS
   cudaEvent_t fork, sel_done, nms_resolved, nms_all;
   bool nms_pending;              // nms_resolved recorded by erd_step_prepare, not yet waited on
+  ExchangeInfo xchg;             // peer buffers of the avg-factor exchange (world <= 1: none)
+  bool xchg_pending;             // erd_step_prepare posted this rank's factors; the next loss call waits for the peers'
 };
 
 extern "C" {
@@ -200,11 +202,28 @@ int erd_create(ErdContext** ctx) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->nms_resolved, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->nms_all, cudaEventDisableTiming);
   c->nms_pending = false;
+  c->xchg.world = 0;
+  c->xchg.rank = 0;
+  c->xchg_pending = false;
   if (e != cudaSuccess) {
     delete c;
     return fail_cuda(e, "erd_create");
   }
   *ctx = c;
+  return ERD_OK;
+}
+
+int erd_context_set_exchange(ErdContext* c, void* const* peer_bufs, int32_t rank, int32_t world) {
+  if (!c) return fail(ERD_ERR_NULL, "erd_context_set_exchange: NULL context");
+  c->xchg.world = 0;
+  c->xchg_pending = false;
+  if (!peer_bufs || world <= 1) return ERD_OK;   // disabled
+  if (world > kMaxRanks || rank < 0 || rank >= world) return fail(ERD_ERR_BAD_SHAPE, "erd_context_set_exchange: bad rank / world");
+  for (int i = 0; i < kMaxRanks; ++i) c->xchg.peers.buf[i] = i < world ? (unsigned char*)peer_bufs[i] : nullptr;
+  for (int i = 0; i < world; ++i)
+    if (!c->xchg.peers.buf[i]) return fail(ERD_ERR_NULL, "erd_context_set_exchange: NULL peer buffer");
+  c->xchg.rank = rank;
+  c->xchg.world = world;
   return ERD_OK;
 }
 
@@ -341,6 +360,11 @@ int erd_loss_fwd_bwd(ErdContext* ctx, const ErdShape* shape, const float* const*
   a.skip_flag = (upstream && skip_if_unit_upstream) ? ws.counters + 1 : nullptr;
   a.losses = losses;
   a.dlw = dist_loss_weight;
+  a.xchg.world = 0;
+  if (ctx && ctx->xchg_pending) {   // the fused prepare posted this rank's factors: this call's student pass averages
+    a.xchg = ctx->xchg;
+    ctx->xchg_pending = false;
+  }
   // With a context the teacher chain forked by erd_step_prepare is joined where its results are
   // consumed: the ERS selection in front of the student pass, the NMS in front of the take-back.
   cudaError_t e;
@@ -414,8 +438,10 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
   if (g.total_gt > 0 && ((uintptr_t)gt_boxes & 15)) return fail(ERD_ERR_BAD_SHAPE, "gt_boxes must be 16 B aligned");
   Workspace ws;
   carve(g, wsp, &ws);
+  const bool fused_xchg = ctx->xchg.world > 1 && !(flags & ERD_PREPARE_NO_EXCHANGE);
   e = launch_assign_avg(g, ws, ptr5(s_cls), ptr5(s_box), gt_boxes, gt_labels, gt_offsets, pad_hw, b->gt_inds,
-                        b->num_pos, b->avg, main);
+                        b->num_pos, b->avg, fused_xchg ? &ctx->xchg : nullptr, main);
+  ctx->xchg_pending = fused_xchg;
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_step_prepare assignment");
 }
 

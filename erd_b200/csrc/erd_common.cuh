@@ -88,6 +88,23 @@ inline __host__ __device__ int stash_pitch(int ori) { return (ori + kBoxCh + 3) 
 inline __host__ __device__ int nms_words(int sel_cap) { return (sel_cap + 63) / 64; }
 inline __host__ __device__ int nms_nz_words(int sel_cap) { return (nms_words(sel_cap) + 63) / 64; }
 
+// ---------------------------------------------------------------- the avg-factor exchange (exchange.cu)
+// Every rank owns a symmetric buffer all peers have mapped: 2 x kMaxRanks slots (double buffered by the parity of
+// the epoch), then the epoch counter and a status word.
+constexpr int kMaxRanks = 64;
+struct ExchangeSlot {
+  float a0, a1;
+  unsigned int epoch, pad;
+};
+struct ExchangePeers {
+  unsigned char* buf[kMaxRanks];
+};
+constexpr size_t kExchangeSlotBytes = sizeof(ExchangeSlot) * 2 * kMaxRanks;   // then: epoch counter, status
+struct ExchangeInfo {   // passed by value to the kernels that post / wait; world <= 1: no exchange
+  ExchangePeers peers;
+  int rank, world;
+};
+
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ int level_of_tile(const Geo& g, int tile) {
   int l = 0;
@@ -184,6 +201,55 @@ struct Quad {
   }
 };
 
+// Post this rank's two local factors to every peer (thread t < world stores into peer t's buffer) under a new
+// epoch.  Call with the whole CTA (one __syncthreads inside); `s_epoch` is a shared-memory word.
+__device__ __forceinline__ void exchange_post(const ExchangeInfo& x, float a0, float a1, unsigned int* s_epoch) {
+  unsigned char* mine = x.peers.buf[x.rank];
+  unsigned int* ctr = reinterpret_cast<unsigned int*>(mine + kExchangeSlotBytes);
+  if (threadIdx.x == 0) {
+    *s_epoch = ctr[0] + 1u;
+    ctr[0] = *s_epoch;
+  }
+  __syncthreads();
+  const unsigned int e = *s_epoch;
+  const int t = threadIdx.x;
+  if (t < x.world) {
+    ExchangeSlot* dst = reinterpret_cast<ExchangeSlot*>(x.peers.buf[t]) + (e & 1u) * kMaxRanks + x.rank;
+    *reinterpret_cast<volatile float*>(&dst->a0) = a0;
+    *reinterpret_cast<volatile float*>(&dst->a1) = a1;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->epoch), "r"(e) : "memory");   // orders the two stores above
+  }
+}
+
+// Wait until every rank's factors of epoch `e` have arrived in this rank's buffer and average them as reduce_mean
+// does (t / W summed in rank order: identical bits on every rank).  Call with the whole CTA; `s_v` is shared memory
+// [kMaxRanks][2].  A peer that never arrives (spin bound: minutes) is fatal, not silent: the factors become NaN.
+__device__ __forceinline__ void exchange_wait(const ExchangeInfo& x, unsigned int e, float (*s_v)[2], float& avg0, float& avg1) {
+  unsigned char* mine = x.peers.buf[x.rank];
+  unsigned int* ctr = reinterpret_cast<unsigned int*>(mine + kExchangeSlotBytes);
+  const int t = threadIdx.x;
+  if (t < x.world) {
+    const ExchangeSlot* src = reinterpret_cast<const ExchangeSlot*>(mine) + (e & 1u) * kMaxRanks + t;
+    unsigned int seen = 0;
+    long long spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(&src->epoch) : "memory");
+    } while (seen != e && ++spins < (1ll << 28));
+    const bool lost = seen != e;
+    if (lost) ctr[1] = 1u;   // status word: a peer never arrived
+    s_v[t][0] = lost ? __int_as_float(0x7fc00000) : *reinterpret_cast<const volatile float*>(&src->a0);
+    s_v[t][1] = lost ? __int_as_float(0x7fc00000) : *reinterpret_cast<const volatile float*>(&src->a1);
+  }
+  __syncthreads();
+  const float w = (float)x.world;
+  avg0 = 0.f;
+  avg1 = 0.f;
+  for (int r = 0; r < x.world; ++r) {   // t.div_(world) then SUM, rank order (dist_utils.py:59-65)
+    avg0 += s_v[r][0] / w;
+    avg1 += s_v[r][1] / w;
+  }
+}
+
 // ---------------------------------------------------------------- launch accounting (profile.cu)
 enum KernelId { kKErsScan, kKErsFlags, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan, kKNmsOrder,
                 kKUpCheck, kKStudent, kKBoxFix, kNumKernels };
@@ -229,8 +295,8 @@ __device__ __forceinline__ LevelView level_view(const Geo& g, int l, int pad_h, 
 // Anchor a of image n: argmax table entry -> assigned_gt_inds (-1 invalid, 0 background, k > 0
 // = GT k-1 of the image; atss_assigner.py:236-246, gfl_head.py:613-640).  Positives are appended
 // to the image's list; returns the global GT row (>= 0) of a positive, -1 otherwise.
-__device__ __forceinline__ int atss_decode_key(const Geo& g, const Workspace& ws, int pad_h, int pad_w, int first_gt,
-                                               int32_t* __restrict__ gt_inds, int n, int a, unsigned long long key) {
+__device__ __forceinline__ int atss_decode_only(const Geo& g, const Workspace& ws, int pad_h, int pad_w, int first_gt,
+                                                int32_t* __restrict__ gt_inds, int n, int a, unsigned long long key) {
   const int l = level_of_anchor(g, a);
   const LevelView v = level_view(g, l, pad_h, pad_w);
   const int r = a - v.start;
@@ -239,11 +305,17 @@ __device__ __forceinline__ int atss_decode_key(const Geo& g, const Workspace& ws
   if (x < v.vw && y < v.vh) out = key ? (int)(0xffffffffu - (unsigned int)(key & 0xffffffffull)) + 1 : 0;
   gt_inds[(size_t)n * g.A + a] = out;
   if (key) ws.atss_key[(size_t)n * g.A + a] = 0ull;   // leave the table clean for the next step
-  if (out <= 0) return -1;
+  return out <= 0 ? -1 : first_gt + out - 1;
+}
+
+__device__ __forceinline__ int atss_decode_key(const Geo& g, const Workspace& ws, int pad_h, int pad_w, int first_gt,
+                                               int32_t* __restrict__ gt_inds, int n, int a, unsigned long long key) {
+  const int gidx = atss_decode_only(g, ws, pad_h, pad_w, first_gt, gt_inds, n, a, key);
+  if (gidx < 0) return -1;
   const int slot = atomicAdd(ws.pos_counter + n, 1);
-  ws.pos_list[(size_t)n * g.A + slot] = make_int2(a, first_gt + out - 1);
+  ws.pos_list[(size_t)n * g.A + slot] = make_int2(a, gidx);
   ws.pos_rec[(size_t)n * g.A + a].pslot = slot;
-  return first_gt + out - 1;
+  return gidx;
 }
 
 __device__ __forceinline__ int atss_decode_anchor(const Geo& g, const Workspace& ws, const int32_t* __restrict__ pad_hw,
@@ -275,7 +347,8 @@ cudaError_t launch_atss(const Geo& g, const Workspace& ws, const float* gt_boxes
 // atss_finalize + pos_prepass in one launch (the step's student-side chain is latency bound)
 cudaError_t launch_assign_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
                               const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
-                              const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos, float* avg, cudaStream_t st);
+                              const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos, float* avg,
+                              const ExchangeInfo* xchg, cudaStream_t st);   // xchg: post the factors to the peers
 cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
                        const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
                        const int32_t* gt_inds, const int32_t* num_pos, float* avg, cudaStream_t st);
@@ -304,6 +377,7 @@ struct LossArgs {
   const unsigned int* skip_flag;   // non-NULL: kernels return at once when *skip_flag == 0
   float* losses;
   float dlw;
+  ExchangeInfo xchg;   // world > 1: the student pass waits for the peers' factors the assignment prepass posted
 };
 struct LossStreams {
   cudaEvent_t sel_ready;              // may be null: ERS selection already ordered before the caller's stream

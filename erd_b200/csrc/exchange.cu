@@ -14,56 +14,17 @@
 
 namespace erd {
 
-constexpr int kMaxRanks = 64;
-
-struct ExchangeSlot {
-  float a0, a1;
-  unsigned int epoch, pad;
-};
-struct ExchangePeers {
-  unsigned char* buf[kMaxRanks];
-};
-constexpr size_t kSlotBytes = sizeof(ExchangeSlot) * 2 * kMaxRanks;   // then: epoch counter, status
-
-__global__ void __launch_bounds__(kMaxRanks) avg_exchange_kernel(float* __restrict__ avg, ExchangePeers peers, int rank,
-                                                                 int world) {
+// (structures and the post / wait halves: erd_common.cuh -- inside a fused step the assignment prepass posts and
+// the student pass waits, so that no launch of its own sits between them; this stand-alone kernel does both)
+__global__ void __launch_bounds__(kMaxRanks) avg_exchange_kernel(float* __restrict__ avg, ExchangeInfo x) {
   __shared__ unsigned int s_epoch;
   __shared__ float s_v[kMaxRanks][2];
-  unsigned char* mine = peers.buf[rank];
-  unsigned int* ctr = reinterpret_cast<unsigned int*>(mine + kSlotBytes);
+  exchange_post(x, avg[0], avg[1], &s_epoch);
+  float a0, a1;
+  exchange_wait(x, s_epoch, s_v, a0, a1);
   if (threadIdx.x == 0) {
-    s_epoch = ctr[0] + 1u;
-    ctr[0] = s_epoch;
-  }
-  __syncthreads();
-  const unsigned int e = s_epoch;
-  const int par = (int)(e & 1u);
-  const int t = threadIdx.x;
-  if (t < world) {
-    ExchangeSlot* dst = reinterpret_cast<ExchangeSlot*>(peers.buf[t]) + par * kMaxRanks + rank;
-    *reinterpret_cast<volatile float*>(&dst->a0) = avg[0];
-    *reinterpret_cast<volatile float*>(&dst->a1) = avg[1];
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->epoch), "r"(e) : "memory");
-    const ExchangeSlot* src = reinterpret_cast<const ExchangeSlot*>(mine) + par * kMaxRanks + t;
-    unsigned int seen = 0;
-    long long spins = 0;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(&src->epoch) : "memory");
-    } while (seen != e && ++spins < (1ll << 28));   // bounded: a lost peer must not hang the GPU
-    // A peer that never arrived is FATAL, not silent: both factors become NaN, so every loss of the
-    // step is NaN (CheckInvalidLossHook / the caller's own check fires), and the status word says why.
-    const bool lost = seen != e;
-    if (lost) ctr[1] = 1u;
-    s_v[t][0] = lost ? __int_as_float(0x7fc00000) : *reinterpret_cast<const volatile float*>(&src->a0);
-    s_v[t][1] = lost ? __int_as_float(0x7fc00000) : *reinterpret_cast<const volatile float*>(&src->a1);
-  }
-  __syncthreads();
-  if (t < 2) {
-    const float w = (float)world;
-    float s = 0.f;
-    for (int r = 0; r < world; ++r) s += s_v[r][t] / w;   // t.div_(world) then SUM, rank order
-    avg[t] = s;
+    avg[0] = a0;
+    avg[1] = a1;
   }
 }
 
@@ -71,15 +32,17 @@ __global__ void __launch_bounds__(kMaxRanks) avg_exchange_kernel(float* __restri
 
 extern "C" {
 
-size_t erd_avg_exchange_bytes(void) { return erd::kSlotBytes + 16; }
+size_t erd_avg_exchange_bytes(void) { return erd::kExchangeSlotBytes + 16; }
 
 int erd_avg_exchange(float* avg, void* const* peer_bufs, int32_t rank, int32_t world, void* stream) {
   if (!avg || !peer_bufs || world < 1 || world > erd::kMaxRanks || rank < 0 || rank >= world) return -2;
-  erd::ExchangePeers p;
-  for (int i = 0; i < erd::kMaxRanks; ++i) p.buf[i] = i < world ? (unsigned char*)peer_bufs[i] : nullptr;
+  erd::ExchangeInfo x;
+  for (int i = 0; i < erd::kMaxRanks; ++i) x.peers.buf[i] = i < world ? (unsigned char*)peer_bufs[i] : nullptr;
   for (int i = 0; i < world; ++i)
-    if (!p.buf[i]) return -2;
-  erd::avg_exchange_kernel<<<1, erd::kMaxRanks, 0, (cudaStream_t)stream>>>(avg, p, rank, world);
+    if (!x.peers.buf[i]) return -2;
+  x.rank = rank;
+  x.world = world;
+  erd::avg_exchange_kernel<<<1, erd::kMaxRanks, 0, (cudaStream_t)stream>>>(avg, x);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

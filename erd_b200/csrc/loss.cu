@@ -132,7 +132,7 @@ constexpr int kAssignPer = 4;   // anchors per thread: the whole grid is one wav
 __global__ void __launch_bounds__(256) assign_prepass_kernel(Geo g, Workspace ws, PosArgs A,
                                                              const int32_t* __restrict__ pad_hw,
                                                              int32_t* __restrict__ gt_inds,
-                                                             int32_t* __restrict__ num_pos) {
+                                                             int32_t* __restrict__ num_pos, ExchangeInfo xchg) {
   const int n = blockIdx.y;
   const int lane = threadIdx.x & 31;
   __shared__ double s_acc[2 * kLevels + 1];
@@ -147,21 +147,35 @@ __global__ void __launch_bounds__(256) assign_prepass_kernel(Geo g, Workspace ws
     key[i] = a < g.A ? ws.atss_key[(size_t)n * g.A + a] : 0ull;
   }
   const int pad_h = pad_hw[n * 2], pad_w = pad_hw[n * 2 + 1], first_gt = A.gt_offsets[n];
+  // decode all of the warp's 128 anchors first and collect its positives in a shared-memory list: the list is then
+  // worked off eight positives at a time, so a warp pays one round of dependent loads per eight positives (not one per
+  // 32-anchor row that happens to hold a positive) and one returning atomic for its slots in the image's list
+  __shared__ int2 s_list[256 / 32][32 * kAssignPer];
+  const int warp = threadIdx.x >> 5;
+  int cnt = 0;   // warp-uniform
 #pragma unroll
   for (int i = 0; i < kAssignPer; ++i) {
     const int a = a0 + i * 256;
-    const int gidx = a < g.A ? atss_decode_key(g, ws, pad_h, pad_w, first_gt, gt_inds, n, a, key[i]) : -1;
-    unsigned todo = __ballot_sync(0xffffffffu, gidx >= 0);
-    while (todo) {   // warp-uniform
-      // the (lane >> 2)-th positive still to do, if there is one
-      unsigned m = todo;
-      for (int k = 0; k < (lane >> 2); ++k) m &= m - 1;
-      const bool live = m != 0;
-      const int src = live ? __ffs(m) - 1 : 0;
-      const int pa = __shfl_sync(0xffffffffu, a, src);
-      const int pg = __shfl_sync(0xffffffffu, gidx, src);
-      pos_item(g, ws, A, n, live, live ? pa : 0, live ? pg : 0, lane & 3, s_acc);
-      for (int k = 0; k < 8 && todo; ++k) todo &= todo - 1;
+    const int gidx = a < g.A ? atss_decode_only(g, ws, pad_h, pad_w, first_gt, gt_inds, n, a, key[i]) : -1;
+    const unsigned m = __ballot_sync(0xffffffffu, gidx >= 0);
+    if (gidx >= 0) s_list[warp][cnt + __popc(m & ((1u << lane) - 1u))] = make_int2(a, gidx);
+    cnt += __popc(m);
+  }
+  if (cnt) {   // warp-uniform
+    int base = 0;
+    if (lane == 0) base = atomicAdd(ws.pos_counter + n, cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    for (int e = lane; e < cnt; e += 32) {   // the image's positives list and the slot of each positive
+      const int2 ent = s_list[warp][e];
+      ws.pos_list[(size_t)n * g.A + base + e] = ent;
+      ws.pos_rec[(size_t)n * g.A + ent.x].pslot = base + e;
+    }
+    for (int e0 = 0; e0 < cnt; e0 += 8) {   // lane = positive-in-round x side
+      const int e = e0 + (lane >> 2);
+      const bool live = e < cnt;
+      const int2 ent = live ? s_list[warp][e] : make_int2(0, 0);
+      pos_item(g, ws, A, n, live, ent.x, ent.y, lane & 3, s_acc);
     }
   }
   __syncthreads();
@@ -182,6 +196,9 @@ __global__ void __launch_bounds__(256) assign_prepass_kernel(Geo g, Workspace ws
     ws.pre_acc[threadIdx.x] = 0.0;
     if (threadIdx.x == 2 * kLevels) A.avg[1] = (float)v;
   }
+  __shared__ float s_avg[2];
+  __shared__ unsigned int s_epoch;
+  if (threadIdx.x == 2 * kLevels) s_avg[1] = (float)((volatile double*)ws.pre_pub)[2 * kLevels];
   if (threadIdx.x >= 32 && threadIdx.x < 64) {   // avg[0] = sum_img max(num_pos, 1) (sampling_result.py:96-100)
     long long cnt = 0;
     for (int i = lane; i < g.n_img; i += 32) {
@@ -193,8 +210,16 @@ __global__ void __launch_bounds__(256) assign_prepass_kernel(Geo g, Workspace ws
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) {
       A.avg[0] = (float)cnt;
+      s_avg[0] = (float)cnt;
       ws.counters[3] = 0u;
     }
+  }
+  // Data-parallel runs: post the two local factors to the peers right here -- the student pass waits for theirs in
+  // its prologue, so the exchange costs neither a launch nor a place on the caller's stream (reduce_mean,
+  // mmdet/utils/dist_utils.py:59-65; call sites gfl_head_increment_erd.py:390-391,406-407)
+  if (xchg.world > 1) {
+    __syncthreads();
+    exchange_post(xchg, s_avg[0], s_avg[1], &s_epoch);
   }
 }
 
@@ -305,7 +330,8 @@ cudaError_t launch_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, con
 
 cudaError_t launch_assign_avg(const Geo& g, const Workspace& ws, const Ptr5& s_cls, const Ptr5& s_box,
                               const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
-                              const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos, float* avg, cudaStream_t st) {
+                              const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos, float* avg,
+                              const ExchangeInfo* xchg, cudaStream_t st) {
   cudaError_t e = launch_atss_candidates(g, ws, gt_boxes, gt_offsets, pad_hw, st);
   if (e != cudaSuccess) return e;
   PosArgs a;
@@ -317,9 +343,12 @@ cudaError_t launch_assign_avg(const Geo& g, const Workspace& ws, const Ptr5& s_c
   a.gt_inds = gt_inds;
   a.num_pos = num_pos;
   a.avg = avg;
+  ExchangeInfo x;
+  if (xchg) x = *xchg;
+  else x.world = 0;
   ERD_LAUNCH(kKAvg, st,
              (assign_prepass_kernel<<<dim3((g.A + 256 * kAssignPer - 1) / (256 * kAssignPer), g.n_img), 256, 0, st>>>(
-                 g, ws, a, pad_hw, gt_inds, num_pos)));
+                 g, ws, a, pad_hw, gt_inds, num_pos, x)));
   return cudaGetLastError();
 }
 cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a, cudaStream_t st);   // student.cu

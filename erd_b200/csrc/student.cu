@@ -73,6 +73,7 @@ struct StudentArgs {
   const uint8_t* sel_flags;
   const int32_t* cls_count;
   const float* avg;
+  ExchangeInfo xchg;                 // world > 1: wait for the peers' factors in the prologue (posted by the assignment prepass)
   const float* upstream;
   const unsigned int* skip_flag;
   float dlw;
@@ -406,6 +407,23 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
   }
   for (int i = threadIdx.x; i < kLevels + g.n_img; i += kBThreads) s_loss[i] = 0.0;
   __syncthreads();
+  // The two normalisers.  Data-parallel runs: the mean over ranks of what the assignment prepass posted
+  // (reduce_mean, dist_utils.py:59-65) -- every CTA waits for the peers' slots itself and computes the same bits;
+  // CTA 0 also stores them for the finalize step and the caller.
+  float avg0 = A.avg[0], avg1 = A.avg[1];
+  if (A.xchg.world > 1) {
+    __shared__ float s_xv[kMaxRanks][2];
+    __shared__ unsigned int s_xe;
+    if (threadIdx.x == 0)
+      s_xe = *reinterpret_cast<volatile unsigned int*>(A.xchg.peers.buf[A.xchg.rank] + kExchangeSlotBytes);   // this step's epoch
+    __syncthreads();
+    exchange_wait(A.xchg, s_xe, s_xv, avg0, avg1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      float* out = const_cast<float*>(A.avg);
+      out[0] = avg0;
+      out[1] = avg1;
+    }
+  }
 
   if (warp >= kConsumerWarps) {
     // ================================================================== IO warp of team `team`
@@ -569,8 +587,8 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
   // team's next slot.  Loss sums travel in registers and are flushed (warp shuffle + one shared-memory
   // fp64 atomic) when the level / image of the team's tile sequence changes.
   const int team = warp / kTeamWarps, q = warp % kTeamWarps;
-  const float inv_avg1 = 1.0f / (float)((double)A.avg[0] + (double)kEps32);   // losses/utils.py:60-61
-  const float avg2 = fmaxf(A.avg[1], 1.0f);                                   // :407 clamp_(min=1)
+  const float inv_avg1 = 1.0f / (float)((double)avg0 + (double)kEps32);   // losses/utils.py:60-61
+  const float avg2 = fmaxf(avg1, 1.0f);                                   // :407 clamp_(min=1)
   const ConsumerCtx cc{g, ws, A, lane, q, (ori + kTeamWarps - 1) / kTeamWarps, (cn + kTeamWarps - 1) / kTeamWarps,
                        inv_avg1, avg2, 1.0f / g.T};
   int cur_img = -1, cur_lvl = -1;
@@ -659,6 +677,7 @@ cudaError_t launch_student(const Geo& g, const Workspace& ws, const LossArgs& a,
   A.sel_flags = a.sel_flags;
   A.cls_count = a.cls_count;
   A.avg = a.avg;
+  A.xchg = a.xchg;
   A.upstream = a.upstream;
   A.skip_flag = a.skip_flag;
   A.dlw = a.dlw;

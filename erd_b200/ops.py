@@ -174,6 +174,8 @@ class ErdPath:
         self.max_plans = 8
         self._cap: Dict[tuple, int] = {}
         self._ctx: Dict[int, C.c_void_p] = {}
+        self._fused_exchange: Dict[int, bool] = {}   # device -> the context posts / waits inside the step's kernels
+        self._posted = False                         # the last prepare() posted this rank's factors
 
     def _context(self, device) -> C.c_void_p:
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -227,6 +229,7 @@ class ErdPath:
                                          p.num_pos.data_ptr(), p.ws.data_ptr(), _stream()), 'erd_atss_assign')
 
     def avg_factors(self, p: Plan, s_cls, s_box):
+        self._posted = False   # fresh local factors: a following reduce_avg has to reduce them
         N.check(self.lib.erd_avg_factors(C.byref(p.shape), _ptrs(s_cls), _ptrs(s_box), p.gt_boxes.data_ptr(),
                                          p.gt_labels.data_ptr(),
                                          p.gt_offsets.data_ptr(), p.gt_inds.data_ptr(), p.num_pos.data_ptr(),
@@ -238,9 +241,25 @@ class ErdPath:
                                          p.keep_count.data_ptr(), p.sel_flags.data_ptr(), p.ws.data_ptr(),
                                          _stream()), 'erd_teacher_nms')
 
+    def _ensure_exchange(self, device) -> bool:
+        """Give the device's context the peer buffers of the avg-factor exchange (first call: a collective
+        rendezvous, outside any graph capture).  True when the exchange is fused into the step's kernels."""
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in self._fused_exchange:
+            ex = peer_exchange(self.lib, device)
+            if ex is not None:
+                N.check(self.lib.erd_context_set_exchange(self._context(device), ex.peers, ex.rank, ex.world_size),
+                        'erd_context_set_exchange')
+            self._fused_exchange[idx] = ex is not None
+        return self._fused_exchange[idx]
+
     def reduce_avg(self, p: Plan):
-        """reduce_mean of both normalisers (dist_utils.py:59-65) in one 8-byte exchange: a single
-        kernel over NVLink peer memory when the ranks share a node, else one NCCL all-reduce."""
+        """reduce_mean of both normalisers (dist_utils.py:59-65) in one 8-byte exchange.  After a fused
+        ``prepare`` on one node nothing is left to do here: the assignment kernel has posted this rank's factors
+        to the peers and the student pass averages them in its prologue.  Otherwise: a single kernel over NVLink
+        peer memory when the ranks share a node, else one NCCL all-reduce."""
+        if self._posted:
+            return
         ex = peer_exchange(self.lib, p.device)
         if ex is not None:
             ex.reduce_mean_(p.avg)
@@ -260,6 +279,7 @@ class ErdPath:
 
     # ---- fused step -------------------------------------------------------------------
     def prepare(self, p: Plan, t_cls, t_box, s_cls, s_box, ers_done: bool = False):
+        self._posted = self._ensure_exchange(p.device)
         N.check(self.lib.erd_step_prepare(
             self._context(p.device), C.byref(p.shape), _ptrs(t_cls), _ptrs(t_box), _ptrs(s_cls), _ptrs(s_box),
             p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(),

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define ERD_MAX_LEVELS 5
-#define ERD_ABI_VERSION 4
+#define ERD_ABI_VERSION 5
 
 typedef enum ErdStatus {
   ERD_OK = 0,
@@ -199,6 +199,8 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
 /* flags for erd_step_prepare */
 #define ERD_PREPARE_ERS_DONE 1u /* erd_ers_select already ran on these teacher tensors (sel_pos);
                                    its lists, counts, sel_flags and the teacher cache are reused */
+#define ERD_PREPARE_NO_EXCHANGE 2u /* do not post the avg factors to the peers even if the context has an
+                                      exchange (the caller reduces buf->avg itself before erd_loss_fwd_bwd) */
 
 /* reduce_mean of the two avg factors (mmdet/utils/dist_utils.py:59-65, call sites
  * gfl_head_increment_erd.py:390-391,406-407) over NVLink peer memory, for one process per GPU
@@ -211,6 +213,13 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
  * of the step is NaN, and word [erd_avg_exchange_bytes()/4 - 3] of the own buffer becomes 1. */
 size_t erd_avg_exchange_bytes(void);
 int erd_avg_exchange(float* avg, void* const* peer_bufs, int32_t rank, int32_t world, void* stream);
+/* The same exchange WITHOUT a launch of its own, for the fused step: once the context knows the peer buffers,
+ * erd_step_prepare's assignment kernel posts this rank's factors to the peers from its last block, and the student
+ * pass of the next erd_loss_fwd_bwd(ctx, ...) waits for the peers' factors in its prologue, averages them
+ * (identical bits on every rank) and also WRITES the means into avg[0..1] for the caller.  The exchange then sits on
+ * no stream's critical path.  peer_bufs as above; world <= 1 or NULL disables it.  Collective per step like
+ * erd_avg_exchange; do not mix the two on the same buffers within a step. */
+int erd_context_set_exchange(ErdContext* ctx, void* const* peer_bufs, int32_t rank, int32_t world);
 
 /* --- inference post-process (next row of the scope table) ---------------------------
  * Replaces GFLHead._predict_by_feat_single (mmdet/models/dense_heads/gfl_head.py:408-502) with
