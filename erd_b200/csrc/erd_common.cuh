@@ -256,7 +256,7 @@ enum KernelId { kKErsScan, kKErsFlags, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 // Developer build only (-DERD_DEV_ABLATE): ERD_ABLATE=<mask> skips kernels by id to measure what
-// each one costs inside the full schedule (scripts/ablate.sh).  Results are garbage when set.
+// each one costs inside the full schedule.  Results are garbage when set.
 #ifdef ERD_DEV_ABLATE
 bool ablated(int id);
 #define ERD_ABLATED(id) ::erd::ablated(id)
