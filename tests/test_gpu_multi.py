@@ -1,4 +1,5 @@
-"""Multi-GPU parity of the path's one collective (skipped on a single-GPU box)."""
+"""Multi-GPU parity of the path's one collective -- stand-alone and fused into the step, the latter against the oracle with
+world-averaged factors (skipped on a single-GPU box; bench.py --gpus N asserts the factors there)."""
 import os
 import subprocess
 import sys
