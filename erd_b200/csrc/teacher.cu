@@ -12,8 +12,8 @@
 // Structure: one CTA per SM, up to 16 warps, each its own pipeline with its own shared-memory slot
 // for one tile of 32 anchors -- [ori x 32] class logits and [68 x 32] box logits, two 2-D TMA
 // loads (cp.async.bulk.tensor), one anchor per lane: request, wait, scan, publish, request the
-// next.  Nothing synchronises the warps.  The loads carry an L2 evict_last hint: the student pass
-// comes back for the rows of the selected anchors, and 126 MB of L2 hold most of the teacher.
+// next.  Nothing synchronises the warps.  The loads carry an L2 evict_first hint: the tensors are
+// streamed once (the student pass reads the stash, not these lines).
 // Levels whose rows are not 16-byte aligned come in as 4-byte cp.async copies.
 //
 // The stash.  The student pass needs the teacher's whole logit column of every ERS anchor (class-
@@ -105,7 +105,7 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
       A.box_count[i] = 0;
     }
   unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));   // the student pass comes back for rows of these lines
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));   // streamed once: the student pass reads the stash, not these lines
   float* data = reinterpret_cast<float*>(s_raw + (size_t)warp * A.stage_bytes);
   unsigned long long* full = &s_full[warp];
 
