@@ -390,6 +390,9 @@ def run_ours(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {'value': world * n * A * e_steps / float(dt.item()), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                'd2h_bytes_per_step': plan.num_losses * 4, 'steps': e_steps,
+               # the copies are what this number measures: per-rank host->device rate over the whole step (N ranks share
+               # the host's memory and PCIe root complexes, which is why e2e does not scale like `value`)
+               'h2d_gbs_per_rank': h2d * e_steps / float(dt.item()) / 1e9,
                'api': 'GFLIncrementERD.sel_pos + GFLHeadIncrementERD.loss_by_feat + backward, pinned host tensors'}
 
     if world > 1:
