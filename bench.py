@@ -61,8 +61,8 @@ def bytes_per_anchor(ori):
 # dram__bytes_write.sum) from the --set full captures in profiles/r2_ncu_full_student_teacher.csv; the launch list
 # of a whole bench run is profiles/r2_launches.csv.  A kernel
 # that writes shows less than its algorithmic bytes: dirty lines still sit in the 126 MB L2 when it ends.
-NCU_ALONE_US = {'ers_scan': 48.7, 'student_pass': 97.1}
-NCU_TRAFFIC_BYTES = {'ers_scan': 171.5e6, 'student_pass': 396.5e6}
+NCU_ALONE_US = {'ers_scan': 47.8, 'student_pass': 93.2}
+NCU_TRAFFIC_BYTES = {'ers_scan': 161.8e6, 'student_pass': 368.5e6}
 
 
 def parse():
