@@ -218,3 +218,35 @@ def test_cuda_graph_of_the_step_survives_new_targets():
     assert torch.equal(got[0], losses)
     for x, y in zip(got[2], g_cls + g_box):
         assert torch.equal(x, y)
+
+
+def test_stash_hits_and_misses_give_the_same_bits():
+    """The teacher pass stashes by provisional thresholds left by the PREVIOUS call; whatever they are -- none (first
+    call), well matched (same distribution), too low (flooding the stash) or too high (nothing stashed, every ERS
+    column gathered from the tensors) -- the step's results must be bit-identical to a fresh plan's."""
+    import torch
+    iid = make_batch(2, (480, 640), ori=40, seed=71, mode='gaussian', gt_size_pow=2.0).to('cuda')
+    planted = make_batch(2, (480, 640), ori=40, seed=72, mode='trained', gt_size_pow=2.0).to('cuda')
+
+    def run(path, b):
+        p, losses, g_cls, g_box = path.step(b.t_cls, b.t_box, b.s_cls, b.s_box, b.gt_bboxes, b.gt_labels, b.pad_shapes,
+                                            b.num_classes, b.ori, b.reg_max)
+        torch.cuda.synchronize()
+        slot = p.workspace_field('t_slot', torch.int16).view(b.num_imgs, -1).int() & 0xffff
+        sel = (p.sel_flags & 3) != 0
+        hit = float((sel & (slot != 0)).sum()) / max(int(sel.sum()), 1)
+        return (losses.clone(), [t.clone() for t in g_cls + g_box], p.sel_flags.clone() & 3, p.keep_count.clone()), hit
+
+    fresh = {name: run(ErdPath(), b)[0] for name, b in (('iid', iid), ('planted', planted))}
+    path = ErdPath()
+    hits = []
+    for name, b in (('iid', iid), ('iid', iid), ('planted', planted), ('planted', planted), ('iid', iid), ('iid', iid)):
+        got, hit = run(path, b)
+        hits.append(round(hit, 3))
+        want = fresh[name]
+        assert torch.equal(got[0], want[0]), (name, hits)
+        assert all(torch.equal(x, y) for x, y in zip(got[1], want[1])), (name, hits)
+        assert torch.equal(got[2], want[2]) and torch.equal(got[3], want[3])
+    print('stash hit rates over the sequence:', hits)
+    assert hits[0] == 0.0 and hits[1] == 1.0      # nothing to go by on the first call, a perfect estimate on the second
+    assert hits[4] < 0.5 and hits[5] == 1.0       # planted -> iid: the estimate is too high once, then it has adapted
