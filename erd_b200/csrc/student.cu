@@ -56,7 +56,8 @@ struct __align__(32) TileHeader {
   PosRec rec[kStageItems];          // records of the tile's first positives (index: rec_of[item])
   float kd[kBT];                    // weighted KL of the items that are box candidates (consumers -> IO warp)
   int n, l, hw0, cnt;               // the tile: image, level, first anchor of the level, anchors
-  int n_items, cls_k, tma, pad0;    // cls_k: K_cls of the tile's image (class-response normaliser)
+  int n_items, cls_k, tma;          // cls_k: K_cls of the tile's image (class-response normaliser)
+  float inv_kc;                     // 1 / (K_cls * ori)
   unsigned char role[kBT];
   unsigned char item_col[kBT];      // special columns of the tile, ascending
   unsigned char col_item[kBT];      // column -> its item index
@@ -157,7 +158,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
 // `tb` / `tbs`: the teacher's box column of this anchor (staged in the slot: stride 1; global: stride H*W).
 __device__ __forceinline__ void item_box_rows(const Geo& g, const Workspace& ws, const StudentArgs& A, const BTile& b,
                                               float* box, const TileHeader* hd, float* hd_kd, const float* tb, size_t tbs,
-                                              int it, int icol, int hwI, bool is_pos, bool is_cand, float w_kd, float avg2,
+                                              int it, int icol, int hwI, bool is_pos, bool is_cand, float w_kd, const float (&k4)[4],
                                               float inv_T, size_t ga0, int lane) {
   constexpr int pitch = kBT;
   const int side = lane >> 3, bb = lane & 7;
@@ -213,10 +214,10 @@ __device__ __forceinline__ void item_box_rows(const Geo& g, const Workspace& ws,
     }
     kl = warp_sum(kl);   // over the four sides
     const float kT = g.T;
-    const float scale = upstream_of(A.upstream, acc_dbox(g, b.n)) * A.dlw * g.w_ld / 4.0f * (kT * kT / (float)kBins) / kT;
+    const float scale = upstream_of(A.upstream, acc_dbox(g, b.n)) * k4[0];   // dlw * w_ld / 4 * (T^2 / bins) / T
 #pragma unroll
     for (int i = 0; i < 3; ++i) out[i] *= scale;
-    if (lane == 0) hd_kd[it] = w_kd * (kl / (float)kBins * (kT * kT));   // .mean(1) * T*T; the store warp files it
+    if (lane == 0) hd_kd[it] = w_kd * (kl * k4[1]);   // .mean(1) * T*T; the IO warp files it
   }
   if (is_pos) {   // GIoU + DFL rows of a positive, through the softmax Jacobian (:285-310)
     const int ri = hd->rec_of[it];
@@ -241,8 +242,8 @@ __device__ __forceinline__ void item_box_rows(const Geo& g, const Workspace& ws,
     const DflTarget tg = dfl_target(pg, side);
     if (rec.label >= 0) {
       const float gd = pos_side_giou_grad(pg, side);
-      const float cb = upstream_of(A.upstream, acc_bbox(b.l)) * g.w_bbox / (1.0f + kEps32) / avg2 * rec.w * gd;
-      const float cd = upstream_of(A.upstream, acc_dfl(b.l)) * g.w_dfl / 4.0f / avg2 * rec.w;
+      const float cb = upstream_of(A.upstream, acc_bbox(b.l)) * k4[2] * rec.w * gd;   // w_bbox / (1 + eps) / avg2
+      const float cd = upstream_of(A.upstream, acc_dfl(b.l)) * k4[3] * rec.w;           // w_dfl / 4 / avg2
       float* prow = is_cand ? ws.pos_rows + ((size_t)b.n * g.pos_cap + rec.pslot) * kBoxCh + side * kBins : nullptr;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -273,6 +274,7 @@ struct ConsumerCtx {
   const StudentArgs& A;
   int lane, q, oq, cq;           // q: warp in its team = quarter of the channels
   float inv_avg1, avg2, inv_T;
+  float kd_scale, kl_scale, cb0, cd0;   // per-kernel constants of the special columns (no division per column)
 };
 
 // One tile, one consumer warp: the dense part of this warp's quarter of the channels and the items
@@ -348,6 +350,7 @@ __device__ __forceinline__ void consume_tile(const ConsumerCtx& cc, int j, float
   // Item i of the team's tile j goes to its warp (i + j) % 4.  Lane layout for the box rows: lane = side * 8 + b,
   // holding bins b, b + 8 (and 16 for b == 0) of its side; reductions over a side are 8-lane shuffles.
   const int n_items = hd->n_items;
+  const float k4[4] = {cc.kd_scale, cc.kl_scale, cc.cb0, cc.cd0};
   for (int it = (q - j) & (kTeamWarps - 1); it < n_items; it += kTeamWarps) {
     const int icol = hd->item_col[it];
     const unsigned irole = hd->role[icol];
@@ -363,8 +366,7 @@ __device__ __forceinline__ void consume_tile(const ConsumerCtx& cc, int j, float
     float* box = data + (size_t)C * kBT;
     if (is_cls || is_cand) {
       // old-class rows of the column: lane owns channels lane, lane + 32, ...
-      const float kc = (float)hd->cls_k * (float)ori;
-      const float scale_dc = upstream_of(A.upstream, acc_dcls(b.n)) * A.dlw * 2.0f / kc;
+      const float scale_dc = upstream_of(A.upstream, acc_dcls(b.n)) * A.dlw * 2.0f * hd->inv_kc;   // 2 / (K ori)
       float mx_old = -INFINITY;
       for (int c = lane; c < ori; c += 32) {
         const float xs = data[c * kBT + icol];
@@ -379,10 +381,10 @@ __device__ __forceinline__ void consume_tile(const ConsumerCtx& cc, int j, float
       }
       if (is_pos || is_cand) {
         const float w_kd = sigmoid_ref(warp_max(mx_old));                                      // :217-218
-        item_box_rows(g, ws, A, b, box, hd, hd->kd, tb, ts, it, icol, hwI, is_pos, is_cand, w_kd, cc.avg2, cc.inv_T, ga0, lane);
+        item_box_rows(g, ws, A, b, box, hd, hd->kd, tb, ts, it, icol, hwI, is_pos, is_cand, w_kd, k4, cc.inv_T, ga0, lane);
       }
     } else {
-      item_box_rows(g, ws, A, b, box, hd, hd->kd, tb, ts, it, icol, hwI, is_pos, false, 0.f, cc.avg2, cc.inv_T, ga0, lane);
+      item_box_rows(g, ws, A, b, box, hd, hd->kd, tb, ts, it, icol, hwI, is_pos, false, 0.f, k4, cc.inv_T, ga0, lane);
     }
   }
 }
@@ -547,6 +549,7 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
         hd->cnt = b.cnt;
         hd->n_items = __popc(m);
         hd->cls_k = kcls;
+        hd->inv_kc = 1.0f / ((float)kcls * (float)ori);   // K = 0: inf, and the (non-existent) rows' scale with it
         hd->tma = tma ? 1 : 0;
       }
       // The teacher's columns of the tile's first items: one bulk copy of the anchor's stash row (written by
@@ -603,7 +606,9 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
   const float inv_avg1 = 1.0f / (float)((double)avg0 + (double)kEps32);   // losses/utils.py:60-61
   const float avg2 = fmaxf(avg1, 1.0f);                                   // :407 clamp_(min=1)
   const ConsumerCtx cc{g, ws, A, lane, q, (ori + kTeamWarps - 1) / kTeamWarps, (cn + kTeamWarps - 1) / kTeamWarps,
-                       inv_avg1, avg2, 1.0f / g.T};
+                       inv_avg1, avg2, 1.0f / g.T,
+                       A.dlw * g.w_ld / 4.0f * (g.T * g.T / (float)kBins) / g.T, g.T * g.T / (float)kBins,
+                       g.w_bbox / (1.0f + kEps32) / avg2, g.w_dfl / 4.0f / avg2};
   int cur_img = -1, cur_lvl = -1;
   float dcls_part = 0.f;   // sum (x_s - x_t)^2 of the current image, this thread
   float qfl_part = 0.f;    // QFL loss sum of the current (image, level), this thread
