@@ -11,7 +11,7 @@ import os
 from . import build as _build
 
 MAX_LEVELS = 5
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class ErdShape(C.Structure):
@@ -40,6 +40,11 @@ class ErdStepBuffers(C.Structure):
                                            'sel_flags', 'gt_inds', 'num_pos', 'keep', 'keep_count', 'avg')]
 
 
+class ErdTeacherHead(C.Structure):
+    _fields_ = [('w_cls', C.c_void_p), ('w_reg', C.c_void_p), ('b_cls', C.c_void_p), ('b_reg', C.c_void_p),
+                ('scale', C.c_float * MAX_LEVELS)]
+
+
 PtrArray = C.c_void_p * MAX_LEVELS
 _P, _I, _F = C.c_void_p, C.c_int32, C.c_float
 _SH = C.POINTER(ErdShape)
@@ -56,6 +61,10 @@ SIGNATURES = {
     'erd_create': [C.POINTER(_P)],
     'erd_destroy': [_P],
     'erd_ers_select': [_SH, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P],
+    'erd_teacher_head_packed_floats': [_I],
+    'erd_teacher_head_pack': [_P, _I, _P, _P],
+    'erd_teacher_head_fused': [_SH, C.POINTER(ErdTeacherHead), PtrArray, PtrArray, C.POINTER(PtrArray), C.POINTER(PtrArray),
+                               _P, _P, _P, _P],
     'erd_atss_assign': [_SH, _P, _P, _P, _P, _P, _P, _P, _P],
     'erd_avg_factors': [_SH, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P],
     'erd_teacher_nms': [_SH, _P, _P, _P, _F, _P, _P, _P, _P, _P],
@@ -95,7 +104,7 @@ def load():
         fn.argtypes = argtypes
         fn.restype = (C.c_char_p if name in ('erd_last_error', 'erd_profile_kernel_name')
                       else C.c_ulonglong if name == 'erd_launch_count'
-                      else C.c_size_t if name == 'erd_avg_exchange_bytes' else C.c_int)
+                      else C.c_size_t if name in ('erd_avg_exchange_bytes', 'erd_teacher_head_packed_floats') else C.c_int)
     if lib.erd_abi_version() != ABI_VERSION:
         raise RuntimeError(f'liberd_b200 ABI {lib.erd_abi_version()} != binding {ABI_VERSION}')
     _lib = lib

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.environ.get('ERD_B200_LIB') or os.path.join(LIB_DIR, 'liberd_b200.so')   # (override: A/B runs of developer builds)
-SOURCES = ['api.cu', 'ers.cu', 'atss.cu', 'nms.cu', 'loss.cu', 'student.cu', 'teacher.cu', 'predict.cu', 'exchange.cu', 'profile.cu']
+SOURCES = ['api.cu', 'ers.cu', 'atss.cu', 'nms.cu', 'loss.cu', 'student.cu', 'teacher.cu', 'teacher_head.cu', 'predict.cu', 'exchange.cu', 'profile.cu']
 
 
 def nvcc_path() -> str:

@@ -79,7 +79,8 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->t_arg = (int*)take(NA * 4);
   ws->t_u = (float*)take(NA * 4);
   ws->t_dist = (float4*)take(NA * 16);
-  const size_t tiles32 = (size_t)g.A / 32 + kLevels;   // >= sum_l ceil(hw_l / 32)
+  size_t tiles32 = (size_t)g.A / 32 + kLevels;   // >= sum_l ceil(hw_l / 32)
+  if (tiles32 < (size_t)head_partials_per_img(g)) tiles32 = (size_t)head_partials_per_img(g);   // tiny levels, fused teacher head
   ws->ers_part = (double*)take((size_t)g.n_img * tiles32 * 4 * 8);
   ws->t_stash = (float*)take((size_t)g.n_img * kStashRows * stash_pitch(g.ori) * 4);
   ws->t_slot = (unsigned short*)take(NA * 2);
@@ -185,6 +186,8 @@ int erd_workspace_field(const ErdShape* shape, void* wsp, const char* name, void
   else if (!strcmp(name, "pthr_state")) { *ptr = ws.pthr_state; *bytes = 16; }
   else if (!strcmp(name, "t_m")) { *ptr = ws.t_m; *bytes = NA * 4; }
   else if (!strcmp(name, "t_u")) { *ptr = ws.t_u; *bytes = NA * 4; }
+  else if (!strcmp(name, "t_arg")) { *ptr = ws.t_arg; *bytes = NA * 4; }
+  else if (!strcmp(name, "t_dist")) { *ptr = ws.t_dist; *bytes = NA * 16; }
   else return fail(ERD_ERR_BAD_SHAPE, "erd_workspace_field: unknown field");
   return ERD_OK;
 }
@@ -252,6 +255,48 @@ int erd_ers_select(const ErdShape* shape, const float* const* t_cls, const float
   cudaError_t e = launch_ers(g, ws, ptr5(t_cls), ptr5(t_box), cls_inds, cls_count, box_inds, box_count, thr,
                              sel_flags, (cudaStream_t)stream);
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_ers_select");
+}
+
+size_t erd_teacher_head_packed_floats(int32_t out_channels) {
+  return out_channels > 0 ? (size_t)head_ncls_pad(out_channels) * 256 * 9 : 0;
+}
+
+int erd_teacher_head_pack(const float* w_oihw, int32_t out_channels, float* packed, void* stream) {
+  if (!w_oihw || !packed) return fail(ERD_ERR_NULL, "erd_teacher_head_pack: NULL argument");
+  if (out_channels < 1 || out_channels > 256) return fail(ERD_ERR_BAD_SHAPE, "erd_teacher_head_pack: 1 <= out_channels <= 256");
+  cudaError_t e = launch_head_pack(w_oihw, out_channels, packed, (cudaStream_t)stream);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_teacher_head_pack");
+}
+
+int erd_teacher_head_fused(const ErdShape* shape, const ErdTeacherHead* head, const float* const* cls_feat,
+                           const float* const* reg_feat, float* const* t_cls_out, float* const* t_box_out,
+                           int32_t* cls_count, int32_t* box_count, void* wsp, void* stream) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (!head || !head->w_cls || !head->w_reg || !head->b_cls || !head->b_reg || NULLS(cls_feat) || NULLS(reg_feat) ||
+      !cls_count || !box_count || !wsp)
+    return fail(ERD_ERR_NULL, "erd_teacher_head_fused: NULL argument");
+  const bool emit = t_cls_out || t_box_out;
+  if (emit && (!t_cls_out || !t_box_out)) return fail(ERD_ERR_NULL, "erd_teacher_head_fused: both logit outputs or none");
+  MPtr5 oc, ob;
+  for (int l = 0; l < kLevels; ++l) {
+    if (((uintptr_t)cls_feat[l] | (uintptr_t)reg_feat[l]) & 15)
+      return fail(ERD_ERR_BAD_SHAPE, "erd_teacher_head_fused: features must be 16 B aligned");
+    if (emit && (!t_cls_out[l] || !t_box_out[l])) return fail(ERD_ERR_NULL, "erd_teacher_head_fused: NULL logit output");
+    oc.p[l] = emit ? t_cls_out[l] : nullptr;
+    ob.p[l] = emit ? t_box_out[l] : nullptr;
+  }
+  if (((uintptr_t)head->w_cls | (uintptr_t)head->w_reg) & 15)
+    return fail(ERD_ERR_BAD_SHAPE, "erd_teacher_head_fused: packed weights must be 16 B aligned");
+  if ((long long)g.n_img * g.h[0] * g.w[0] * 64 >= (1ll << 32))
+    return fail(ERD_ERR_BAD_SHAPE, "erd_teacher_head_fused: level 0 exceeds 64 GB of features");
+  Workspace ws;
+  carve(g, wsp, &ws);
+  cudaError_t e = launch_teacher_head(g, ws, ptr5(cls_feat), ptr5(reg_feat), head->w_cls, head->w_reg, head->b_cls,
+                                      head->b_reg, head->scale, emit ? &oc : nullptr, emit ? &ob : nullptr, cls_count,
+                                      box_count, (cudaStream_t)stream);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_teacher_head_fused");
 }
 
 int erd_atss_assign(const ErdShape* shape, const float* gt_boxes, const int64_t* gt_labels,
@@ -407,13 +452,15 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
     Geo gt;
     rc = make_geo(shape, &gt);
     if (rc) return rc;
-    if (NULLS(t_cls) || NULLS(t_box) || !b->cls_inds || !b->cls_count || !b->box_inds || !b->box_count || !b->thr ||
+    if ((!(flags & ERD_PREPARE_TEACHER_CACHED) && (NULLS(t_cls) || NULLS(t_box))) || !b->cls_inds || !b->cls_count || !b->box_inds || !b->box_count || !b->thr ||
         !b->sel_flags || !wsp)
       return fail(ERD_ERR_NULL, "erd_step_prepare: NULL ERS argument");
-    set_vec(&gt, t_cls, t_box);
+    if (!(flags & ERD_PREPARE_TEACHER_CACHED)) set_vec(&gt, t_cls, t_box);
     Workspace wt;
     carve(gt, wsp, &wt);
     int tiles = 0;
+    if (flags & ERD_PREPARE_TEACHER_CACHED) tiles = head_partials_per_img(gt);   // erd_teacher_head_fused wrote cache and sums
+    else
     e = launch_teacher_pass(gt, wt, ptr5(t_cls), ptr5(t_box), b->cls_count, b->box_count, &tiles, ctx->side);
     if (e == cudaSuccess) e = launch_ers_flags(gt, wt, tiles, b->thr, b->sel_flags, b->cls_count, b->box_count, ctx->side);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->sel_done, ctx->side);

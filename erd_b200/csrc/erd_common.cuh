@@ -252,7 +252,7 @@ __device__ __forceinline__ void exchange_wait(const ExchangeInfo& x, unsigned in
 
 // ---------------------------------------------------------------- launch accounting (profile.cu)
 enum KernelId { kKErsScan, kKErsFlags, kKErsSelect, kKAtssCand, kKAtssFin, kKAvg, kKNmsSort, kKNmsMask, kKNmsScan, kKNmsOrder,
-                kKUpCheck, kKStudent, kKBoxFix, kNumKernels };
+                kKUpCheck, kKStudent, kKBoxFix, kKTeacherHead, kNumKernels };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 // Developer build only (-DERD_DEV_ABLATE): ERD_ABLATE=<mask> skips kernels by id to measure what
@@ -334,6 +334,14 @@ cudaError_t launch_ers(const Geo& g, const Workspace& ws, const Ptr5& t_cls, con
 cudaError_t launch_teacher_pass(const Geo& g, const Workspace& ws, const Ptr5& t_cls, const Ptr5& t_box,
                                 int32_t* cls_count, int32_t* box_count, int* tiles_per_img,
                                 cudaStream_t st);   // also zeroes the two count vectors
+// teacher_head.cu: the teacher head's last convolutions fused with the teacher pass (tcgen05 implicit GEMM)
+int head_ncls_pad(int out_channels);
+int head_partials_per_img(const Geo& g);
+cudaError_t launch_head_pack(const float* w_oihw, int out_channels, float* packed, cudaStream_t st);
+cudaError_t launch_teacher_head(const Geo& g, const Workspace& ws, const Ptr5& f_cls, const Ptr5& f_reg, const float* w_cls,
+                                const float* w_reg, const float* b_cls, const float* b_reg, const float* scale,
+                                const MPtr5* o_cls, const MPtr5* o_box, int32_t* cls_count, int32_t* box_count,
+                                cudaStream_t st);
 cudaError_t launch_ers_flags(const Geo& g, const Workspace& ws, int tiles_per_img, float* thr, uint8_t* sel_flags,
                              int32_t* cls_count, int32_t* box_count, cudaStream_t st);
 cudaError_t launch_ers_lists(const Geo& g, const Workspace& ws, int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds,

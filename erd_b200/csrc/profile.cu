@@ -10,7 +10,7 @@ namespace erd {
 
 static const char* kKernelNames[kNumKernels] = {"ers_scan", "ers_flags", "ers_select", "atss_candidates", "atss_finalize",
                                                 "pos_prepass", "nms_prep", "nms_mask", "nms_resolve", "nms_order", "upstream_check",
-                                                "student_pass", "box_fix"};
+                                                "student_pass", "box_fix", "teacher_head"};
 
 struct ProfState {
   std::mutex mu;

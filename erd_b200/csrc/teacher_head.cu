@@ -1,0 +1,504 @@
+// Teacher head-output producer fusion: the teacher head's LAST 3x3 convolutions
+// (gfl_cls: 256 -> ori classes, gfl_reg: 256 -> 68 box-distribution channels, + bias, box branch x Scale;
+// mmdet/models/dense_heads/gfl_head.py:228-230, called under no_grad from
+// mmdet/models/detectors/gfl_increment_erd.py:205) as ONE tcgen05 implicit GEMM whose epilogue is the teacher
+// pass: the accumulators never become a tensor that is re-read -- the per-anchor cache (max sigmoid, first
+// argmax, max box logit, softmax integrals), the fp64 threshold sums and the stash rows come straight out of
+// tensor memory.  The 432 B/anchor read of teacher.cu disappears from the loss step (the logits can still be
+// emitted, write-only, for callers that want them / for stash misses).
+//
+// GEMM view.  M = anchors, N = output channels (ori padded to 16, and 68 padded to 80), K = 9 taps x 256
+// channels, TF32 operands (what cuDNN runs the fp32 reference convolution in by default), fp32 accumulation
+// in TMEM.  A CTA works on a 16 x 16 pixel patch of one level of one image = two M=128 MMAs (left and right
+// 8-pixel halves) per tower that share every weight tile.
+//
+// A operand without im2col, without re-loading per tap.  The patch WITH its halo (18 x 18 pixels, zero filled
+// outside the map = the convolution's padding) is staged ONCE per 32-channel slice, in the no-swizzle K-major
+// core-matrix layout [16-byte channel chunk][halo pixel][16 B]: a pixel's row is 16 B, 8 consecutive pixels
+// of a halo row are one 8 x 16 B core matrix, the next 8-row group of the MMA's M is the next halo row
+// (stride-byte-offset 18 * 16 B), the next 16 B of K is the next plane (leading-byte-offset 324 * 16 B).
+// Each of the 9 taps is then the SAME buffer seen through a descriptor whose start address is shifted by
+// (dy * 18 + dx) * 16 B -- 16-byte alignment is all the no-swizzle layout asks of a start address.  So every
+// input byte crosses L2 -> shared memory once per patch (1.27x with the halo), not nine times.
+// Input layout: NHWC fp32 (torch channels_last), so a pixel's 32 channels are one 128-byte line.
+//
+// Warp roles (320 threads, one CTA per SM, persistent over the patches):
+//   warps 0-3  A producers: 16-byte cp.async (zero-fill = padding) into the stage, two stages;
+//   warp  4    B loader: one elected lane, 1-D bulk copies (cp.async.bulk) of the pre-packed weight tile of
+//              (32-channel slice, tap) -- the packed image IS the shared-memory image -- three stages;
+//   warp  5    TMEM allocation + the single MMA-issuing thread (tcgen05.mma kind::tf32, commit -> mbarriers);
+//   warps 6-9  epilogue: tcgen05.ld of the own lane quadrant, one anchor per lane, exactly the arithmetic of
+//              teacher.cu (identical bits for identical logits).  Accumulators are double buffered in TMEM
+//              when they fit (ori <= 48), so the epilogue of patch i runs under the MMAs of patch i + 1.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "erd_common.cuh"
+
+namespace erd {
+
+constexpr int kHC = 256;                          // tower channels (feat_channels of every gfl_increment config)
+constexpr int kKC = 32;                           // channels per A stage
+constexpr int kNKC = kHC / kKC;                   // 8 slices
+constexpr int kPlanes = kKC / 4;                  // 16-byte chunks per pixel and slice
+constexpr int kPatch = 16;
+constexpr int kHalo = kPatch + 2;                 // 18
+constexpr int kHaloPx = kHalo * kHalo;            // 324
+constexpr int kAPlane = kHaloPx * 16;             // 5 184 B: one 16-byte chunk of every halo pixel (LBO of A)
+constexpr int kATower = kAPlane * kPlanes;        // 41 472 B
+constexpr int kAStageBytes = 2 * kATower;         // cls tower + reg tower
+constexpr int kAStages = 2;
+constexpr int kBStages = 3;
+constexpr int kRegPad = 80;                       // 68 box channels padded to a legal UMMA N
+constexpr int kHeadThreads = 320;
+constexpr int kCopiesPerTower = kHaloPx * kPlanes;                 // 2 592 16-byte copies
+constexpr int kCopyIters = (kCopiesPerTower + 127) / 128;         // 21 per producer thread
+
+struct HeadArgs {
+  Ptr5 f_cls, f_reg;            // NHWC (N, H, W, 256)
+  MPtr5 o_cls, o_box;           // optional NCHW logits (emit)
+  const float* w_cls;           // packed by head_pack_kernel
+  const float* w_reg;
+  const float* b_cls;
+  const float* b_reg;
+  float scale[kLevels];
+  int32_t* cls_count;
+  int32_t* box_count;
+  int ncls_pad;
+  int tiles_x[kLevels];
+  int lvl_tile_start[kLevels + 1];
+  int tiles_per_img, total_tiles;
+  int stash_pitch;
+  int emit;
+  int n_acc, acc_stride;        // accumulator buffers in TMEM and their column stride
+  int b_stage_bytes;
+};
+
+struct HTile {
+  int n, l, y0, x0, sub;
+};
+
+__device__ __forceinline__ HTile h_tile(const HeadArgs& A, int t) {
+  HTile b;
+  b.n = t / A.tiles_per_img;
+  b.sub = t - b.n * A.tiles_per_img;
+  b.l = 0;
+#pragma unroll
+  for (int i = 1; i < kLevels; ++i) b.l += (b.sub >= A.lvl_tile_start[i]) ? 1 : 0;
+  const int r = b.sub - A.lvl_tile_start[b.l];
+  const int ty = r / A.tiles_x[b.l];
+  b.y0 = ty * kPatch;
+  b.x0 = (r - ty * A.tiles_x[b.l]) * kPatch;
+  return b;
+}
+
+__device__ __forceinline__ uint32_t h_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void h_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void h_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void h_commit(uint32_t bar) {   // arrives when every MMA issued so far has completed
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, no swizzle, version 1 (Blackwell): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | 1 << 46
+__device__ __forceinline__ uint64_t h_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void h_mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
+      ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void h_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// instruction descriptor: D fp32, A / B tf32, both K-major, M = 128, N
+__host__ __device__ constexpr uint32_t h_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Workspace ws, HeadArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long s_bar[2 * kAStages + 2 * kBStages + 4];
+  __shared__ uint32_t s_tmem;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + kAStages * kAStageBytes;
+  float* s_bias = reinterpret_cast<float*>(sB + kBStages * A.b_stage_bytes);   // [ncls_pad] class, [80] box
+  int* s_stash_cnt = reinterpret_cast<int*>(s_bias + A.ncls_pad + kRegPad);      // [n_img]
+  const uint32_t bar0 = h_smem(s_bar);
+  auto full_a = [&](int s) { return bar0 + 8u * s; };
+  auto empty_a = [&](int s) { return bar0 + 8u * (kAStages + s); };
+  auto full_b = [&](int s) { return bar0 + 8u * (2 * kAStages + s); };
+  auto empty_b = [&](int s) { return bar0 + 8u * (2 * kAStages + kBStages + s); };
+  auto t_full = [&](int s) { return bar0 + 8u * (2 * kAStages + 2 * kBStages + s); };
+  auto t_empty = [&](int s) { return bar0 + 8u * (2 * kAStages + 2 * kBStages + 2 + s); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ori = g.ori;
+  const int ncp = A.ncls_pad;
+
+  if (threadIdx.x == 0) {
+    auto init = [](uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); };
+    for (int s = 0; s < kAStages; ++s) { init(full_a(s), 128); init(empty_a(s), 1); }
+    for (int s = 0; s < kBStages; ++s) { init(full_b(s), 1); init(empty_b(s), 1); }
+    for (int s = 0; s < 2; ++s) { init(t_full(s), 1); init(t_empty(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < ncp + kRegPad; i += blockDim.x)
+    s_bias[i] = i < ncp ? (i < ori ? A.b_cls[i] : 0.f) : (i - ncp < kBoxCh ? A.b_reg[i - ncp] : 0.f);
+  for (int i = threadIdx.x; i < g.n_img; i += blockDim.x) s_stash_cnt[i] = 0;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < g.n_img; i += blockDim.x) {
+      A.cls_count[i] = 0;
+      A.box_count[i] = 0;
+    }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(h_smem(&s_tmem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ A producers
+    const int tid = threadIdx.x;
+    const int j = tid & 7;   // this thread's 16-byte chunk of the slice (128 is a multiple of 8: it never changes)
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x) {
+      const HTile b = h_tile(A, t);
+      const int H = g.h[b.l], W = g.w[b.l];
+      uint32_t off[kCopyIters];   // source of copy i in 16-byte units, ~0: outside the map (zero fill)
+#pragma unroll
+      for (int i = 0; i < kCopyIters; ++i) {
+        const int px = (tid >> 3) + 16 * i;
+        const int hy = px / kHalo, hx = px - hy * kHalo;
+        const int gy = b.y0 - 1 + hy, gx = b.x0 - 1 + hx;
+        const bool ok = px < kHaloPx && gy >= 0 && gy < H && gx >= 0 && gx < W;
+        off[i] = ok ? (uint32_t)(((b.n * H + gy) * W + gx) * (kHC / 4) + j) : 0xFFFFFFFFu;
+      }
+      const float4* fc = reinterpret_cast<const float4*>(A.f_cls.p[b.l]);
+      const float4* fr = reinterpret_cast<const float4*>(A.f_reg.p[b.l]);
+      for (int kc = 0; kc < kNKC; ++kc, ++it) {
+        const int s = it % kAStages;
+        h_wait(empty_a(s), ((it / kAStages) & 1u) ^ 1u);
+        const uint32_t dst = h_smem(sA + (size_t)s * kAStageBytes) + j * kAPlane + (tid >> 3) * 16;
+#pragma unroll
+        for (int i = 0; i < kCopyIters; ++i) {
+          if ((tid >> 3) + 16 * i < kHaloPx) {
+            const bool ok = off[i] != 0xFFFFFFFFu;
+            const uint32_t o = ok ? off[i] + kc * kPlanes : 0u;
+            const uint32_t sz = ok ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * 256), "l"(fc + o), "r"(sz) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + kATower + i * 256), "l"(fr + o), "r"(sz) : "memory");
+          }
+        }
+        // this thread's copies have landed: make them visible to the tensor core's (async) proxy and hand the stage
+        // over.  (The other stage is being consumed meanwhile; a stage fills faster than the MMAs drain one.)
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        h_arrive(full_a(s));
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ B loader
+    if (lane == 0) {
+      uint32_t ib = 0;
+      const uint32_t cls_bytes = (uint32_t)ncp * 128u, reg_bytes = (uint32_t)kRegPad * 128u;
+      for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x) {
+        for (int kt = 0; kt < kNKC * 9; ++kt, ++ib) {   // (slice, tap) in the order the packed weights are stored
+          const int s = ib % kBStages;
+          h_wait(empty_b(s), ((ib / kBStages) & 1u) ^ 1u);
+          asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(full_b(s)), "r"(cls_bytes + reg_bytes) : "memory");
+          const uint32_t dst = h_smem(sB + (size_t)s * A.b_stage_bytes);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst), "l"(A.w_cls + (size_t)kt * ncp * 32), "r"(cls_bytes), "r"(full_b(s)) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst + cls_bytes), "l"(A.w_reg + (size_t)kt * kRegPad * 32), "r"(reg_bytes), "r"(full_b(s)) : "memory");
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_cls = h_idesc(ncp), idesc_reg = h_idesc(kRegPad);
+      const uint32_t lbo_cls = (uint32_t)ncp * 16u, lbo_reg = (uint32_t)kRegPad * 16u;
+      uint32_t ia = 0, ib = 0, itile = 0;
+      for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, ++itile) {
+        const int acc = itile % A.n_acc;
+        h_wait(t_empty(acc), ((itile / A.n_acc) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d0 = tmem + acc * A.acc_stride;
+        for (int kc = 0; kc < kNKC; ++kc, ++ia) {
+          const int sa = ia % kAStages;
+          h_wait(full_a(sa), (ia / kAStages) & 1u);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          const uint32_t a_stage = h_smem(sA + (size_t)sa * kAStageBytes);
+          for (int tap = 0; tap < 9; ++tap, ++ib) {
+            const int sb = ib % kBStages;
+            h_wait(full_b(sb), (ib / kBStages) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint32_t a0 = a_stage + (dy * kHalo + dx) * 16;   // the tap: the same buffer, shifted start
+            const uint32_t bc = h_smem(sB + (size_t)sb * A.b_stage_bytes), br = bc + ncp * 128;
+#pragma unroll
+            for (int s = 0; s < kKC / 8; ++s) {     // K = 8 per MMA: two 16-byte planes
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {         // left / right 8-pixel half of the patch: M = 16 rows x 8 pixels
+                const uint32_t accum = (kc | tap | s) ? 1u : 0u;
+                const uint32_t dh = d0 + h * (ncp + kRegPad);
+                h_mma(dh, h_desc(a0 + 2 * s * kAPlane + h * 128, kAPlane, kHalo * 16),
+                      h_desc(bc + 2 * s * lbo_cls, lbo_cls, 128), idesc_cls, accum);
+                h_mma(dh + ncp, h_desc(a0 + kATower + 2 * s * kAPlane + h * 128, kAPlane, kHalo * 16),
+                      h_desc(br + 2 * s * lbo_reg, lbo_reg, 128), idesc_reg, accum);
+              }
+            }
+            h_commit(empty_b(sb));
+          }
+          h_commit(empty_a(sa));
+        }
+        h_commit(t_full(acc));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue = the teacher pass
+    const int q = warp & 3;   // TMEM lane quadrant this warp may read
+    const unsigned int pc_bits = __ldg(ws.pthr_state), pb_bits = __ldg(ws.pthr_state + 1);
+    const float pthr_c = pc_bits ? from_ordered_bits(~pc_bits) : INFINITY;
+    const float pthr_b = pb_bits ? from_ordered_bits(~pb_bits) : INFINITY;
+    const int rows = ori + kBoxCh;
+    uint32_t itile = 0;
+    for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, ++itile) {
+      const HTile b = h_tile(A, t);
+      const int H = g.h[b.l], W = g.w[b.l], HW = H * W;
+      const float scale = A.scale[b.l];
+      const int acc = itile % A.n_acc;
+      h_wait(t_full(acc), (itile / A.n_acc) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      double sums[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int mrow = 32 * q + lane;
+        const int y = b.y0 + (mrow >> 3), x = b.x0 + 8 * h + (mrow & 7);
+        const bool in = y < H && x < W;
+        const int hw = y * W + x;
+        const uint32_t taddr = tmem + acc * A.acc_stride + h * (ncp + kRegPad) + ((uint32_t)(32 * q) << 16);
+        float* oc = A.emit && in ? A.o_cls.p[b.l] + (size_t)b.n * ori * HW + hw : nullptr;
+        float* ob = A.emit && in ? A.o_box.p[b.l] + (size_t)b.n * kBoxCh * HW + hw : nullptr;
+        // class logits: first maximum (argmax semantics of torch.max, gfl_head_increment_erd.py:194-195)
+        float best = 0.f;
+        int arg = 0;
+        for (int c0 = 0; c0 < ori; c0 += 8) {
+          float v[8];
+          h_ld8(taddr + c0, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = c0 + e;
+            if (c < ori) {
+              const float val = v[e] + s_bias[c];
+              if (oc) oc[(size_t)c * HW] = val;
+              if (c == 0) {
+                best = val;
+              } else if (val > best) {
+                best = val;
+                arg = c;
+              }
+            }
+          }
+        }
+        // box logits: (conv + bias) * Scale (gfl_head.py:229), then the Integral (gfl_head_increment_erd.py:40-54)
+        float z[72];
+#pragma unroll
+        for (int ch = 0; ch < 9; ++ch) h_ld8(taddr + ncp + 8 * ch, *reinterpret_cast<float(*)[8]>(&z[8 * ch]));
+#pragma unroll
+        for (int c = 0; c < kBoxCh; ++c) {
+          z[c] = (z[c] + s_bias[ncp + c]) * scale;
+          if (ob) ob[(size_t)c * HW] = z[c];
+        }
+        float u = -INFINITY;
+        float dist[4];
+#pragma unroll
+        for (int sd = 0; sd < 4; ++sd) {
+          const float* zs = z + sd * kBins;
+          float mx = zs[0];
+#pragma unroll
+          for (int k = 1; k < kBins; ++k) mx = fmaxf(mx, zs[k]);
+          const float kL2e = 1.4426950408889634f;
+          const float bias = -mx * kL2e;
+          float sum = 0.f, num = 0.f;
+#pragma unroll
+          for (int k = 0; k < kBins; ++k) {
+            const float e = ex2_approx(fmaf(zs[k], kL2e, bias));
+            sum += e;
+            num = fmaf((float)k, e, num);
+          }
+          dist[sd] = __fdiv_rn(num, sum);
+          u = fmaxf(u, mx);
+        }
+        const float m = sigmoid_ref(best);
+        const size_t ga = (size_t)b.n * g.A + g.start[b.l] + hw;
+        // stash: the column of every anchor that clears the provisional thresholds (teacher.cu)
+        {
+          const bool want = in && (m > pthr_c || u > pthr_b);
+          const unsigned wm = __ballot_sync(0xffffffffu, want);
+          unsigned short myslot = 0;
+          if (wm) {   // warp-uniform
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_stash_cnt[b.n], __popc(wm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int idx = base + __popc(wm & ((1u << lane) - 1u));
+            const bool ok = want && idx < kStashPerCta;
+            const int row = (int)blockIdx.x * kStashPerCta + idx;
+            float* dst = ws.t_stash + ((size_t)b.n * kStashRows + (ok ? row : 0)) * A.stash_pitch;
+            if (ok) myslot = (unsigned short)(row + 1);
+            for (int c0 = 0; c0 < ori; c0 += 8) {   // the class part again from TMEM (the load is warp-collective)
+              float v[8];
+              h_ld8(taddr + c0, v);
+              if (ok) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (c0 + e < ori) dst[c0 + e] = v[e] + s_bias[c0 + e];
+              }
+            }
+            if (ok) {
+#pragma unroll
+              for (int c = 0; c < kBoxCh; ++c) dst[ori + c] = z[c];
+            }
+          }
+          if (in) ws.t_slot[ga] = myslot;
+        }
+        if (in) {
+          sums[0] += (double)m;
+          sums[1] += (double)m * (double)m;
+          sums[2] += (double)u;
+          sums[3] += (double)u * (double)u;
+          ws.t_m[ga] = m;
+          ws.t_arg[ga] = arg;
+          ws.t_u[ga] = u;
+          ws.t_dist[ga] = make_float4(dist[0], dist[1], dist[2], dist[3]);
+        }
+      }
+      // every lane's TMEM reads of this buffer are complete (h_ld8 waits): hand it back to the MMA thread
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) h_arrive(t_empty(acc));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sums[i] = warp_sum(sums[i]);
+      if (lane < 4) {
+        const double v = lane == 0 ? sums[0] : lane == 1 ? sums[1] : lane == 2 ? sums[2] : sums[3];
+        __stcg(ws.ers_part + ((size_t)b.n * A.tiles_per_img * 4 + (size_t)b.sub * 4 + q) * 4 + lane, v);
+      }
+    }
+    (void)rows;
+  }
+  // ---------------------------------------------------------------------- teardown
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// OIHW (O, 256, 3, 3) -> the shared-memory image of every (slice, tap) weight tile:
+// [slice kc][tap][16-byte chunk j][output row n < Opad][4 floats], channel = kc * 32 + j * 4 + e; rows >= O are zero.
+__global__ void head_pack_kernel(const float* __restrict__ w, int O, int Opad, float* __restrict__ out) {
+  const int total = Opad * kHC * 9;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int e = idx & 3;
+    int r = idx >> 2;
+    const int n = r % Opad;
+    r /= Opad;
+    const int j = r & 7;
+    r >>= 3;
+    const int tap = r % 9, kc = r / 9;
+    const int c = kc * kKC + j * 4 + e;
+    out[idx] = n < O ? w[((size_t)n * kHC + c) * 9 + tap] : 0.f;
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+int head_ncls_pad(int ori) { return (ori + 15) & ~15; }
+
+// 4 threshold partials per patch (one per epilogue warp); what launch_ers_flags is told to reduce
+int head_partials_per_img(const Geo& g) {
+  int tiles = 0;
+  for (int l = 0; l < kLevels; ++l) tiles += ((g.h[l] + kPatch - 1) / kPatch) * ((g.w[l] + kPatch - 1) / kPatch);
+  return tiles * 4;
+}
+
+cudaError_t launch_head_pack(const float* w, int O, float* out, cudaStream_t st) {
+  const int Opad = head_ncls_pad(O);
+  head_pack_kernel<<<256, 256, 0, st>>>(w, O, Opad, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_teacher_head(const Geo& g, const Workspace& ws, const Ptr5& f_cls, const Ptr5& f_reg, const float* w_cls,
+                                const float* w_reg, const float* b_cls, const float* b_reg, const float* scale,
+                                const MPtr5* o_cls, const MPtr5* o_box, int32_t* cls_count, int32_t* box_count,
+                                cudaStream_t st) {
+  HeadArgs A;
+  A.f_cls = f_cls;
+  A.f_reg = f_reg;
+  A.emit = (o_cls && o_box) ? 1 : 0;
+  for (int l = 0; l < kLevels; ++l) {
+    A.o_cls.p[l] = A.emit ? o_cls->p[l] : nullptr;
+    A.o_box.p[l] = A.emit ? o_box->p[l] : nullptr;
+    A.scale[l] = scale[l];
+  }
+  A.w_cls = w_cls;
+  A.w_reg = w_reg;
+  A.b_cls = b_cls;
+  A.b_reg = b_reg;
+  A.cls_count = cls_count;
+  A.box_count = box_count;
+  A.ncls_pad = head_ncls_pad(g.ori);
+  if (A.ncls_pad > 256) return cudaErrorInvalidValue;
+  int tiles = 0;
+  for (int l = 0; l < kLevels; ++l) {
+    A.lvl_tile_start[l] = tiles;
+    A.tiles_x[l] = (g.w[l] + kPatch - 1) / kPatch;
+    tiles += ((g.h[l] + kPatch - 1) / kPatch) * A.tiles_x[l];
+  }
+  A.lvl_tile_start[kLevels] = tiles;
+  A.tiles_per_img = tiles;
+  A.total_tiles = tiles * g.n_img;
+  A.stash_pitch = stash_pitch(g.ori);
+  A.acc_stride = 2 * (A.ncls_pad + kRegPad);
+  if (A.acc_stride > 512) return cudaErrorInvalidValue;
+  A.n_acc = 2 * A.acc_stride <= 512 ? 2 : 1;
+  A.b_stage_bytes = (A.ncls_pad + kRegPad) * 128;
+  const size_t smem = (size_t)kAStages * kAStageBytes + (size_t)kBStages * A.b_stage_bytes +
+                      (size_t)(A.ncls_pad + kRegPad) * 4 + (((size_t)g.n_img * 4 + 15) & ~(size_t)15);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  static size_t smem_set = 0;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(teacher_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  int grid = sms;
+  if (grid > A.total_tiles) grid = A.total_tiles;
+  if (grid > kStashCtas) grid = kStashCtas;   // the stash is laid out per CTA
+  ERD_LAUNCH(kKTeacherHead, st, (teacher_head_kernel<<<grid, kHeadThreads, smem, st>>>(g, ws, A)));
+  return cudaGetLastError();
+}
+
+}  // namespace erd

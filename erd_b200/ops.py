@@ -161,6 +161,34 @@ class Plan:
             cnt.copy_(torch.tensor(counts, dtype=torch.int32), non_blocking=False)
 
 
+class TeacherHead:
+    """The frozen teacher's last head convolutions in the layout ``erd_teacher_head_fused`` streams
+    (gfl_cls / gfl_reg weights re-laid-out once, biases, per-level Scale values; gfl_head.py:228-230)."""
+
+    def __init__(self, gfl_cls_weight: torch.Tensor, gfl_cls_bias: torch.Tensor, gfl_reg_weight: torch.Tensor,
+                 gfl_reg_bias: torch.Tensor, scales: Sequence[float]):
+        lib = N.load()
+        if not gfl_cls_weight.is_cuda:
+            raise RuntimeError('erd_b200 runs on CUDA tensors only; there is no CPU fallback')
+        for w in (gfl_cls_weight, gfl_reg_weight):
+            if tuple(w.shape[1:]) != (256, 3, 3):
+                raise ValueError(f'teacher head weight must be (O, 256, 3, 3), got {tuple(w.shape)}')
+        if len(scales) != N.MAX_LEVELS:
+            raise ValueError('one Scale value per level')
+        self.ori = int(gfl_cls_weight.shape[0])
+        self.packed = []
+        for w in (gfl_cls_weight, gfl_reg_weight):
+            w = w.detach().float().contiguous()
+            out = torch.empty(lib.erd_teacher_head_packed_floats(int(w.shape[0])), dtype=torch.float32, device=w.device)
+            N.check(lib.erd_teacher_head_pack(w.data_ptr(), int(w.shape[0]), out.data_ptr(), _stream()),
+                    'erd_teacher_head_pack')
+            self.packed.append(out)
+        self.b_cls = gfl_cls_bias.detach().float().contiguous()
+        self.b_reg = gfl_reg_bias.detach().float().contiguous()
+        self.c = N.ErdTeacherHead(self.packed[0].data_ptr(), self.packed[1].data_ptr(), self.b_cls.data_ptr(),
+                                  self.b_reg.data_ptr(), (C.c_float * N.MAX_LEVELS)(*[float(v) for v in scales]))
+
+
 class ErdPath:
     """The hot path behind the reference's ``sel_pos`` / ``loss_by_feat`` (one per process)."""
 
@@ -223,6 +251,30 @@ class ErdPath:
                 'erd_ers_select')
         p.ers_generation += 1
 
+    def teacher_head_fused(self, p: Plan, head: TeacherHead, cls_feats, reg_feats, t_cls=None, t_box=None):
+        """The teacher head's last convolutions fused with the teacher pass (``erd_teacher_head_fused``).
+        ``cls_feats`` / ``reg_feats``: tower outputs (N, 256, H, W) in channels_last storage.  ``t_cls`` / ``t_box``:
+        optional NCHW tensors that receive the logits.  Follow with ``prepare(..., teacher_cached=True)``."""
+        if head.ori != p.ori:
+            raise ValueError('teacher head classes != plan ori classes')
+        for name, fs in (('cls_feat', cls_feats), ('reg_feat', reg_feats)):
+            if len(fs) != len(p.shapes):
+                raise ValueError(f'{name}: one tensor per level')
+            for f, (h, w) in zip(fs, p.shapes):
+                if tuple(f.shape) != (p.n, 256, h, w) or f.dtype != torch.float32:
+                    raise ValueError(f'{name}: expected fp32 {(p.n, 256, h, w)}, got {tuple(f.shape)} {f.dtype}')
+                if not f.is_contiguous(memory_format=torch.channels_last):
+                    raise ValueError(f'{name}: channels_last (NHWC) storage required')
+        emit = t_cls is not None
+        if emit:
+            _check_level_tensors('teacher cls_scores', t_cls, p.n, p.ori, p.shapes)
+            _check_level_tensors('teacher bbox_preds', t_box, p.n, 4 * (p.reg_max + 1), p.shapes)
+        oc, ob = (_ptrs(t_cls), _ptrs(t_box)) if emit else (None, None)
+        N.check(self.lib.erd_teacher_head_fused(C.byref(p.shape), C.byref(head.c), _ptrs(cls_feats), _ptrs(reg_feats),
+                                                C.byref(oc) if emit else None, C.byref(ob) if emit else None,
+                                                p.cls_count.data_ptr(), p.box_count.data_ptr(), p.ws.data_ptr(),
+                                                _stream()), 'erd_teacher_head_fused')
+
     def atss_assign(self, p: Plan):
         N.check(self.lib.erd_atss_assign(C.byref(p.shape), p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(),
                                          p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(), p.gt_inds.data_ptr(),
@@ -278,12 +330,13 @@ class ErdPath:
             losses.data_ptr(), _ptrs(g_cls), _ptrs(g_box), p.ws.data_ptr(), _stream()), 'erd_loss_fwd_bwd')
 
     # ---- fused step -------------------------------------------------------------------
-    def prepare(self, p: Plan, t_cls, t_box, s_cls, s_box, ers_done: bool = False):
+    def prepare(self, p: Plan, t_cls, t_box, s_cls, s_box, ers_done: bool = False, teacher_cached: bool = False):
         self._posted = self._ensure_exchange(p.device)
         N.check(self.lib.erd_step_prepare(
             self._context(p.device), C.byref(p.shape), _ptrs(t_cls), _ptrs(t_box), _ptrs(s_cls), _ptrs(s_box),
             p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(), p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(),
-            self.nms_iou_thr, C.byref(p.bufs), p.ws.data_ptr(), _stream(), 1 if ers_done else 0),
+            self.nms_iou_thr, C.byref(p.bufs), p.ws.data_ptr(), _stream(),
+            (1 if ers_done else 0) | (4 if teacher_cached else 0)),
             'erd_step_prepare')
         if not ers_done:
             p.ers_generation += 1
@@ -291,7 +344,7 @@ class ErdPath:
     def step(self, t_cls, t_box, s_cls, s_box, gt_bboxes, gt_labels, pad_shapes, num_classes: int, ori: int,
              reg_max: int = 16, dist_loss_weight: float = 1.0, upstream: Optional[torch.Tensor] = None,
              g_cls: Optional[List[torch.Tensor]] = None, g_box: Optional[List[torch.Tensor]] = None,
-             targets_set: bool = False, ers_done: bool = False):
+             targets_set: bool = False, ers_done: bool = False, teacher_cached: bool = False):
         """ERS + assignment + NMS + fused loss forward/backward.
         Returns (plan, losses (3L+2N,), g_cls[5], g_box[5])."""
         p = self.plan(s_cls, num_classes, ori, reg_max,
@@ -307,7 +360,7 @@ class ErdPath:
         if g_box is None:
             g_box = [torch.empty_like(t) for t in s_box]
         losses = torch.empty(p.num_losses, dtype=torch.float32, device=p.device)
-        self.prepare(p, t_cls, t_box, s_cls, s_box, ers_done)
+        self.prepare(p, t_cls, t_box, s_cls, s_box, ers_done, teacher_cached)
         self.reduce_avg(p)
         self.loss_fwd_bwd(p, t_cls, t_box, s_cls, s_box, g_cls, g_box, losses, dist_loss_weight, upstream)
         return p, losses, g_cls, g_box

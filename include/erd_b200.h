@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define ERD_MAX_LEVELS 5
-#define ERD_ABI_VERSION 5
+#define ERD_ABI_VERSION 6
 
 typedef enum ErdStatus {
   ERD_OK = 0,
@@ -199,6 +199,9 @@ int erd_step_prepare(ErdContext* ctx, const ErdShape* shape, const float* const*
 /* flags for erd_step_prepare */
 #define ERD_PREPARE_ERS_DONE 1u /* erd_ers_select already ran on these teacher tensors (sel_pos);
                                    its lists, counts, sel_flags and the teacher cache are reused */
+#define ERD_PREPARE_TEACHER_CACHED 4u /* erd_teacher_head_fused already filled the teacher cache, the threshold sums and the
+                                         stash on this workspace (it was ordered on `stream` before this call): the
+                                         teacher pass is skipped; t_cls / t_box are only passed on (may hold NULLs) */
 #define ERD_PREPARE_NO_EXCHANGE 2u /* do not post the avg factors to the peers even if the context has an
                                       exchange (the caller reduces buf->avg itself before erd_loss_fwd_bwd) */
 
@@ -220,6 +223,34 @@ int erd_avg_exchange(float* avg, void* const* peer_bufs, int32_t rank, int32_t w
  * no stream's critical path.  peer_bufs as above; world <= 1 or NULL disables it.  Collective per step like
  * erd_avg_exchange; do not mix the two on the same buffers within a step. */
 int erd_context_set_exchange(ErdContext* ctx, void* const* peer_bufs, int32_t rank, int32_t world);
+
+/* --- teacher head-output producer fusion (next row of the scope table) -----------------
+ * Replaces the teacher head's last convolutions -- gfl_cls / gfl_reg (3x3, 256 -> ori / 4*(reg_max+1)) + bias and the
+ * box branch's Scale, mmdet/models/dense_heads/gfl_head.py:228-230, run under no_grad by
+ * GFLIncrementERD.loss (mmdet/models/detectors/gfl_increment_erd.py:205) -- TOGETHER with the streaming half of
+ * erd_ers_select: one tcgen05 (TF32, fp32 accumulate) implicit GEMM whose epilogue writes the per-anchor teacher
+ * cache, the threshold sums and the stash directly, so the teacher logits are never re-read (and need not exist).
+ * cls_feat[l] / reg_feat[l]: outputs of the teacher's cls / reg tower at level l, (N, H_l, W_l, 256) fp32 -- NHWC, i.e.
+ * torch channels_last storage of the (N, 256, H_l, W_l) tensor; 16 B aligned.
+ * head->w_cls / w_reg: the conv weights re-laid-out once by erd_teacher_head_pack (the teacher is frozen);
+ * b_cls (ori,), b_reg (4*(reg_max+1),) biases; scale[l] the Scale parameters.
+ * t_cls_out / t_box_out: NULL, or per-level NCHW fp32 tensors that receive the logits exactly as GFLHead.forward
+ * would emit them (write-only; they are what erd_loss_fwd_bwd reads for an ERS anchor that missed the stash).
+ * Zeroes cls_count / box_count like erd_ers_select's scan.  Follow with erd_step_prepare(..., ERD_PREPARE_TEACHER_CACHED)
+ * on the same stream and workspace. */
+typedef struct ErdTeacherHead {
+  const float* w_cls;                 /* erd_teacher_head_pack(gfl_cls.weight)            */
+  const float* w_reg;                 /* erd_teacher_head_pack(gfl_reg.weight)            */
+  const float* b_cls;
+  const float* b_reg;
+  float scale[ERD_MAX_LEVELS];
+} ErdTeacherHead;
+/* floats of the packed image of an (out_channels, 256, 3, 3) weight */
+size_t erd_teacher_head_packed_floats(int32_t out_channels);
+int erd_teacher_head_pack(const float* w_oihw, int32_t out_channels, float* packed, void* stream);
+int erd_teacher_head_fused(const ErdShape* shape, const ErdTeacherHead* head, const float* const* cls_feat,
+                           const float* const* reg_feat, float* const* t_cls_out, float* const* t_box_out,
+                           int32_t* cls_count, int32_t* box_count, void* ws, void* stream);
 
 /* --- inference post-process (next row of the scope table) ---------------------------
  * Replaces GFLHead._predict_by_feat_single (mmdet/models/dense_heads/gfl_head.py:408-502) with
@@ -245,7 +276,8 @@ int erd_predict(const ErdShape* shape, const ErdPredictConfig* cfg, const float*
 /* Introspection for tests and diagnostics: device address and size of a named workspace array
  * ("t_slot": uint16 [N][A] stash row + 1 of each anchor; "pthr_state": uint32 [4] provisional thresholds as
  * ~ordered bits, 0 = none;
- * "t_m", "t_u": float [N][A] the teacher cache the thresholds are taken over).  ERD_ERR_BAD_SHAPE for an
+ * "t_m", "t_u": float [N][A] the teacher cache the thresholds are taken over; "t_arg": int32 [N][A] argmax class,
+ * "t_dist": float [N][A][4] softmax-integral distances).  ERD_ERR_BAD_SHAPE for an
  * unknown name.  No reference counterpart. */
 int erd_workspace_field(const ErdShape* shape, void* workspace, const char* name, void** ptr, size_t* bytes);
 

@@ -1,0 +1,105 @@
+"""Teacher head-output producer fusion: the teacher's last head convolutions
+(gfl_head.py:228-230) as a tcgen05 implicit GEMM whose epilogue is the teacher pass.
+
+Three claims, each checked through the C ABI:
+  1. the logits it emits are the convolution's: against an fp64 convolution on the CPU, inside the worst-case bound
+     of TF32 operand truncation (2 * 2**-10 * sum |x||w|, the tolerance of the precision cuDNN runs the fp32
+     reference convolution in by default);
+  2. its epilogue IS the teacher pass: cache (max sigmoid, argmax, max box logit, integral distances) bit-identical
+     to erd_ers_select run on the emitted logits, thresholds and selections identical;
+  3. a whole step behind it (ERD_PREPARE_TEACHER_CACHED) gives the same bits as the standard step on those logits.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from erd_b200.ops import ErdPath, TeacherHead
+from erd_b200.synth import make_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _towers(n, shapes, seed):
+    g = torch.Generator().manual_seed(seed)
+    mk = lambda h, w: torch.randn(n, 256, h, w, generator=g).relu_()   # tower outputs are post-ReLU
+    return [mk(h, w) for h, w in shapes], [mk(h, w) for h, w in shapes]
+
+
+def _head_params(ori, seed):
+    g = torch.Generator().manual_seed(seed + 1)
+    w_cls = torch.randn(ori, 256, 3, 3, generator=g) * 0.03
+    w_reg = torch.randn(68, 256, 3, 3, generator=g) * 0.03
+    b_cls = torch.full((ori,), -4.59511985013459) + 0.3 * torch.randn(ori, generator=g)
+    b_reg = 0.2 * torch.randn(68, generator=g)
+    scales = [1.0, 0.9, 1.1, 1.25, 0.8]
+    return w_cls, b_cls, w_reg, b_reg, scales
+
+
+@pytest.mark.parametrize('ori,img_hw,n', [(40, (200, 264), 2), (70, (136, 200), 3), (40, (333, 190), 1)])
+def test_fused_teacher_head(ori, img_hw, n):
+    batch = make_batch(n, img_hw, ori=ori, seed=31 + ori, num_gt=(2, 5))
+    shapes = batch.shapes
+    cls_f, reg_f = _towers(n, shapes, seed=ori)
+    w_cls, b_cls, w_reg, b_reg, scales = _head_params(ori, seed=ori)
+    dev = 'cuda'
+    head = TeacherHead(w_cls.to(dev), b_cls.to(dev), w_reg.to(dev), b_reg.to(dev), scales)
+    cl = lambda xs: [x.to(dev).contiguous(memory_format=torch.channels_last) for x in xs]
+    cls_d, reg_d = cl(cls_f), cl(reg_f)
+    b = batch.to(dev)
+
+    fused, plain = ErdPath(), ErdPath()
+    pf = fused.plan(b.s_cls, batch.num_classes, ori, batch.reg_max)
+    pp = plain.plan(b.s_cls, batch.num_classes, ori, batch.reg_max)
+    assert pf is not pp
+    t_cls = [torch.full((n, ori, h, w), float('nan'), device=dev) for h, w in shapes]
+    t_box = [torch.full((n, 68, h, w), float('nan'), device=dev) for h, w in shapes]
+
+    for rep in range(2):   # second round: the stash is live (provisional thresholds of round one)
+        # ---- 1. the logits
+        fused.teacher_head_fused(pf, head, cls_d, reg_d, t_cls, t_box)
+        torch.cuda.synchronize()
+        for l in range(5):
+            x_c, x_r = cls_f[l].double(), reg_f[l].double()
+            ref_c = F.conv2d(x_c, w_cls.double(), b_cls.double(), padding=1)
+            ref_r = F.conv2d(x_r, w_reg.double(), b_reg.double(), padding=1) * scales[l]
+            bound_c = 2.0e-3 * F.conv2d(x_c.abs(), w_cls.double().abs(), padding=1) + 1e-5
+            bound_r = (2.0e-3 * F.conv2d(x_r.abs(), w_reg.double().abs(), padding=1) + 1e-5) * scales[l]
+            err_c = (t_cls[l].cpu().double() - ref_c).abs()
+            err_r = (t_box[l].cpu().double() - ref_r).abs()
+            assert torch.isfinite(t_cls[l]).all() and torch.isfinite(t_box[l]).all(), f'level {l}: unwritten logits'
+            assert (err_c <= bound_c).all(), f'level {l} cls: max err {err_c.max():.3e}, bound {bound_c.max():.3e}'
+            assert (err_r <= bound_r).all(), f'level {l} box: max err {err_r.max():.3e}, bound {bound_r.max():.3e}'
+            # and far inside it on average (truncation errors do not all line up)
+            assert err_c.mean() < 0.1 * bound_c.mean() and err_r.mean() < 0.1 * bound_r.mean()
+
+        # ---- 2. the epilogue is the teacher pass
+        plain.ers_select(pp, t_cls, t_box)
+        torch.cuda.synchronize()
+        for name, dt in (('t_m', torch.int32), ('t_u', torch.int32), ('t_arg', torch.int32), ('t_dist', torch.int32)):
+            a, c = pf.workspace_field(name, dt), pp.workspace_field(name, dt)
+            assert torch.equal(a, c), f'{name}: {(a != c).sum().item()} of {a.numel()} words differ'
+
+        # ---- 3. the step behind it
+        outs = []
+        for path, p, cached in ((fused, pf, True), (plain, pp, False)):
+            p.set_targets(b.gt_bboxes, b.gt_labels, b.pad_shapes)
+            if cached:   # (the cache was written above; the standard path scans the logits itself)
+                pass
+            _, losses, g_cls, g_box = path.step(t_cls, t_box, b.s_cls, b.s_box, None, None, None, batch.num_classes,
+                                                ori, batch.reg_max, targets_set=True, teacher_cached=cached)
+            torch.cuda.synchronize()
+            outs.append((losses.clone(), [g.clone() for g in g_cls], [g.clone() for g in g_box], p.thr.clone(),
+                         p.cls_count.clone(), p.box_count.clone(), p.sel_flags.clone(), p.keep_count.clone()))
+        (lf, gcf, gbf, thrf, ccf, bcf, sff, kcf), (lp, gcp, gbp, thrp, ccp, bcp, sfp, kcp) = outs
+        assert torch.equal(thrf.view(torch.int32), thrp.view(torch.int32)), (thrf, thrp)
+        assert torch.equal(ccf, ccp) and torch.equal(bcf, bcp) and torch.equal(kcf, kcp)
+        assert int(ccp.sum()) > 0 and int(bcp.sum()) > 0, 'nothing selected: the test would be vacuous'
+        assert torch.equal(sff, sfp)
+        assert torch.equal(lf.view(torch.int32), lp.view(torch.int32)), (lf, lp)
+        for a, c in zip(gcf + gbf, gcp + gbp):
+            assert torch.equal(a.view(torch.int32), c.view(torch.int32))
+        if rep == 1:   # the fused epilogue stashed: selected anchors found their rows
+            slots = pf.workspace_field('t_slot', torch.int16).view(n, -1)
+            sel = (sff.view(n, -1) & 3) != 0
+            assert (slots[sel] != 0).float().mean() > 0.5, 'the fused epilogue did not stash the selected columns'
+        # the next round of the fused path starts from its own provisional thresholds
