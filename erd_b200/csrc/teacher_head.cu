@@ -49,7 +49,7 @@ constexpr int kAPlane = kHaloPx * 16;             // 5 184 B: one 16-byte chunk 
 constexpr int kATower = kAPlane * kPlanes;        // 41 472 B
 constexpr int kAStageBytes = 2 * kATower;         // cls tower + reg tower
 constexpr int kAStages = 2;
-constexpr int kBStages = 3;
+constexpr int kBStages = 4;                        // at most (as many as fit: 4 for ori <= 48, else 3)
 constexpr int kRegPad = 80;                       // 68 box channels padded to a legal UMMA N
 constexpr int kHeadThreads = 320;
 constexpr int kCopiesPerTower = kHaloPx * kPlanes;                 // 2 592 16-byte copies
@@ -72,7 +72,7 @@ struct HeadArgs {
   int stash_pitch;
   int emit;
   int n_acc, acc_stride;        // accumulator buffers in TMEM and their column stride
-  int b_stage_bytes;
+  int b_stage_bytes, b_stages;
 };
 
 struct HTile {
@@ -106,10 +106,8 @@ __device__ __forceinline__ void h_arrive(uint32_t bar) {
 __device__ __forceinline__ void h_commit(uint32_t bar) {   // arrives when every MMA issued so far has completed
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// K-major, no swizzle, version 1 (Blackwell): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | 1 << 46
-__device__ __forceinline__ uint64_t h_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
+// shared-memory matrix descriptor, K-major, no swizzle, version 1 (Blackwell):
+// start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | 1 << 46 (built as two 32-bit words by the issuer)
 __device__ __forceinline__ void h_mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
@@ -124,6 +122,15 @@ __device__ __forceinline__ void h_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// one lane of a converged warp (the same one every time): what issues MMAs / commits.  The surrounding control flow
+// stays warp-uniform, so descriptors live in uniform registers (a lane == 0 branch made the compiler waterfall
+// five R2UR broadcasts in a loop around every MMA: 60-100 cycles per issue, 4x the MMA's own time).
+__device__ __forceinline__ bool h_elect() {
+  uint32_t pred;
+  asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint64_t h_desc2(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 // instruction descriptor: D fp32, A / B tf32, both K-major, M = 128, N
 __host__ __device__ constexpr uint32_t h_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
@@ -135,7 +142,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
   __shared__ uint32_t s_tmem;
   unsigned char* sA = smem;
   unsigned char* sB = smem + kAStages * kAStageBytes;
-  float* s_bias = reinterpret_cast<float*>(sB + kBStages * A.b_stage_bytes);   // [ncls_pad] class, [80] box
+  float* s_bias = reinterpret_cast<float*>(sB + A.b_stages * A.b_stage_bytes);   // [ncls_pad] class, [80] box
   int* s_stash_cnt = reinterpret_cast<int*>(s_bias + A.ncls_pad + kRegPad);      // [n_img]
   const uint32_t bar0 = h_smem(s_bar);
   auto full_a = [&](int s) { return bar0 + 8u * s; };
@@ -174,8 +181,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
 
   if (warp < 4) {
     // ------------------------------------------------------------------ A producers
-    const int tid = threadIdx.x;
-    const int j = tid & 7;   // this thread's 16-byte chunk of the slice (128 is a multiple of 8: it never changes)
+    // Lane mapping: a warp instruction copies 4 pixels x 8 chunks (four full 128-byte lines of global memory); the 8
+    // lanes of each quarter warp (one shared-memory phase of a 16-byte access) take chunks {2a, 2a+1} of 4 consecutive
+    // pixels: plane stride 5 184 = 64 mod 128, so they land in 8 distinct 16-byte bank groups (j-major lanes were a 4-way
+    // conflict: 26 wavefronts per LDGSTS).
+    const int p4 = lane & 3;
+    const int j = 2 * (lane >> 3) + ((lane >> 2) & 1);
+    const int px0 = 4 * warp + p4;              // + 16 * i
     uint32_t it = 0;
     for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x) {
       const HTile b = h_tile(A, t);
@@ -183,7 +195,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
       uint32_t off[kCopyIters];   // source of copy i in 16-byte units, ~0: outside the map (zero fill)
 #pragma unroll
       for (int i = 0; i < kCopyIters; ++i) {
-        const int px = (tid >> 3) + 16 * i;
+        const int px = px0 + 16 * i;
         const int hy = px / kHalo, hx = px - hy * kHalo;
         const int gy = b.y0 - 1 + hy, gx = b.x0 - 1 + hx;
         const bool ok = px < kHaloPx && gy >= 0 && gy < H && gx >= 0 && gx < W;
@@ -194,10 +206,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
       for (int kc = 0; kc < kNKC; ++kc, ++it) {
         const int s = it % kAStages;
         h_wait(empty_a(s), ((it / kAStages) & 1u) ^ 1u);
-        const uint32_t dst = h_smem(sA + (size_t)s * kAStageBytes) + j * kAPlane + (tid >> 3) * 16;
+        const uint32_t dst = h_smem(sA + (size_t)s * kAStageBytes) + j * kAPlane + px0 * 16;
 #pragma unroll
         for (int i = 0; i < kCopyIters; ++i) {
-          if ((tid >> 3) + 16 * i < kHaloPx) {
+          if (px0 + 16 * i < kHaloPx) {
             const bool ok = off[i] != 0xFFFFFFFFu;
             const uint32_t o = ok ? off[i] + kc * kPlanes : 0u;
             const uint32_t sz = ok ? 16u : 0u;
@@ -214,14 +226,14 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
       }
     }
   } else if (warp == 4) {
-    // ------------------------------------------------------------------ B loader
-    if (lane == 0) {
-      uint32_t ib = 0;
-      const uint32_t cls_bytes = (uint32_t)ncp * 128u, reg_bytes = (uint32_t)kRegPad * 128u;
-      for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x) {
-        for (int kt = 0; kt < kNKC * 9; ++kt, ++ib) {   // (slice, tap) in the order the packed weights are stored
-          const int s = ib % kBStages;
-          h_wait(empty_b(s), ((ib / kBStages) & 1u) ^ 1u);
+    // ------------------------------------------------------------------ B loader (warp-uniform loops, one lane issues)
+    uint32_t ib = 0;
+    const uint32_t cls_bytes = (uint32_t)ncp * 128u, reg_bytes = (uint32_t)kRegPad * 128u;
+    for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x) {
+      for (int kt = 0; kt < kNKC * 9; ++kt, ++ib) {   // (slice, tap) in the order the packed weights are stored
+        const int s = ib % A.b_stages;
+        h_wait(empty_b(s), ((ib / A.b_stages) & 1u) ^ 1u);
+        if (h_elect()) {
           asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(full_b(s)), "r"(cls_bytes + reg_bytes) : "memory");
           const uint32_t dst = h_smem(sB + (size_t)s * A.b_stage_bytes);
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -229,48 +241,54 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                        ::"r"(dst + cls_bytes), "l"(A.w_reg + (size_t)kt * kRegPad * 32), "r"(reg_bytes), "r"(full_b(s)) : "memory");
         }
+        __syncwarp();
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc_cls = h_idesc(ncp), idesc_reg = h_idesc(kRegPad);
-      const uint32_t lbo_cls = (uint32_t)ncp * 16u, lbo_reg = (uint32_t)kRegPad * 16u;
-      uint32_t ia = 0, ib = 0, itile = 0;
-      for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, ++itile) {
-        const int acc = itile % A.n_acc;
-        h_wait(t_empty(acc), ((itile / A.n_acc) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d0 = tmem + acc * A.acc_stride;
-        for (int kc = 0; kc < kNKC; ++kc, ++ia) {
-          const int sa = ia % kAStages;
-          h_wait(full_a(sa), (ia / kAStages) & 1u);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          const uint32_t a_stage = h_smem(sA + (size_t)sa * kAStageBytes);
-          for (int tap = 0; tap < 9; ++tap, ++ib) {
-            const int sb = ib % kBStages;
-            h_wait(full_b(sb), (ib / kBStages) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint32_t a0 = a_stage + (dy * kHalo + dx) * 16;   // the tap: the same buffer, shifted start
-            const uint32_t bc = h_smem(sB + (size_t)sb * A.b_stage_bytes), br = bc + ncp * 128;
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loops, one lane issues)
+    const uint32_t idesc_cls = h_idesc(ncp), idesc_reg = h_idesc(kRegPad);
+    const uint32_t lbo_cls = (uint32_t)ncp * 16u, lbo_reg = (uint32_t)kRegPad * 16u;
+    // descriptor words: lo = start >> 4 | LBO >> 4 << 16, hi = SBO >> 4 | version 1 << 14
+    const uint32_t hi_a = (uint32_t)(kHalo * 16 >> 4) | (1u << 14), hi_b = (128u >> 4) | (1u << 14);
+    const uint32_t lo_a_lbo = (uint32_t)(kAPlane >> 4) << 16, lo_c_lbo = (lbo_cls >> 4) << 16, lo_r_lbo = (lbo_reg >> 4) << 16;
+    uint32_t ia = 0, ib = 0, itile = 0;
+    for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, ++itile) {
+      const int acc = itile % A.n_acc;
+      h_wait(t_empty(acc), ((itile / A.n_acc) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d0 = tmem + acc * A.acc_stride;
+      for (int kc = 0; kc < kNKC; ++kc, ++ia) {
+        const int sa = ia % kAStages;
+        h_wait(full_a(sa), (ia / kAStages) & 1u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t a_stage = h_smem(sA + (size_t)sa * kAStageBytes);
+        for (int tap = 0; tap < 9; ++tap, ++ib) {
+          const int sb = ib % A.b_stages;
+          h_wait(full_b(sb), (ib / A.b_stages) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int dy = tap / 3, dx = tap - dy * 3;
+          // the tap: the same buffer, shifted start (all in 16-byte units from here on)
+          const uint32_t a0 = ((a_stage + (dy * kHalo + dx) * 16) >> 4) | lo_a_lbo;
+          const uint32_t bc = h_smem(sB + (size_t)sb * A.b_stage_bytes);
+          const uint32_t bc0 = (bc >> 4) | lo_c_lbo, br0 = ((bc + ncp * 128) >> 4) | lo_r_lbo;
+          if (h_elect()) {
 #pragma unroll
             for (int s = 0; s < kKC / 8; ++s) {     // K = 8 per MMA: two 16-byte planes
 #pragma unroll
               for (int h = 0; h < 2; ++h) {         // left / right 8-pixel half of the patch: M = 16 rows x 8 pixels
                 const uint32_t accum = (kc | tap | s) ? 1u : 0u;
                 const uint32_t dh = d0 + h * (ncp + kRegPad);
-                h_mma(dh, h_desc(a0 + 2 * s * kAPlane + h * 128, kAPlane, kHalo * 16),
-                      h_desc(bc + 2 * s * lbo_cls, lbo_cls, 128), idesc_cls, accum);
-                h_mma(dh + ncp, h_desc(a0 + kATower + 2 * s * kAPlane + h * 128, kAPlane, kHalo * 16),
-                      h_desc(br + 2 * s * lbo_reg, lbo_reg, 128), idesc_reg, accum);
+                const uint32_t a_lo = a0 + (2 * s * kAPlane + h * 128) / 16;
+                h_mma(dh, h_desc2(a_lo, hi_a), h_desc2(bc0 + 2 * s * (lbo_cls >> 4), hi_b), idesc_cls, accum);
+                h_mma(dh + ncp, h_desc2(a_lo + kATower / 16, hi_a), h_desc2(br0 + 2 * s * (lbo_reg >> 4), hi_b), idesc_reg, accum);
               }
             }
             h_commit(empty_b(sb));
+            if (tap == 8) h_commit(empty_a(sa));
+            if (tap == 8 && kc == kNKC - 1) h_commit(t_full(acc));
           }
-          h_commit(empty_a(sa));
+          __syncwarp();
         }
-        h_commit(t_full(acc));
       }
     }
   } else {
@@ -479,9 +497,11 @@ cudaError_t launch_teacher_head(const Geo& g, const Workspace& ws, const Ptr5& f
   if (A.acc_stride > 512) return cudaErrorInvalidValue;
   A.n_acc = 2 * A.acc_stride <= 512 ? 2 : 1;
   A.b_stage_bytes = (A.ncls_pad + kRegPad) * 128;
-  const size_t smem = (size_t)kAStages * kAStageBytes + (size_t)kBStages * A.b_stage_bytes +
-                      (size_t)(A.ncls_pad + kRegPad) * 4 + (((size_t)g.n_img * 4 + 15) & ~(size_t)15);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  const size_t fixed = (size_t)kAStages * kAStageBytes + (size_t)(A.ncls_pad + kRegPad) * 4 + (((size_t)g.n_img * 4 + 15) & ~(size_t)15);
+  A.b_stages = kBStages;
+  while (A.b_stages > 2 && fixed + (size_t)A.b_stages * A.b_stage_bytes > 227 * 1024 - 256) --A.b_stages;
+  const size_t smem = fixed + (size_t)A.b_stages * A.b_stage_bytes;
+  if (smem > 227 * 1024 - 256) return cudaErrorInvalidValue;
   static size_t smem_set = 0;
   static int sms = 0;
   if (!sms) {
