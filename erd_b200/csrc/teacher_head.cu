@@ -23,7 +23,7 @@
 // Input layout: NHWC fp32 (torch channels_last), so a pixel's 32 channels are one 128-byte line.
 //
 // Warp roles (320 threads, one CTA per SM, persistent over the patches):
-//   warps 0-3  A producers: 16-byte cp.async (zero-fill = padding) into the stage, two stages;
+//   warps 0-3  A producers: 16-byte loads -> 16-byte shared stores (zeros = padding) into the stage, two stages;
 //   warp  4    B loader: one elected lane, 1-D bulk copies (cp.async.bulk) of the pre-packed weight tile of
 //              (32-channel slice, tap) -- the packed image IS the shared-memory image -- three stages;
 //   warp  5    TMEM allocation + the single MMA-issuing thread (tcgen05.mma kind::tf32, commit -> mbarriers);
@@ -54,6 +54,7 @@ constexpr int kRegPad = 80;                       // 68 box channels padded to a
 constexpr int kHeadThreads = 320;
 constexpr int kCopiesPerTower = kHaloPx * kPlanes;                 // 2 592 16-byte copies
 constexpr int kCopyIters = (kCopiesPerTower + 127) / 128;         // 21 per producer thread
+constexpr int kCopyBatch = 7;                                      // loads in flight per thread and tower
 
 struct HeadArgs {
   Ptr5 f_cls, f_reg;            // NHWC (N, H, W, 256)
@@ -121,6 +122,14 @@ __device__ __forceinline__ void h_ld8(uint32_t taddr, float (&v)[8]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float4 h_ldg16(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void h_sts16(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 // one lane of a converged warp (the same one every time): what issues MMAs / commits.  The surrounding control flow
 // stays warp-uniform, so descriptors live in uniform registers (a lane == 0 branch made the compiler waterfall
@@ -207,20 +216,27 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
         const int s = it % kAStages;
         h_wait(empty_a(s), ((it / kAStages) & 1u) ^ 1u);
         const uint32_t dst = h_smem(sA + (size_t)s * kAStageBytes) + j * kAPlane + px0 * 16;
+        // global -> registers -> 16-byte shared stores, in three batches of 14 loads per thread (28 KB in flight per
+        // SM).  (cp.async writes shared memory sector by sector as the data return: 21 wavefronts per warp
+        // instruction instead of 4, a quarter of the shared-memory bandwidth the MMA operand fetch needs.)
 #pragma unroll
-        for (int i = 0; i < kCopyIters; ++i) {
-          if (px0 + 16 * i < kHaloPx) {
-            const bool ok = off[i] != 0xFFFFFFFFu;
-            const uint32_t o = ok ? off[i] + kc * kPlanes : 0u;
-            const uint32_t sz = ok ? 16u : 0u;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * 256), "l"(fc + o), "r"(sz) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + kATower + i * 256), "l"(fr + o), "r"(sz) : "memory");
+        for (int b0 = 0; b0 < kCopyIters; b0 += kCopyBatch) {
+          float4 vc[kCopyBatch], vr[kCopyBatch];
+#pragma unroll
+          for (int i = 0; i < kCopyBatch; ++i) {
+            const bool ok = off[b0 + i] != 0xFFFFFFFFu;
+            vc[i] = ok ? h_ldg16(fc + off[b0 + i] + kc * kPlanes) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vr[i] = ok ? h_ldg16(fr + off[b0 + i] + kc * kPlanes) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < kCopyBatch; ++i) {
+            if (px0 + 16 * (b0 + i) < kHaloPx) {
+              h_sts16(dst + (b0 + i) * 256, vc[i]);
+              h_sts16(dst + kATower + (b0 + i) * 256, vr[i]);
+            }
           }
         }
-        // this thread's copies have landed: make them visible to the tensor core's (async) proxy and hand the stage
-        // over.  (The other stage is being consumed meanwhile; a stage fills faster than the MMAs drain one.)
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // make the stage visible to the tensor core's (async) proxy and hand it over
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         h_arrive(full_a(s));
       }
