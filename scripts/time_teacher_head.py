@@ -93,6 +93,55 @@ def main():
     lib.erd_profile_enable(0)
     i = names.index('ers_scan')
     out['teacher_pass_scan_ms'] = tot[i] / max(cnt[i], 1)
+    # ---- the whole teacher side + loss step, replayed from CUDA graphs (16 images of synthetic student outputs / GT)
+    from erd_b200.synth import make_batch
+    batch = make_batch(n, (args.hw[0], args.hw[1] - 11 if args.hw[1] == 1344 else args.hw[1]), ori=ori, seed=1234)
+    assert batch.shapes == shapes, (batch.shapes, shapes)
+    b = batch.to(dev)
+    p.set_targets(b.gt_bboxes, b.gt_labels, b.pad_shapes)
+    g_cls = [torch.empty_like(t) for t in b.s_cls]
+    g_box = [torch.empty_like(t) for t in b.s_box]
+    losses = torch.empty(p.num_losses, device=dev)
+
+    def loss_step(cached):
+        path.prepare(p, t_cls, t_box, b.s_cls, b.s_box, teacher_cached=cached)
+        path.reduce_avg(p)
+        path.loss_fwd_bwd(p, t_cls, t_box, b.s_cls, b.s_box, g_cls, g_box, losses, 1.0)
+
+    def graphed(fn):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        return timed(gr.replay, args.iters)
+
+    path.teacher_head_fused(p, head, cls_f, reg_f, t_cls, t_box)   # real logits for the standard step
+    out['loss_step_standard_ms'] = graphed(lambda: loss_step(False))
+    l_std = losses.clone()
+
+    def fused_then_step():
+        path.teacher_head_fused(p, head, cls_f, reg_f, t_cls, t_box)
+        loss_step(True)
+    out['fused_emit_plus_loss_step_ms'] = graphed(fused_then_step)
+    out['losses_identical_to_standard_step'] = bool(torch.equal(losses, l_std))
+
+    def fused_noemit_then_step():
+        path.teacher_head_fused(p, head, cls_f, reg_f)
+        loss_step(True)
+    out['fused_no_emit_plus_loss_step_ms'] = graphed(fused_noemit_then_step)
+
+    def cudnn_then_step():
+        for l in range(5):
+            F.conv2d(cls_f[l], w_cls, b_cls, padding=1)
+            F.conv2d(reg_f[l], w_reg, b_reg, padding=1).mul_(scales[l])
+        loss_step(False)
+    out['cudnn_convs_plus_loss_step_ms'] = graphed(cudnn_then_step)
     print(json.dumps(out))
 
 
