@@ -65,6 +65,7 @@ SIGNATURES = {
     'erd_teacher_head_pack': [_P, _I, _P, _P],
     'erd_teacher_head_fused': [_SH, C.POINTER(ErdTeacherHead), PtrArray, PtrArray, C.POINTER(PtrArray), C.POINTER(PtrArray),
                                _P, _P, _P, _P],
+    'erd_ers_select_cached': [_SH, _P, _P, _P, _P, _P, _P, _P, _P],
     'erd_atss_assign': [_SH, _P, _P, _P, _P, _P, _P, _P, _P],
     'erd_avg_factors': [_SH, PtrArray, PtrArray, _P, _P, _P, _P, _P, _P, _P, _P],
     'erd_teacher_nms': [_SH, _P, _P, _P, _F, _P, _P, _P, _P, _P],

@@ -299,6 +299,20 @@ int erd_teacher_head_fused(const ErdShape* shape, const ErdTeacherHead* head, co
   return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_teacher_head_fused");
 }
 
+int erd_ers_select_cached(const ErdShape* shape, int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds,
+                          int32_t* box_count, float* thr, uint8_t* sel_flags, void* wsp, void* stream) {
+  Geo g;
+  int rc = make_geo(shape, &g);
+  if (rc) return rc;
+  if (!cls_inds || !cls_count || !box_inds || !box_count || !thr || !sel_flags || !wsp)
+    return fail(ERD_ERR_NULL, "erd_ers_select_cached: NULL argument");
+  Workspace ws;
+  carve(g, wsp, &ws);
+  cudaError_t e = launch_ers_flags(g, ws, head_partials_per_img(g), thr, sel_flags, cls_count, box_count, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = launch_ers_lists(g, ws, cls_inds, cls_count, box_inds, box_count, thr, sel_flags, (cudaStream_t)stream);
+  return e == cudaSuccess ? ERD_OK : fail_cuda(e, "erd_ers_select_cached");
+}
+
 int erd_atss_assign(const ErdShape* shape, const float* gt_boxes, const int64_t* gt_labels,
                     const int32_t* gt_offsets, const int32_t* pad_hw, int32_t* gt_inds, int32_t* num_pos, void* wsp,
                     void* stream) {

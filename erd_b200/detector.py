@@ -17,12 +17,13 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from .head import ErsSelection, GFLHeadIncrementERD, fused_sel_pos
+from .head import ErsSelection, GFLHeadIncrementERD, fused_sel_pos, fused_teacher_head
 
 
 class GFLIncrementERD(nn.Module):
     def __init__(self, bbox_head: GFLHeadIncrementERD, ori_num_classes: int, ori_model: Optional[nn.Module] = None,
-                 extract_feat: Optional[Callable] = None, top_k: int = 100, dist_loss_weight: float = 1) -> None:
+                 extract_feat: Optional[Callable] = None, top_k: int = 100, dist_loss_weight: float = 1,
+                 fuse_teacher_head: bool = False) -> None:
         super().__init__()
         self.bbox_head = bbox_head
         self.ori_num_classes = int(ori_num_classes)
@@ -30,6 +31,9 @@ class GFLIncrementERD(nn.Module):
         self.dist_loss_weight = dist_loss_weight
         self.ori_model = ori_model              # frozen teacher: images -> (cls_scores, bbox_preds)
         self._extract_feat = extract_feat       # student backbone + neck
+        # run the teacher's last head convolutions inside the teacher pass.  Needs a teacher with
+        # ``extract_feat`` and a ``bbox_head`` that exposes its towers (see ``fused_teacher_head``).
+        self.fuse_teacher_head = bool(fuse_teacher_head)
         if ori_model is not None:
             for p in ori_model.parameters():    # :115-116
                 p.requires_grad = False
@@ -74,9 +78,17 @@ class GFLIncrementERD(nn.Module):
 
     def loss(self, batch_inputs: Tensor, batch_data_samples) -> dict:
         """gfl_increment_erd.py:202-220."""
-        with torch.no_grad():   # the reference relies on requires_grad=False instead (:205)
-            ori_outs = self.ori_model(batch_inputs)
-        sel = self.sel_pos(*ori_outs)
+        if self.fuse_teacher_head:
+            head = self.bbox_head
+            with torch.no_grad():
+                ori_outs, (cls_sel, box_sel), _ = fused_teacher_head(
+                    head.path, self.ori_model.bbox_head, self.ori_model.extract_feat(batch_inputs), head.num_classes,
+                    head.reg_max)
+            sel = (cls_sel, _LazyGather(cls_sel, ori_outs[0]), box_sel, _LazyGather(box_sel, ori_outs[1]))
+        else:
+            with torch.no_grad():   # the reference relies on requires_grad=False instead (:205)
+                ori_outs = self.ori_model(batch_inputs)
+            sel = self.sel_pos(*ori_outs)
         new_outs = self.bbox_head(self._extract_feat(batch_inputs))
         return self.bbox_head.loss(ori_outs, new_outs, batch_data_samples, *sel, self.ori_num_classes,
                                    self.dist_loss_weight, self)

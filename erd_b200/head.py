@@ -139,6 +139,39 @@ def fused_sel_pos(path: ErdPath, num_classes: int, reg_max: int, ori_num_classes
     return plan, t_cls, t_box, ErsSelection(plan, 'cls', gen), ErsSelection(plan, 'box', gen)
 
 
+def fused_teacher_head(path: ErdPath, teacher_head, feats, num_classes: int, reg_max: int):
+    """The teacher's head with its LAST convolutions fused into the teacher pass (SURVEY 8(f) rank 1;
+    ``gfl_head.py:205-230`` + ``gfl_increment_erd.py:143-200,205`` in one tcgen05 kernel): the towers run in
+    PyTorch/cuDNN (channels_last, so their outputs are the NHWC tensors the kernel streams), ``gfl_cls`` /
+    ``gfl_reg`` + bias + Scale run inside ``erd_teacher_head_fused``, whose epilogue writes the per-anchor teacher
+    cache, the threshold sums and the stash; the logits are still emitted (write-only) because ``loss_by_feat``
+    takes them as ``ori_outs``.  ``teacher_head``: a module with ``cls_convs``, ``reg_convs``, ``gfl_cls``,
+    ``gfl_reg`` and ``scales`` (the standalone ``GFLHeadIncrementERD`` or mmdet's ``GFLHead``).
+    Returns ((cls_scores, bbox_preds), (topk_cls_inds, topk_bbox_inds), plan)."""
+    from .ops import TeacherHead
+    th = getattr(teacher_head, '_erd_packed', None)
+    if th is None or th.packed[0].device != feats[0].device:
+        sc = teacher_head.scales
+        scales = ([float(v) for v in sc.detach().flatten()] if isinstance(sc, torch.Tensor)
+                  else [float(m.scale.detach()) for m in sc])      # mmdet: ModuleList of Scale
+        th = TeacherHead(teacher_head.gfl_cls.weight, teacher_head.gfl_cls.bias, teacher_head.gfl_reg.weight,
+                         teacher_head.gfl_reg.bias, scales)
+        teacher_head._erd_packed = th       # the teacher is frozen: packed once
+    cls_f, reg_f = [], []
+    for f in feats:
+        f = f.contiguous(memory_format=torch.channels_last)
+        cls_f.append(teacher_head.cls_convs(f).float().contiguous(memory_format=torch.channels_last))
+        reg_f.append(teacher_head.reg_convs(f).float().contiguous(memory_format=torch.channels_last))
+    n, ori = int(cls_f[0].shape[0]), th.ori
+    plan = path.plan(cls_f, num_classes, ori, reg_max)
+    t_cls = [torch.empty(n, ori, h, w, dtype=torch.float32, device=cls_f[0].device) for h, w in plan.shapes]
+    t_box = [torch.empty(n, 4 * (reg_max + 1), h, w, dtype=torch.float32, device=cls_f[0].device) for h, w in plan.shapes]
+    path.teacher_head_fused(plan, th, cls_f, reg_f, t_cls, t_box)
+    path.ers_select_cached(plan)
+    gen = plan.ers_generation
+    return (t_cls, t_box), (ErsSelection(plan, 'cls', gen), ErsSelection(plan, 'box', gen)), plan
+
+
 def _cfg_get(cfg, key, default=None):
     return cfg.get(key, default) if cfg is not None else default
 

@@ -275,6 +275,14 @@ class ErdPath:
                                                 p.cls_count.data_ptr(), p.box_count.data_ptr(), p.ws.data_ptr(),
                                                 _stream()), 'erd_teacher_head_fused')
 
+    def ers_select_cached(self, p: Plan):
+        """Thresholds, flags and ordered lists from the cache ``teacher_head_fused`` has just written."""
+        N.check(self.lib.erd_ers_select_cached(C.byref(p.shape), p.cls_inds.data_ptr(), p.cls_count.data_ptr(),
+                                               p.box_inds.data_ptr(), p.box_count.data_ptr(), p.thr.data_ptr(),
+                                               p.sel_flags.data_ptr(), p.ws.data_ptr(), _stream()),
+                'erd_ers_select_cached')
+        p.ers_generation += 1
+
     def atss_assign(self, p: Plan):
         N.check(self.lib.erd_atss_assign(C.byref(p.shape), p.gt_boxes.data_ptr(), p.gt_labels.data_ptr(),
                                          p.gt_offsets.data_ptr(), p.pad_hw.data_ptr(), p.gt_inds.data_ptr(),

@@ -252,6 +252,12 @@ int erd_teacher_head_fused(const ErdShape* shape, const ErdTeacherHead* head, co
                            const float* const* reg_feat, float* const* t_cls_out, float* const* t_box_out,
                            int32_t* cls_count, int32_t* box_count, void* ws, void* stream);
 
+/* erd_ers_select without its streaming scan, for a workspace whose teacher cache and threshold sums
+ * erd_teacher_head_fused has just written (same stream): thresholds, flags, counts and the ordered lists
+ * (GFLIncrementERD.sel_pos, gfl_increment_erd.py:143-200).  Outputs as erd_ers_select. */
+int erd_ers_select_cached(const ErdShape* shape, int32_t* cls_inds, int32_t* cls_count, int32_t* box_inds,
+                          int32_t* box_count, float* thr, uint8_t* sel_flags, void* ws, void* stream);
+
 /* --- inference post-process (next row of the scope table) ---------------------------
  * Replaces GFLHead._predict_by_feat_single (mmdet/models/dense_heads/gfl_head.py:408-502) with
  * filter_scores_and_topk (mmdet/models/utils/misc.py:308-354) and BaseDenseHead._bbox_post_process

@@ -103,3 +103,86 @@ def test_fused_teacher_head(ori, img_hw, n):
             sel = (sff.view(n, -1) & 3) != 0
             assert (slots[sel] != 0).float().mean() > 0.5, 'the fused epilogue did not stash the selected columns'
         # the next round of the fused path starts from its own provisional thresholds
+
+
+def test_detector_loss_with_fused_teacher_head():
+    """GFLIncrementERD.loss (gfl_increment_erd.py:202-220) with ``fuse_teacher_head=True``: the teacher's towers in
+    PyTorch, its last convolutions inside the teacher pass.  The loss dict and the student's gradients must be the
+    bits of the standard route (teacher forward -> sel_pos -> loss) run on the logits the fused route emitted, and
+    those logits must be the teacher's convolutions."""
+    import torch.nn as nn
+    from erd_b200.detector import GFLIncrementERD
+    from erd_b200.head import GFLHeadIncrementERD, parse_losses
+
+    torch.manual_seed(7)
+    dev = 'cuda'
+    tc = dict(assigner=dict(type='ATSSAssigner', topk=9), allowed_border=-1, pos_weight=-1)
+
+    class Body(nn.Module):   # stand-in for backbone + FPN: five 256-channel levels
+        def __init__(self):
+            super().__init__()
+            self.stem = nn.Conv2d(3, 256, 3, stride=8, padding=1)
+
+        def forward(self, x):
+            f = torch.relu(self.stem(x))
+            out = [f]
+            for _ in range(4):
+                out.append(torch.nn.functional.avg_pool2d(out[-1], 2, 2, ceil_mode=True))
+            return out
+
+    class Teacher(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = Body()
+            self.bbox_head = GFLHeadIncrementERD(40, 256, stacked_convs=2, reg_max=16, train_cfg=tc)
+
+        def extract_feat(self, x):
+            return self.body(x)
+
+        def forward(self, x):
+            return self.bbox_head(self.extract_feat(x))
+
+    teacher = Teacher().to(dev)
+    with torch.no_grad():   # a trained-looking teacher: some confident responses
+        teacher.bbox_head.gfl_cls.weight.mul_(6.0)
+        teacher.bbox_head.gfl_reg.weight.mul_(6.0)
+        teacher.bbox_head.scales.copy_(torch.tensor([1.0, 0.9, 1.1, 1.2, 0.8]))
+    student_body = Body().to(dev)
+    head = GFLHeadIncrementERD(80, 256, stacked_convs=2, reg_max=16, train_cfg=tc).to(dev)
+    n, H, W = 2, 256, 320
+    x = torch.randn(n, 3, H, W, device=dev)
+    gts = [type('GT', (), dict(bboxes=torch.tensor([[20., 30., 120., 140.], [150., 60., 300., 220.]], device=dev),
+                               labels=torch.tensor([3, 17], device=dev)))() for _ in range(n)]
+    samples = [type('S', (), dict(gt_instances=g, metainfo=dict(img_shape=(H, W), pad_shape=(H, W))))() for g in gts]
+
+    def run(fuse, ori_outs_override=None):
+        det = GFLIncrementERD(head, 40, ori_model=teacher if ori_outs_override is None else None,
+                              extract_feat=student_body, fuse_teacher_head=fuse)
+        if ori_outs_override is not None:
+            det.ori_model = lambda _x: ori_outs_override
+        head.zero_grad(set_to_none=True)
+        student_body.zero_grad(set_to_none=True)
+        losses = det.loss(x, samples)
+        parse_losses(losses).backward()
+        torch.cuda.synchronize()
+        flat = torch.stack(losses['loss_cls'] + losses['loss_bbox'] + losses['loss_dfl'] + losses['loss_dist_cls'] +
+                           losses['loss_dist_bbox']).detach().clone()
+        grads = [p.grad.detach().clone() for p in list(head.parameters()) + list(student_body.parameters())
+                 if p.grad is not None]
+        return flat, grads
+
+    flat_f, grads_f = run(True)
+    # the logits the fused route emitted (re-run the fused head to fetch them) against the teacher's own forward
+    from erd_b200.head import fused_teacher_head
+    with torch.no_grad():
+        (t_cls, t_box), (cls_sel, box_sel), plan = fused_teacher_head(head.path, teacher.bbox_head, teacher.extract_feat(x), 80, 16)
+        ref_cls, ref_box = teacher(x)
+    for a, r in zip(t_cls + t_box, ref_cls + ref_box):
+        assert (a - r).abs().max() <= 2e-2 * max(1.0, float(r.abs().max())), 'emitted logits are not the head convolutions'
+    assert sum(int(c) for c in plan.cls_count) > 0 and sum(int(c) for c in plan.box_count) > 0
+    flat_s, grads_s = run(False, ori_outs_override=(t_cls, t_box))
+    assert torch.isfinite(flat_f).all()
+    assert torch.equal(flat_f.view(torch.int32), flat_s.view(torch.int32)), (flat_f, flat_s)
+    assert len(grads_f) == len(grads_s) and len(grads_f) > 0
+    for a, c in zip(grads_f, grads_s):
+        assert torch.allclose(a, c, rtol=1e-4, atol=1e-7)   # cuDNN backward of the student convs is not run-to-run exact
