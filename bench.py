@@ -75,6 +75,7 @@ def parse():
     ap.add_argument('--imgs', type=int, default=0, help='images per GPU (default: the config\'s)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-teacher-head', action='store_true', help='skip the fused teacher-head side measurement')
     return ap.parse_args()
 
 
@@ -183,6 +184,93 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- our arm
+def time_teacher_head(path, plan, b, g_cls, g_box, losses, n, A, ori, steps):
+    """The teacher side + loss step with the last head convolutions (a) in cuDNN followed by the standard step and
+    (b) inside erd_teacher_head_fused followed by the step with ERD_PREPARE_TEACHER_CACHED.  Synthetic tower
+    features (post-ReLU N(0,1), NHWC) and head weights; CUDA graph replay, CUDA events."""
+    import torch.nn.functional as F
+    from erd_b200.ops import TeacherHead
+    dev = b.s_cls[0].device
+    gen = torch.Generator(device=dev).manual_seed(77)
+    shapes = [tuple(t.shape[2:]) for t in b.s_cls]
+    feat = lambda h, w: torch.randn(n, 256, h, w, device=dev, generator=gen).relu_().contiguous(memory_format=torch.channels_last)
+    cls_f, reg_f = [feat(h, w) for h, w in shapes], [feat(h, w) for h, w in shapes]
+    w_cls = torch.randn(ori, 256, 3, 3, device=dev, generator=gen) * 0.03
+    w_reg = torch.randn(68, 256, 3, 3, device=dev, generator=gen) * 0.03
+    b_cls, b_reg = torch.full((ori,), -4.6, device=dev), torch.zeros(68, device=dev)
+    head = TeacherHead(w_cls, b_cls, w_reg, b_reg, [1.0] * 5)
+    t_cls = [torch.empty(n, ori, h, w, device=dev) for h, w in shapes]
+    t_box = [torch.empty(n, 68, h, w, device=dev) for h, w in shapes]
+
+    def loss_step(cached):
+        path.prepare(plan, t_cls, t_box, b.s_cls, b.s_box, teacher_cached=cached)
+        path.reduce_avg(plan)
+        path.loss_fwd_bwd(plan, t_cls, t_box, b.s_cls, b.s_box, g_cls, g_box, losses, 1.0)
+
+    def cudnn_convs():
+        for l in range(5):
+            t_cls[l] = F.conv2d(cls_f[l], w_cls, b_cls, padding=1)
+            t_box[l] = F.conv2d(reg_f[l], w_reg, b_reg, padding=1).mul_(1.0)
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def graphed(fn, iters):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        return timed(gr.replay, iters)
+
+    iters = max(10, min(steps, 50))
+    out = {'what': 'teacher head last convs (256 -> ori / 68, 3x3) + teacher pass + loss step, one GPU, '
+                   f'{n} images x {A} anchors, tower features NHWC fp32 synthetic; CUDA graph replay',
+           'math': 'tcgen05 kind::tf32, fp32 accumulate (cuDNN arm: torch default allow_tf32 for convolutions)'}
+    out['fused_kernel_ms'] = timed(lambda: path.teacher_head_fused(plan, head, cls_f, reg_f, t_cls, t_box), iters)
+    out['fused_kernel_no_logits_ms'] = timed(lambda: path.teacher_head_fused(plan, head, cls_f, reg_f), iters)
+    out['cudnn_convs_ms'] = timed(cudnn_convs, iters)
+    flops = 2.0 * n * A * 2304 * (ori + 68)
+    out['fused_kernel_useful_tflops'] = flops / out['fused_kernel_no_logits_ms'] / 1e9
+    out['cudnn_convs_useful_tflops'] = flops / out['cudnn_convs_ms'] / 1e9
+    t_cls = [torch.empty(n, ori, h, w, device=dev) for h, w in shapes]
+    t_box = [torch.empty(n, 68, h, w, device=dev) for h, w in shapes]
+    path.teacher_head_fused(plan, head, cls_f, reg_f, t_cls, t_box)
+
+    def std_nocopy():
+        for l in range(5):
+            F.conv2d(cls_f[l], w_cls, b_cls, padding=1)
+            F.conv2d(reg_f[l], w_reg, b_reg, padding=1).mul_(1.0)
+        loss_step(False)
+
+    def fused():
+        path.teacher_head_fused(plan, head, cls_f, reg_f, t_cls, t_box)
+        loss_step(True)
+    out['cudnn_convs_plus_step_ms'] = graphed(std_nocopy, iters)
+    loss_step(False)
+    torch.cuda.synchronize()
+    l_std = losses.clone()
+    out['fused_plus_step_ms'] = graphed(fused, iters)
+    torch.cuda.synchronize()
+    out['losses_bit_identical_to_standard_step_on_the_emitted_logits'] = bool(torch.equal(losses, l_std))
+    out['speedup_teacher_side_plus_step'] = out['cudnn_convs_plus_step_ms'] / out['fused_plus_step_ms']
+    return out
+
+
 def run_ours(args):
     if os.environ.get('ERD_BENCH_DEBUG'):
         import faulthandler
@@ -395,6 +483,16 @@ def run_ours(args):
                'h2d_gbs_per_rank': h2d * e_steps / float(dt.item()) / 1e9,
                'api': 'GFLIncrementERD.sel_pos + GFLHeadIncrementERD.loss_by_feat + backward, pinned host tensors'}
 
+    # ---- SURVEY 8(f) rank 1, measured beside the headline (not part of `value`): the teacher head's last convolutions
+    # fused with the teacher pass (erd_teacher_head_fused, tcgen05 TF32) against cuDNN's convolutions + the standard
+    # step, teacher side + loss step replayed from one CUDA graph each; same student tensors / GT as the headline.
+    fused_head = None
+    if world == 1 and not args.no_teacher_head:
+        try:
+            fused_head = time_teacher_head(path, plan, b, g_cls, g_box, losses, n, A, ORI, args.steps)
+        except Exception as e:   # never lose the headline over the side measurement
+            fused_head = {'error': repr(e)[:300]}
+
     if world > 1:
         from erd_b200.dist_utils import peer_exchange
         collective = ('8-byte avg-factor mean: one kernel over NVLink peer memory (erd_avg_exchange)'
@@ -438,7 +536,7 @@ def run_ours(args):
             'launch_mode': {'value_from': 'cuda_graph_replay' if ms_graph is not None else 'eager',
                             'ms_per_step_eager': ms_eager / args.steps, 'graph_error': graph_err},
             'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'api_device_resident': api,
-            'multi_rank_check': multi,
+            'multi_rank_check': multi, 'teacher_head_fused': fused_head,
         }
         if not args.no_cpu_baseline and world == 1:
             anchors, times, cores = time_cpu_oracle(n, 10, 2, budget_s=25.0)
