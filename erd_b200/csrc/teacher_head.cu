@@ -74,6 +74,7 @@ struct HeadArgs {
   int emit;
   int n_acc, acc_stride;        // accumulator buffers in TMEM and their column stride
   int b_stage_bytes, b_stages;
+  int exp;                      // developer experiments (-DERD_HEAD_EXP, env ERD_HEAD_EXP): results are garbage when set
 };
 
 struct HTile {
@@ -219,6 +220,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
         // global -> registers -> 16-byte shared stores, in three batches of 14 loads per thread (28 KB in flight per
         // SM).  (cp.async writes shared memory sector by sector as the data return: 21 wavefronts per warp
         // instruction instead of 4, a quarter of the shared-memory bandwidth the MMA operand fetch needs.)
+#ifdef ERD_HEAD_EXP
+        if (!(A.exp & 1))
+#endif
 #pragma unroll
         for (int b0 = 0; b0 < kCopyIters; b0 += kCopyBatch) {
           float4 vc[kCopyBatch], vr[kCopyBatch];
@@ -249,6 +253,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
       for (int kt = 0; kt < kNKC * 9; ++kt, ++ib) {   // (slice, tap) in the order the packed weights are stored
         const int s = ib % A.b_stages;
         h_wait(empty_b(s), ((ib / A.b_stages) & 1u) ^ 1u);
+#ifdef ERD_HEAD_EXP
+        if (A.exp & 2) {
+          if (h_elect()) h_arrive(full_b(s));
+          __syncwarp();
+          continue;
+        }
+#endif
         if (h_elect()) {
           asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(full_b(s)), "r"(cls_bytes + reg_bytes) : "memory");
           const uint32_t dst = h_smem(sB + (size_t)s * A.b_stage_bytes);
@@ -287,6 +298,45 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
           const uint32_t a0 = ((a_stage + (dy * kHalo + dx) * 16) >> 4) | lo_a_lbo;
           const uint32_t bc = h_smem(sB + (size_t)sb * A.b_stage_bytes);
           const uint32_t bc0 = (bc >> 4) | lo_c_lbo, br0 = ((bc + ncp * 128) >> 4) | lo_r_lbo;
+#ifdef ERD_HEAD_EXP
+          if ((A.exp & 16) && h_elect()) {   // chain-major order: each accumulator's four K steps back to back
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int tw = 0; tw < 2; ++tw) {
+#pragma unroll
+                for (int s = 0; s < kKC / 8; ++s) {
+                  const uint32_t accum = (kc | tap | s) ? 1u : 0u;
+                  const uint32_t dh = d0 + h * (ncp + kRegPad);
+                  const uint32_t a_lo = a0 + (2 * s * kAPlane + h * 128) / 16;
+                  if (tw == 0) h_mma(dh, h_desc2(a_lo, hi_a), h_desc2(bc0 + 2 * s * (lbo_cls >> 4), hi_b), idesc_cls, accum);
+                  else h_mma(dh + ncp, h_desc2(a_lo + kATower / 16, hi_a), h_desc2(br0 + 2 * s * (lbo_reg >> 4), hi_b), idesc_reg, accum);
+                }
+              }
+            }
+          }
+          if ((A.exp & 32) && h_elect()) {   // K split: odd K steps accumulate into a second set of columns (n_acc forced to 1)
+#pragma unroll
+            for (int s = 0; s < kKC / 8; ++s) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t accum = (kc | tap | (s >> 1)) ? 1u : 0u;
+                const uint32_t dh = d0 + h * (ncp + kRegPad) + (s & 1) * 256;
+                const uint32_t a_lo = a0 + (2 * s * kAPlane + h * 128) / 16;
+                h_mma(dh, h_desc2(a_lo, hi_a), h_desc2(bc0 + 2 * s * (lbo_cls >> 4), hi_b), idesc_cls, accum);
+                h_mma(dh + ncp, h_desc2(a_lo + kATower / 16, hi_a), h_desc2(br0 + 2 * s * (lbo_reg >> 4), hi_b), idesc_reg, accum);
+              }
+            }
+          }
+          if ((A.exp & 64) && h_elect()) {   // no MMAs at all: the barrier protocol alone
+          }
+          if ((A.exp & (48 | 64)) && h_elect()) {
+            h_commit(empty_b(sb));
+            if (tap == 8) h_commit(empty_a(sa));
+            if (tap == 8 && kc == kNKC - 1) h_commit(t_full(acc));
+          }
+          if (!(A.exp & (48 | 64)))
+#endif
           if (h_elect()) {
 #pragma unroll
             for (int s = 0; s < kKC / 8; ++s) {     // K = 8 per MMA: two 16-byte planes
@@ -295,7 +345,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
                 const uint32_t accum = (kc | tap | s) ? 1u : 0u;
                 const uint32_t dh = d0 + h * (ncp + kRegPad);
                 const uint32_t a_lo = a0 + (2 * s * kAPlane + h * 128) / 16;
+#ifdef ERD_HEAD_EXP
+                if (!(A.exp & 8))
+#endif
                 h_mma(dh, h_desc2(a_lo, hi_a), h_desc2(bc0 + 2 * s * (lbo_cls >> 4), hi_b), idesc_cls, accum);
+#ifdef ERD_HEAD_EXP
+                if (!(A.exp & 4))
+#endif
                 h_mma(dh + ncp, h_desc2(a_lo + kATower / 16, hi_a), h_desc2(br0 + 2 * s * (lbo_reg >> 4), hi_b), idesc_reg, accum);
               }
             }
@@ -486,6 +542,10 @@ cudaError_t launch_teacher_head(const Geo& g, const Workspace& ws, const Ptr5& f
   A.f_cls = f_cls;
   A.f_reg = f_reg;
   A.emit = (o_cls && o_box) ? 1 : 0;
+  A.exp = 0;
+#ifdef ERD_HEAD_EXP
+  if (const char* e = getenv("ERD_HEAD_EXP")) A.exp = atoi(e);
+#endif
   for (int l = 0; l < kLevels; ++l) {
     A.o_cls.p[l] = A.emit ? o_cls->p[l] : nullptr;
     A.o_box.p[l] = A.emit ? o_box->p[l] : nullptr;
@@ -512,6 +572,9 @@ cudaError_t launch_teacher_head(const Geo& g, const Workspace& ws, const Ptr5& f
   A.acc_stride = 2 * (A.ncls_pad + kRegPad);
   if (A.acc_stride > 512) return cudaErrorInvalidValue;
   A.n_acc = 2 * A.acc_stride <= 512 ? 2 : 1;
+#ifdef ERD_HEAD_EXP
+  if (A.exp & 32) A.n_acc = 1;
+#endif
   A.b_stage_bytes = (A.ncls_pad + kRegPad) * 128;
   const size_t fixed = (size_t)kAStages * kAStageBytes + (size_t)(A.ncls_pad + kRegPad) * 4 + (((size_t)g.n_img * 4 + 15) & ~(size_t)15);
   A.b_stages = kBStages;
