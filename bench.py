@@ -247,6 +247,20 @@ def time_teacher_head(path, plan, b, g_cls, g_box, losses, n, A, ori, steps):
     flops = 2.0 * n * A * 2304 * (ori + 68)
     out['fused_kernel_useful_tflops'] = flops / out['fused_kernel_no_logits_ms'] / 1e9
     out['cudnn_convs_useful_tflops'] = flops / out['cudnn_convs_ms'] / 1e9
+    try:
+        peak_bf16 = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('bf16_tflops', 1632.0))
+    except Exception:
+        peak_bf16 = 1632.0
+    npad = ((ori + 15) // 16) * 16 + 80          # columns the MMAs compute (N padded to legal UMMA shapes)
+    tiles = sum(-(-h // 16) * -(-w // 16) for h, w in shapes) * n   # 16 x 16 pixel patches incl. the ragged edges
+    executed = 2.0 * tiles * 256 * 2304 * npad
+    out['roofline'] = {'bound': 'tensor', 'unit': 'TFLOP/s', 'achieved': flops / out['fused_kernel_no_logits_ms'] / 1e9,
+                       'executed_incl_padding': executed / out['fused_kernel_no_logits_ms'] / 1e9,
+                       'peak': peak_bf16 / 2, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 issues at half the '
+                       'bf16 rate: K = 8 instead of 16 per MMA)',
+                       'frac': flops / out['fused_kernel_no_logits_ms'] / 1e9 / (peak_bf16 / 2),
+                       'note': 'N = 48 / 80 per MMA: each MMA fetches a 4 KB A tile from shared memory for 24 / 40 cycles of '
+                               'math, so shared-memory operand bandwidth, not the tensor pipe, bounds it (DESIGN 4b)'}
     t_cls = [torch.empty(n, ori, h, w, device=dev) for h, w in shapes]
     t_box = [torch.empty(n, 68, h, w, device=dev) for h, w in shapes]
     path.teacher_head_fused(plan, head, cls_f, reg_f, t_cls, t_box)
