@@ -162,34 +162,77 @@ teacher_pass_kernel(Geo g, Workspace ws, TeacherArgs A, const __grid_constant__ 
     asm volatile("cp.async.wait_all;" ::: "memory");
     // ---- scan: one anchor per lane.  Lanes past the level's end hold zeros: computing on them
     // unconditionally keeps the loops free of predicates (their results are discarded).
-    float best = col[0];
-    int arg = 0;
-    for (int c = 1; c < ori; ++c) {   // first maximum: argmax semantics of torch.max (gfl_head_increment_erd.py:194-195)
-      const float v = col[c * kAT];
-      if (v > best) { best = v; arg = c; }
+    // The lane's instruction stream is what bounds this pass (4 warps per scheduler, every value a dependent chain),
+    // so the chains are laid out for instruction-level parallelism -- without changing a single result bit:
+    // the class argmax as four interleaved first-maximum chains (classes c = r mod 4) merged first-index-stable, the
+    // four softmax integrals advanced together one bin at a time (each side's own operation order is unchanged), the
+    // four IEEE divisions at the end (their slow-path branch used to fence one side's code off from the next).
+    float cb[4];
+    int ca[4];
+    cb[0] = col[0];              // chain 0 starts from class 0 (a NaN there propagates as in torch.max's scan order)
+    ca[0] = 0;
+#pragma unroll
+    for (int r = 1; r < 4; ++r) { cb[r] = -INFINITY; ca[r] = r; }
+    {
+      int c = 0;
+      for (; c + 8 <= ori; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = col[(c + e) * kAT];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (v[e] > cb[e & 3]) { cb[e & 3] = v[e]; ca[e & 3] = c + e; }
+      }
+      for (; c < ori; c += 4) {   // ori % 8 classes left: chains stay (c mod 4)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c + e < ori) {
+            const float v = col[(c + e) * kAT];
+            if (v > cb[e]) { cb[e] = v; ca[e] = c + e; }
+          }
+      }
     }
+    // first maximum overall = the smallest index among the chains' maxima (argmax semantics of torch.max,
+    // gfl_head_increment_erd.py:194-195)
+    auto take = [](float& b0, int& a0, float b1, int a1) {
+      if (b1 > b0 || (b1 == b0 && a1 < a0)) { b0 = b1; a0 = a1; }
+    };
+    take(cb[0], ca[0], cb[1], ca[1]);
+    take(cb[2], ca[2], cb[3], ca[3]);
+    take(cb[0], ca[0], cb[2], ca[2]);
+    const float best = cb[0];
+    const int arg = ca[0];
     float u = -INFINITY;
     float dist[4];
+    {
+      float z[4][kBins];
 #pragma unroll
-    for (int sd = 0; sd < 4; ++sd) {
-      const float* scol = col + (size_t)(ori + sd * kBins) * kAT;
-      float z[kBins];
+      for (int sd = 0; sd < 4; ++sd)
 #pragma unroll
-      for (int j = 0; j < kBins; ++j) z[j] = scol[j * kAT];
-      float mx = z[0];
-#pragma unroll
-      for (int j = 1; j < kBins; ++j) mx = fmaxf(mx, z[j]);
+        for (int j = 0; j < kBins; ++j) z[sd][j] = col[(size_t)(ori + sd * kBins + j) * kAT];
       const float kL2e = 1.4426950408889634f;
-      const float bias = -mx * kL2e;
-      float sum = 0.f, num = 0.f;
+      float bias[4], sum[4], num[4];
+#pragma unroll
+      for (int sd = 0; sd < 4; ++sd) {
+        float mx = z[sd][0];
+#pragma unroll
+        for (int j = 1; j < kBins; ++j) mx = fmaxf(mx, z[sd][j]);
+        bias[sd] = -mx * kL2e;
+        sum[sd] = 0.f;
+        num[sd] = 0.f;
+        u = fmaxf(u, mx);
+      }
 #pragma unroll
       for (int j = 0; j < kBins; ++j) {
-        const float e = ex2_approx(fmaf(z[j], kL2e, bias));   // exp(z - mx), 2 ulp
-        sum += e;
-        num = fmaf((float)j, e, num);
+#pragma unroll
+        for (int sd = 0; sd < 4; ++sd) {
+          const float e = ex2_approx(fmaf(z[sd][j], kL2e, bias[sd]));   // exp(z - mx), 2 ulp
+          sum[sd] += e;
+          num[sd] = fmaf((float)j, e, num[sd]);
+        }
       }
-      dist[sd] = __fdiv_rn(num, sum);                           // Integral (:40-54)
-      u = fmaxf(u, mx);
+#pragma unroll
+      for (int sd = 0; sd < 4; ++sd) dist[sd] = __fdiv_rn(num[sd], sum[sd]);   // Integral (:40-54)
     }
     const bool in = lane < b.cnt;
     const float m = sigmoid_ref(best);

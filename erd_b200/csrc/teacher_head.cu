@@ -420,23 +420,31 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
         }
         float u = -INFINITY;
         float dist[4];
-#pragma unroll
-        for (int sd = 0; sd < 4; ++sd) {
-          const float* zs = z + sd * kBins;
-          float mx = zs[0];
-#pragma unroll
-          for (int k = 1; k < kBins; ++k) mx = fmaxf(mx, zs[k]);
+        {   // the four integrals advanced together, divisions last: teacher.cu's scan, operation for operation
           const float kL2e = 1.4426950408889634f;
-          const float bias = -mx * kL2e;
-          float sum = 0.f, num = 0.f;
+          float bias[4], sum[4], num[4];
+#pragma unroll
+          for (int sd = 0; sd < 4; ++sd) {
+            const float* zs = z + sd * kBins;
+            float mx = zs[0];
+#pragma unroll
+            for (int k = 1; k < kBins; ++k) mx = fmaxf(mx, zs[k]);
+            bias[sd] = -mx * kL2e;
+            sum[sd] = 0.f;
+            num[sd] = 0.f;
+            u = fmaxf(u, mx);
+          }
 #pragma unroll
           for (int k = 0; k < kBins; ++k) {
-            const float e = ex2_approx(fmaf(zs[k], kL2e, bias));
-            sum += e;
-            num = fmaf((float)k, e, num);
+#pragma unroll
+            for (int sd = 0; sd < 4; ++sd) {
+              const float e = ex2_approx(fmaf(z[sd * kBins + k], kL2e, bias[sd]));
+              sum[sd] += e;
+              num[sd] = fmaf((float)k, e, num[sd]);
+            }
           }
-          dist[sd] = __fdiv_rn(num, sum);
-          u = fmaxf(u, mx);
+#pragma unroll
+          for (int sd = 0; sd < 4; ++sd) dist[sd] = __fdiv_rn(num[sd], sum[sd]);
         }
         const float m = sigmoid_ref(best);
         const size_t ga = (size_t)b.n * g.A + g.start[b.l] + hw;
