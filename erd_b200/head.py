@@ -157,11 +157,17 @@ def fused_teacher_head(path: ErdPath, teacher_head, feats, num_classes: int, reg
         th = TeacherHead(teacher_head.gfl_cls.weight, teacher_head.gfl_cls.bias, teacher_head.gfl_reg.weight,
                          teacher_head.gfl_reg.bias, scales)
         teacher_head._erd_packed = th       # the teacher is frozen: packed once
+    def tower(convs, x):   # nn.Sequential (standalone mirror) or mmdet's ModuleList of ConvModule (gfl_head.py:222-227)
+        if isinstance(convs, nn.ModuleList):
+            for conv in convs:
+                x = conv(x)
+            return x
+        return convs(x)
     cls_f, reg_f = [], []
     for f in feats:
         f = f.contiguous(memory_format=torch.channels_last)
-        cls_f.append(teacher_head.cls_convs(f).float().contiguous(memory_format=torch.channels_last))
-        reg_f.append(teacher_head.reg_convs(f).float().contiguous(memory_format=torch.channels_last))
+        cls_f.append(tower(teacher_head.cls_convs, f).float().contiguous(memory_format=torch.channels_last))
+        reg_f.append(tower(teacher_head.reg_convs, f).float().contiguous(memory_format=torch.channels_last))
     n, ori = int(cls_f[0].shape[0]), th.ori
     plan = path.plan(cls_f, num_classes, ori, reg_max)
     t_cls = [torch.empty(n, ori, h, w, dtype=torch.float32, device=cls_f[0].device) for h, w in plan.shapes]

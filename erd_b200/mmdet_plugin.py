@@ -18,7 +18,7 @@ functions the standalone mirrors (head.py, detector.py) run under the GPU parity
 """
 from __future__ import annotations
 
-from .head import ErdPath, _LOSS_DEFAULTS, fused_loss_by_feat, fused_sel_pos   # noqa: F401
+from .head import ErdPath, _LOSS_DEFAULTS, fused_loss_by_feat, fused_sel_pos, fused_teacher_head   # noqa: F401
 from .detector import _LazyGather
 
 try:
@@ -77,6 +77,27 @@ if HAVE_MMDET:
     @MODELS.register_module()
     class GFLIncrementERDB200(_RefDetector):
         """The reference detector with ``sel_pos`` running on the sm_100a kernels."""
+
+        def __init__(self, *args, fuse_teacher_head: bool = False, **kwargs):
+            super().__init__(*args, **kwargs)
+            # SURVEY 8(f) rank 1: the teacher's last head convolutions inside the teacher pass (tcgen05, TF32)
+            self.fuse_teacher_head = bool(fuse_teacher_head)
+
+        def loss(self, batch_inputs, batch_data_samples):
+            """gfl_increment_erd.py:202-220; with ``fuse_teacher_head`` the teacher head stops after its towers and
+            ``erd_teacher_head_fused`` produces the logits, the teacher cache and the selection in one kernel."""
+            if not self.fuse_teacher_head:
+                return super().loss(batch_inputs, batch_data_samples)
+            import torch
+            head = self.bbox_head
+            with torch.no_grad():
+                ori_outs, (cls_sel, box_sel), _ = fused_teacher_head(
+                    head.path, self.ori_model.bbox_head, self.ori_model.extract_feat(batch_inputs), head.num_classes,
+                    head.reg_max)
+            new_outs = self.bbox_head(self.extract_feat(batch_inputs))
+            return self.bbox_head.loss(ori_outs, new_outs, batch_data_samples, cls_sel, _LazyGather(cls_sel, ori_outs[0]),
+                                       box_sel, _LazyGather(box_sel, ori_outs[1]), self.ori_num_classes,
+                                       self.dist_loss_weight, self)
 
         def sel_pos(self, cls_scores, bbox_preds):
             head = self.bbox_head
