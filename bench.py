@@ -259,8 +259,9 @@ def time_teacher_head(path, plan, b, g_cls, g_box, losses, n, A, ori, steps):
                        'peak': peak_bf16 / 2, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 issues at half the '
                        'bf16 rate: K = 8 instead of 16 per MMA)',
                        'frac': flops / out['fused_kernel_no_logits_ms'] / 1e9 / (peak_bf16 / 2),
-                       'note': 'N = 48 / 80 per MMA: each MMA fetches a 4 KB A tile from shared memory for 24 / 40 cycles of '
-                               'math, so shared-memory operand bandwidth, not the tensor pipe, bounds it (DESIGN 4b)'}
+                       'note': f'N = {npad - 80} / 80 per MMA: each MMA fetches a 4 KB A tile from shared memory for '
+                               f'{(npad - 80) // 2} / 40 cycles of math, so shared-memory operand bandwidth, not the tensor pipe, '
+                               'bounds it (DESIGN 4b)'}
     t_cls = [torch.empty(n, ori, h, w, device=dev) for h, w in shapes]
     t_box = [torch.empty(n, 68, h, w, device=dev) for h, w in shapes]
     path.teacher_head_fused(plan, head, cls_f, reg_f, t_cls, t_box)
