@@ -276,7 +276,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
     const uint32_t idesc_cls = h_idesc(ncp), idesc_reg = h_idesc(kRegPad);
     const uint32_t lbo_cls = (uint32_t)ncp * 16u, lbo_reg = (uint32_t)kRegPad * 16u;
     // descriptor words: lo = start >> 4 | LBO >> 4 << 16, hi = SBO >> 4 | version 1 << 14
-    const uint32_t hi_a = (uint32_t)(kHalo * 16 >> 4) | (1u << 14), hi_b = (128u >> 4) | (1u << 14);
+    uint32_t hi_a = (uint32_t)(kHalo * 16 >> 4) | (1u << 14);
+    const uint32_t hi_b = (128u >> 4) | (1u << 14);
+#ifdef ERD_HEAD_EXP
+    if (A.exp & 128) hi_a = (256u >> 4) | (1u << 14);   // 8-pixel groups 256 B apart: every core matrix 128-byte aligned (with no tap shift)
+#endif
     const uint32_t lo_a_lbo = (uint32_t)(kAPlane >> 4) << 16, lo_c_lbo = (lbo_cls >> 4) << 16, lo_r_lbo = (lbo_reg >> 4) << 16;
     uint32_t ia = 0, ib = 0, itile = 0;
     for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, ++itile) {
@@ -295,7 +299,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int dy = tap / 3, dx = tap - dy * 3;
           // the tap: the same buffer, shifted start (all in 16-byte units from here on)
+#ifdef ERD_HEAD_EXP
+          const uint32_t a0 = ((a_stage + ((A.exp & 128) ? 0 : (dy * kHalo + dx) * 16)) >> 4) | lo_a_lbo;
+#else
           const uint32_t a0 = ((a_stage + (dy * kHalo + dx) * 16) >> 4) | lo_a_lbo;
+#endif
           const uint32_t bc = h_smem(sB + (size_t)sb * A.b_stage_bytes);
           const uint32_t bc0 = (bc >> 4) | lo_c_lbo, br0 = ((bc + ncp * 128) >> 4) | lo_r_lbo;
 #ifdef ERD_HEAD_EXP
