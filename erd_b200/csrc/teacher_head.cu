@@ -285,6 +285,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
     uint32_t ia = 0, ib = 0, itile = 0;
     for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, ++itile) {
       const int acc = itile % A.n_acc;
+      const HTile b = h_tile(A, t);
+      const bool right_half = b.x0 + 8 < g.w[b.l];   // a patch on the map's right edge may hold no pixel in its right half
       h_wait(t_empty(acc), ((itile / A.n_acc) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d0 = tmem + acc * A.acc_stride;
@@ -350,6 +352,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
             for (int s = 0; s < kKC / 8; ++s) {     // K = 8 per MMA: two 16-byte planes
 #pragma unroll
               for (int h = 0; h < 2; ++h) {         // left / right 8-pixel half of the patch: M = 16 rows x 8 pixels
+                if (h == 1 && !right_half) continue;
                 const uint32_t accum = (kc | tap | s) ? 1u : 0u;
                 const uint32_t dh = d0 + h * (ncp + kRegPad);
                 const uint32_t a_lo = a0 + (2 * s * kAPlane + h * 128) / 16;
@@ -389,6 +392,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
       double sums[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
+        if (h == 1 && b.x0 + 8 >= W) break;   // no pixel there: no MMA was issued for this half (warp-uniform)
         const int mrow = 32 * q + lane;
         const int y = b.y0 + (mrow >> 3), x = b.x0 + 8 * h + (mrow & 7);
         const bool in = y < H && x < W;
