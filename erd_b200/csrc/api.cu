@@ -99,6 +99,10 @@ static void carve(const Geo& g, void* base, Workspace* ws) {
   ws->nms_score = (float*)take(NS * 4);
   ws->nms_cls = (int*)take(NS * 4);
   ws->nms_box = (float4*)take(NS * 16);
+  ws->nms_orig = (int*)take(NS * 4);
+  ws->nms_tbox = (float4*)take(NS * 16);
+  ws->nms_tscore = (float*)take(NS * 4);
+  ws->nms_tcls = (int*)take(NS * 4);
   ws->nms_mask = (unsigned long long*)take(NS * nms_words(g.sel_cap) * 8);
   ws->loss_acc = (double*)take((size_t)(3 * kLevels + 2 * g.n_img) * 8);
   ws->bytes = off;

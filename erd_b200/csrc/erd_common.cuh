@@ -75,6 +75,13 @@ struct Workspace {
   float* nms_score;               // [N][sel_cap] teacher confidence of each selected row, list order
   int* nms_cls;                   // [N][sel_cap] class ids in list order
   float4* nms_box;                // [N][sel_cap] class-offset teacher boxes, list order
+  // Loss path only (NULL on the inference path): nms_box / nms_score / nms_cls are held GROUPED BY CLASS, so that the
+  // pair kernel can skip every 64 x 64 tile whose row and column blocks share no class; nms_orig[p] is the list
+  // position of the box at grouped position p, nms_tbox / nms_tscore / nms_tcls the list-order values before grouping.
+  int* nms_orig;
+  float4* nms_tbox;
+  float* nms_tscore;
+  int* nms_tcls;
   unsigned long long* nms_mask;   // [N][sel_cap][W] predecessor bit matrix, W = ceil(sel_cap/64)
   double* loss_acc;               // [3L + 2N]
   size_t bytes;

@@ -19,21 +19,29 @@
 namespace erd {
 
 constexpr int kPrepThreads = 1024;
+constexpr int kClsBuckets = 1024;   // classes >= 1023 share the last bucket (grouping is then coarser, never wrong)
 
-// One CTA per image: teacher boxes of the selected rows, the coordinate maximum, class offsets;
-// zeroes the image's slice of the predecessor matrix and map.
+// One CTA per image: teacher boxes of the selected rows, the coordinate maximum, class offsets; the rows are then
+// GROUPED BY CLASS (counting sort; the order inside a class is arbitrary -- "visited first" is decided per pair from
+// scores and list positions): boxes of different classes never overlap after the class offset, so the pair kernel
+// only has to look at the tiles whose row and column blocks share a class.
+// Zeroes the image's slice of the predecessor matrix and map.
 __global__ void __launch_bounds__(kPrepThreads) nms_prep_kernel(Geo g, Workspace ws,
                                                                 const int32_t* __restrict__ box_inds,
                                                                 const int32_t* __restrict__ box_count,
                                                                 const int32_t* __restrict__ pad_hw) {
   __shared__ float s_max[kPrepThreads / 32];
+  __shared__ int s_cur[kClsBuckets];
+  __shared__ int s_wsum[kPrepThreads / 32];
   const int n = blockIdx.x;
   const int K = box_count[n];
   const int pad_h = pad_hw[n * 2], pad_w = pad_hw[n * 2 + 1];
   const int32_t* list = box_inds + (size_t)n * g.sel_cap;
-  float4* boxes = ws.nms_box + (size_t)n * g.sel_cap;
-  float* score = ws.nms_score + (size_t)n * g.sel_cap;
-  int* cls = ws.nms_cls + (size_t)n * g.sel_cap;
+  float4* tbox = ws.nms_tbox + (size_t)n * g.sel_cap;
+  float* tscore = ws.nms_tscore + (size_t)n * g.sel_cap;
+  int* tcls = ws.nms_tcls + (size_t)n * g.sel_cap;
+  for (int i = threadIdx.x; i < kClsBuckets; i += kPrepThreads) s_cur[i] = 0;
+  __syncthreads();
   float mx = -INFINITY;
   for (int r = threadIdx.x; r < K; r += kPrepThreads) {
     const int a = list[r];
@@ -48,9 +56,11 @@ __global__ void __launch_bounds__(kPrepThreads) nms_prep_kernel(Geo g, Workspace
     const float cx = valid ? (float)(x * s) : 0.f, cy = valid ? (float)(y * s) : 0.f;
     const float4 d = ws.t_dist[ga];   // bin units used as pixels (no * stride), :189-192
     const float4 b = make_float4(__fsub_rn(cx, d.x), __fsub_rn(cy, d.y), __fadd_rn(cx, d.z), __fadd_rn(cy, d.w));
-    boxes[r] = b;
-    cls[r] = ws.t_arg[ga];
-    score[r] = ws.t_m[ga];
+    const int c = ws.t_arg[ga];
+    tbox[r] = b;
+    tcls[r] = c;
+    tscore[r] = ws.t_m[ga];
+    atomicAdd(&s_cur[min(c, kClsBuckets - 1)], 1);
     mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
   }
   // zero the predecessor words / map of the K rows in use
@@ -63,13 +73,40 @@ __global__ void __launch_bounds__(kPrepThreads) nms_prep_kernel(Geo g, Workspace
   mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
   __syncthreads();
+  // exclusive prefix of the class histogram (thread t owns bucket t): the first grouped position of every class
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = s_cur[threadIdx.x];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += s_wsum[w];
+    s_cur[threadIdx.x] = base + inc - v;
+  }
+  __syncthreads();
   float maxc = s_max[0];
   for (int w = 1; w < kPrepThreads / 32; ++w) maxc = fmaxf(maxc, s_max[w]);
   const float unit = __fadd_rn(maxc, 1.0f);   // boxes.max() + 1
+  float4* boxes = ws.nms_box + (size_t)n * g.sel_cap;
+  float* score = ws.nms_score + (size_t)n * g.sel_cap;
+  int* cls = ws.nms_cls + (size_t)n * g.sel_cap;
+  int* orig = ws.nms_orig + (size_t)n * g.sel_cap;
   for (int r = threadIdx.x; r < K; r += kPrepThreads) {   // each thread re-reads what it wrote
-    const float4 b = boxes[r];
-    const float off = __fmul_rn((float)cls[r], unit);
-    boxes[r] = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
+    const float4 b = tbox[r];
+    const int c = tcls[r];
+    const float off = __fmul_rn((float)c, unit);
+    const int bucket = min(c, kClsBuckets - 1);
+    const int p = atomicAdd(&s_cur[bucket], 1);
+    boxes[p] = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
+    score[p] = tscore[r];
+    cls[p] = bucket;
+    orig[p] = r;
   }
 }
 
@@ -78,6 +115,7 @@ __global__ void __launch_bounds__(kPrepThreads) nms_prep_kernel(Geo g, Workspace
 // bits are set with atomics and the per-box map nz[j] records which words are non-zero.
 // 256 threads per 64x64 tile (rb <= cb): four threads share a column, 16 rows each.
 constexpr int kMaskThreads = 256;
+constexpr int kMaxMaskWords = 264;   // 64-box blocks of an image (sel_cap <= 16 384 + slack); beyond it: no tile skipping
 
 __device__ __forceinline__ bool nms_overlaps(const float4& a, float area_a, const float4& b, float area_b,
                                              float iou_thr) {
@@ -111,20 +149,43 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace
   __shared__ float2 s_rx[2][64];   // (x1, x2) of the row boxes: most pairs are rejected on x alone
   __shared__ float s_rarea[2][64];
   __shared__ float s_rscore[2][64];
+  __shared__ int s_rorig[2][64];
+  __shared__ int s_cfirst[kMaxMaskWords], s_clast[kMaxMaskWords];   // first / last class of every 64-box block
   const int col = threadIdx.x >> 2, part = threadIdx.x & 3;
   const int ntile = W * (W + 1) / 2;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; the boxes of the next tile
+  // Grouped by class (loss path): list positions for the "visited first" rule, and the class range of every block --
+  // a tile whose row block ends below the class its column block starts with holds no pair of one class.
+  const int* orig = ws.nms_orig ? ws.nms_orig + (size_t)n * g.sel_cap : nullptr;
+  const bool grouped = orig != nullptr && W <= kMaxMaskWords;
+  if (grouped) {
+    const int* cls = ws.nms_cls + (size_t)n * g.sel_cap;
+    for (int b = threadIdx.x; b < W; b += kMaskThreads) {
+      s_cfirst[b] = cls[b * 64];
+      s_clast[b] = cls[min(K - 1, b * 64 + 63)];
+    }
+    __syncthreads();
+  }
+  // tiles of this CTA: the needed ones among blockIdx.x, blockIdx.x + gridDim.x, ...; the boxes of the next tile
   // are fetched while the current one is evaluated
-  int t = blockIdx.x;
+  int rb = 0, cb = 0;
+  auto next_needed = [&](int t) {   // first needed tile at or after t in this CTA's sequence (ntile: none)
+    for (; t < ntile; t += gridDim.x) {
+      nms_tile_of(t, W, rb, cb);
+      if (!grouped || s_clast[rb] >= s_cfirst[cb]) break;
+    }
+    return t;
+  };
+  int t = next_needed(blockIdx.x);
   if (t >= ntile) return;
-  int rb, cb;
-  nms_tile_of(t, W, rb, cb);
   const bool rthread = threadIdx.x < 64;
+  auto oidx = [&](int p) { return orig ? orig[p] : p; };
   float4 next_row = (rthread && rb * 64 + threadIdx.x < K) ? boxes[rb * 64 + threadIdx.x] : zero4;
   float next_rs = (rthread && rb * 64 + threadIdx.x < K) ? score[rb * 64 + threadIdx.x] : 0.f;
+  int next_ro = (rthread && rb * 64 + threadIdx.x < K) ? oidx(rb * 64 + threadIdx.x) : 0;
   float4 next_col = cb * 64 + col < K ? boxes[cb * 64 + col] : zero4;
   float next_cs = cb * 64 + col < K ? score[cb * 64 + col] : 0.f;
+  int next_co = cb * 64 + col < K ? oidx(cb * 64 + col) : 0;
   int buf = 0;
   while (t < ntile) {
     if (rthread) {
@@ -132,17 +193,20 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace
       s_rx[buf][threadIdx.x] = make_float2(next_row.x, next_row.z);
       s_rarea[buf][threadIdx.x] = __fmul_rn(__fsub_rn(next_row.z, next_row.x), __fsub_rn(next_row.w, next_row.y));
       s_rscore[buf][threadIdx.x] = next_rs;
+      s_rorig[buf][threadIdx.x] = next_ro;
     }
     const float4 a = next_col;
     const float sa = next_cs;
+    const int oa = next_co;
     const int crb = rb, ccb = cb;
-    const int tn = t + gridDim.x;
+    const int tn = next_needed(t + gridDim.x);
     if (tn < ntile) {
-      nms_tile_of(tn, W, rb, cb);
       next_row = (rthread && rb * 64 + threadIdx.x < K) ? boxes[rb * 64 + threadIdx.x] : zero4;
       next_rs = (rthread && rb * 64 + threadIdx.x < K) ? score[rb * 64 + threadIdx.x] : 0.f;
+      next_ro = (rthread && rb * 64 + threadIdx.x < K) ? oidx(rb * 64 + threadIdx.x) : 0;
       next_col = cb * 64 + col < K ? boxes[cb * 64 + col] : zero4;
       next_cs = cb * 64 + col < K ? score[cb * 64 + col] : 0.f;
+      next_co = cb * 64 + col < K ? oidx(cb * 64 + col) : 0;
     }
     __syncthreads();
     const int j = ccb * 64 + col;
@@ -159,7 +223,7 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(Geo g, Workspace
         if (!nms_overlaps(b, s_rarea[buf][r], a, area_a, iou_thr)) continue;
         const int i = crb * 64 + r;
         const float si = s_rscore[buf][r];
-        if (si >= sa) {   // i < j in the list: i is visited first on equal scores too
+        if (si > sa || (si == sa && s_rorig[buf][r] < oa)) {   // i is visited first: higher score, on equal scores the earlier list position
           atomicOr(pred + (size_t)j * Wcap + crb, 1ull << r);
           atomicOr(nz + (size_t)j * NZ + (crb >> 6), 1ull << (crb & 63));
         } else {
@@ -309,12 +373,13 @@ __global__ void __launch_bounds__(kResThreads) nms_resolve_kernel(Geo g, Workspa
   __syncthreads();
   int* out = ws.keep_raw + (size_t)n * g.sel_cap;   // score order comes later (nms_order_kernel)
   const int32_t* list = box_inds + (size_t)n * g.sel_cap;
+  const int* orig = ws.nms_orig ? ws.nms_orig + (size_t)n * g.sel_cap : nullptr;
   for (int j = threadIdx.x; j < K; j += kResThreads) {
     const int wj = j >> 6;
     const unsigned long long kw = kept[wj];
     if (!(kw & (1ull << (j & 63)))) continue;
-    out[(int)dec[wj] + __popcll(kw & ((1ull << (j & 63)) - 1ull))] = j;
-    sel_flags[(size_t)n * g.A + list[j]] |= 4;
+    out[(int)dec[wj] + __popcll(kw & ((1ull << (j & 63)) - 1ull))] = j;   // position in nms_box / nms_score order
+    sel_flags[(size_t)n * g.A + list[orig ? orig[j] : j]] |= 4;
   }
 }
 
@@ -329,8 +394,9 @@ __global__ void __launch_bounds__(kSortThreads) nms_order_kernel(Geo g, Workspac
   const int M = keep_count[n];
   int32_t* out = keep + (size_t)n * g.sel_cap;
   const int* raw = ws.keep_raw + (size_t)n * g.sel_cap;
+  const int* orig = ws.nms_orig ? ws.nms_orig + (size_t)n * g.sel_cap : nullptr;   // grouped position -> list position
   if (M < 2) {
-    if (M == 1 && threadIdx.x == 0) out[0] = raw[0];
+    if (M == 1 && threadIdx.x == 0) out[0] = orig ? orig[raw[0]] : raw[0];
     return;
   }
   int P = 1;
@@ -340,7 +406,7 @@ __global__ void __launch_bounds__(kSortThreads) nms_order_kernel(Geo g, Workspac
     unsigned long long key = ~0ull;
     if (r < M) {
       const int pos = raw[r];
-      key = ((unsigned long long)(~__float_as_uint(score[pos])) << 32) | (unsigned int)pos;
+      key = ((unsigned long long)(~__float_as_uint(score[pos])) << 32) | (unsigned int)(orig ? orig[pos] : pos);
     }
     s_key[r] = key;
   }
