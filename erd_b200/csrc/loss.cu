@@ -138,24 +138,27 @@ __global__ void __launch_bounds__(256) assign_prepass_kernel(Geo g, Workspace ws
   __shared__ double s_acc[2 * kLevels + 1];
   if (threadIdx.x < 2 * kLevels + 1) s_acc[threadIdx.x] = 0.0;
   __syncthreads();
-  // one batch of independent loads: the argmax-table entries of this thread's anchors
-  const int a0 = blockIdx.x * (256 * kAssignPer) + threadIdx.x;
+  // one batch of independent loads: the argmax-table entries of this thread's anchors.  A warp's four 32-anchor
+  // chunks are dealt round-robin over the image's CTAs (chunk c -> CTA c mod gridDim.x), not cut from one contiguous
+  // 1024-anchor range: positives cluster (with many GT boxes nearly every anchor of the coarse levels is one), and
+  // the CTA that owned those levels alone took several times as long as the rest of the grid.
+  const int warp = threadIdx.x >> 5;
+  int anchor[kAssignPer];
   unsigned long long key[kAssignPer];
 #pragma unroll
   for (int i = 0; i < kAssignPer; ++i) {
-    const int a = a0 + i * 256;
-    key[i] = a < g.A ? ws.atss_key[(size_t)n * g.A + a] : 0ull;
+    anchor[i] = ((i * 8 + warp) * (int)gridDim.x + (int)blockIdx.x) * 32 + lane;
+    key[i] = anchor[i] < g.A ? ws.atss_key[(size_t)n * g.A + anchor[i]] : 0ull;
   }
   const int pad_h = pad_hw[n * 2], pad_w = pad_hw[n * 2 + 1], first_gt = A.gt_offsets[n];
   // decode all of the warp's 128 anchors first and collect its positives in a shared-memory list: the list is then
   // worked off eight positives at a time, so a warp pays one round of dependent loads per eight positives (not one per
   // 32-anchor row that happens to hold a positive) and one returning atomic for its slots in the image's list
   __shared__ int2 s_list[256 / 32][32 * kAssignPer];
-  const int warp = threadIdx.x >> 5;
   int cnt = 0;   // warp-uniform
 #pragma unroll
   for (int i = 0; i < kAssignPer; ++i) {
-    const int a = a0 + i * 256;
+    const int a = anchor[i];
     const int gidx = a < g.A ? atss_decode_only(g, ws, pad_h, pad_w, first_gt, gt_inds, n, a, key[i]) : -1;
     const unsigned m = __ballot_sync(0xffffffffu, gidx >= 0);
     if (gidx >= 0) s_list[warp][cnt + __popc(m & ((1u << lane) - 1u))] = make_int2(a, gidx);
