@@ -35,12 +35,19 @@
 namespace erd {
 
 constexpr int kBT = 32;                                   // anchors per tile: one per lane
-constexpr int kTeams = 4;                                 // independent pipelines per CTA
+#ifndef ERD_STUDENT_TEAMS
+#define ERD_STUDENT_TEAMS 4
+#endif
+#ifndef ERD_STUDENT_SPT
+#define ERD_STUDENT_SPT 2
+#endif
+constexpr int kTeams = ERD_STUDENT_TEAMS;                 // independent pipelines per CTA
+constexpr int kSPT = ERD_STUDENT_SPT;                     // slots per team
 constexpr int kTeamWarps = 4;                             // consumer warps per team
 constexpr int kConsumerWarps = kTeams * kTeamWarps;
 constexpr int kConsumers = 32 * kConsumerWarps;
 constexpr int kBThreads = kConsumers + 32 * kTeams;       // + one IO warp per team
-constexpr int kSlots = 2 * kTeams;                        // two slots per team
+constexpr int kSlots = kSPT * kTeams;
 constexpr int kStageItems = 12;                           // special columns per tile whose records / teacher columns are staged in the slot
 constexpr int kStudentFreeSms = 24;                       // SMs left to the kernels that run beside this pass
 constexpr int kQflChunk = 5;                              // QFL elements a thread loads ahead of the arithmetic
@@ -438,8 +445,8 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_store));
     // Tile jj of the team is done: write the slot to the gradient tensors; returns when the slot may be overwritten.
     auto drain = [&](int jj) {
-      const int s = team * 2 + (jj & 1);
-      mbar_wait_parity(&s_done[s], (uint32_t)(jj >> 1) & 1u);
+      const int s = team * kSPT + (jj % kSPT);
+      mbar_wait_parity(&s_done[s], (uint32_t)(jj / kSPT) & 1u);
       const unsigned char* base = s_raw + (size_t)s * A.slot_bytes;
       const float* data = reinterpret_cast<const float*>(base);
       const TileHeader* hd = reinterpret_cast<const TileHeader*>(base + A.hdr_off);
@@ -481,8 +488,8 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
       const unsigned fl = in ? (unsigned)A.sel_flags[ga] : 0u;
       const unsigned srow = in ? (unsigned)ws.t_slot[ga] : 0u;   // the anchor's stash row + 1 (teacher pass), 0: none
       const int kcls = A.cls_count[b.n];
-      if (j >= 2) drain(j - 2);
-      const int s = team * 2 + (j & 1);
+      if (j >= kSPT) drain(j - kSPT);
+      const int s = team * kSPT + (j % kSPT);
       unsigned char* base = s_raw + (size_t)s * A.slot_bytes;
       float* data = reinterpret_cast<float*>(base);
       TileHeader* hd = reinterpret_cast<TileHeader*>(base + A.hdr_off);
@@ -591,8 +598,9 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
       mbar_arrive(full);
 #endif
     }
-    if (j >= 2) drain(j - 2);
-    if (j >= 1) drain(j - 1);
+#pragma unroll
+    for (int d = kSPT; d >= 1; --d)
+      if (j >= d) drain(j - d);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     return;
   }
@@ -624,12 +632,12 @@ student_pass_kernel(Geo g, Workspace ws, StudentArgs A, const __grid_constant__ 
   for (int j = 0;; ++j) {
     const int t = blockIdx.x + (team + kTeams * j) * gridDim.x;
     if (t >= A.total_tiles) break;
-    const int s = team * 2 + (j & 1);
+    const int s = team * kSPT + (j % kSPT);
     unsigned char* base = s_raw + (size_t)s * A.slot_bytes;
     float* data = reinterpret_cast<float*>(base);
     TileHeader* hd = reinterpret_cast<TileHeader*>(base + A.hdr_off);
     const float* tst = reinterpret_cast<const float*>(base + A.tst_off);
-    mbar_wait_parity(&s_full[s], (uint32_t)(j >> 1) & 1u);
+    mbar_wait_parity(&s_full[s], (uint32_t)(j / kSPT) & 1u);
     const int n = hd->n, l = hd->l;
     if (n != cur_img || l != cur_lvl) {   // warp-uniform
       flush();
