@@ -77,7 +77,8 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         import pytest
         pytest.skip('no gcc')
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    structs = {'ErdShape': N.ErdShape, 'ErdSizes': N.ErdSizes, 'ErdStepBuffers': N.ErdStepBuffers}
+    structs = {'ErdShape': N.ErdShape, 'ErdSizes': N.ErdSizes, 'ErdStepBuffers': N.ErdStepBuffers,
+               'ErdPredictConfig': N.ErdPredictConfig, 'ErdTeacherHead': N.ErdTeacherHead}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "erd_b200.h"', 'int main(void) {']
     for name, cls in structs.items():
         lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
