@@ -135,3 +135,28 @@ def test_checkpoint_surgery_expands_the_cls_head():
     assert torch.equal(student_head.gfl_reg.weight, teacher_head.gfl_reg.weight)
     with pytest.raises(RuntimeError):
         det.load_checkpoint_for_new_model(dict(weights=1))
+
+
+def test_fused_teacher_head_host_checks():
+    """The fused teacher head without a GPU: argument checking of the C ABI entry points happens on
+    the host before any launch, the packed-weight size is host arithmetic, and the Python wrapper has no CPU path."""
+    import ctypes as C
+    from erd_b200 import _native as N
+    from erd_b200.ops import TeacherHead
+    lib = N.load()
+    assert lib.erd_teacher_head_packed_floats(40) == 48 * 256 * 9      # 40 classes padded to a legal UMMA N
+    assert lib.erd_teacher_head_packed_floats(68) == 80 * 256 * 9
+    assert lib.erd_teacher_head_packed_floats(0) == 0
+    assert lib.erd_teacher_head_pack(None, 40, None, None) == -2         # ERD_ERR_NULL
+    shape = N.ErdShape(num_imgs=2, num_levels=5, num_classes=80, ori_classes=40, reg_max=16, total_gt=0, anchor_scale=8.0,
+                       loss_weight_cls=1.0, loss_weight_bbox=2.0, loss_weight_dfl=0.25, loss_weight_ld=0.25,
+                       kd_temperature=10.0, max_gt_per_img=0)
+    for l, (h, w) in enumerate(level_shapes(256, 320)):
+        shape.level_h[l], shape.level_w[l], shape.stride[l] = h, w, 8 << l
+    assert lib.erd_teacher_head_fused(C.byref(shape), None, N.PtrArray(), N.PtrArray(), None, None, None, None, None,
+                                      None) == -2
+    assert b'NULL' in lib.erd_last_error()
+    assert lib.erd_ers_select_cached(C.byref(shape), None, None, None, None, None, None, None, None) == -2
+    w = torch.zeros(40, 256, 3, 3)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        TeacherHead(w, torch.zeros(40), torch.zeros(68, 256, 3, 3), torch.zeros(68), [1.0] * 5)
