@@ -7,7 +7,7 @@ frozen 40-class teacher, an 80-class student wrapped in DistributedDataParallel 
 overlapping the conv backward), the loss path through `GFLIncrementERD.sel_pos` + `GFLHeadIncrementERD.loss`
 (C ABI; its 8-byte avg-factor exchange is the path's only own collective), SGD step.
 
-    python scripts/train_step_ddp.py [imgs_per_gpu] [bf16]                                  # 1 GPU
+    python scripts/train_step_ddp.py [imgs_per_gpu] [bf16] [fuse]                           # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \\
         --master-port 29511 scripts/train_step_ddp.py [imgs_per_gpu] [bf16]                 # N GPUs
 
@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'scripts'))
 from erd_b200.detector import GFLIncrementERD           # noqa: E402
-from erd_b200.head import GFLHeadIncrementERD, parse_losses   # noqa: E402
+from erd_b200.head import GFLHeadIncrementERD, fused_teacher_head, parse_losses   # noqa: E402
 from erd_b200.synth import make_gt                       # noqa: E402
 from time_train_step import R50FPN, Teacher              # noqa: E402
 
@@ -44,6 +44,7 @@ def main():
     args = [a for a in sys.argv[1:]]
     n = int(args[0]) if args and args[0].isdigit() else 16
     amp = 'bf16' in args
+    fuse = 'fuse' in args   # the teacher's last head convolutions inside the teacher pass
     rank, local, world = int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -71,11 +72,19 @@ def main():
     for it in range(warm + steps):
         opt.zero_grad(set_to_none=True)
         ev[0].record()
-        with torch.no_grad(), torch.autocast('cuda', torch.bfloat16, enabled=amp):
-            ori_outs = det.ori_model(x)
-        ori_outs = ([t.float() for t in ori_outs[0]], [t.float() for t in ori_outs[1]])
-        ev[1].record()
-        sel = det.sel_pos(*ori_outs)                                    # gfl_increment_erd.py:207-209
+        if fuse:
+            with torch.no_grad():
+                with torch.autocast('cuda', torch.bfloat16, enabled=amp):
+                    feats = det.ori_model.body(x)
+                ori_outs, (cls_sel, box_sel), _ = fused_teacher_head(student.head.path, det.ori_model.head, feats, 80, 16)
+            ev[1].record()
+            sel = (cls_sel, None, box_sel, None)
+        else:
+            with torch.no_grad(), torch.autocast('cuda', torch.bfloat16, enabled=amp):
+                ori_outs = det.ori_model(x)
+            ori_outs = ([t.float() for t in ori_outs[0]], [t.float() for t in ori_outs[1]])
+            ev[1].record()
+            sel = det.sel_pos(*ori_outs)                                    # gfl_increment_erd.py:207-209
         with torch.autocast('cuda', torch.bfloat16, enabled=amp):
             new_outs = model(x)                                         # :210-211 (through DDP)
         new_outs = ([t.float() for t in new_outs[0]], [t.float() for t in new_outs[1]])
@@ -99,7 +108,7 @@ def main():
         print(json.dumps({
             'metric': 'images_per_sec_train_step', 'value': world * n / (step_ms * 1e-3), 'n_gpus': world,
             'images_per_gpu': n, 'ms_per_step': round(step_ms, 3),
-            'conv_precision': 'bf16 autocast' if amp else 'fp32 (TF32 convs)',
+            'conv_precision': 'bf16 autocast' if amp else 'fp32 (TF32 convs)', 'teacher_head_fused': fuse,
             'ms': {'teacher_forward': round(float(t[0]), 3), 'sel_pos_plus_student_forward': round(float(t[1]), 3),
                    'erd_loss_path_fwd_bwd': round(float(t[2]), 3), 'conv_backward_plus_grad_allreduce': round(float(t[3]), 3),
                    'sgd_step': round(float(t[4]), 3)},
