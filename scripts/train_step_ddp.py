@@ -7,7 +7,7 @@ frozen 40-class teacher, an 80-class student wrapped in DistributedDataParallel 
 overlapping the conv backward), the loss path through `GFLIncrementERD.sel_pos` + `GFLHeadIncrementERD.loss`
 (C ABI; its 8-byte avg-factor exchange is the path's only own collective), SGD step.
 
-    python scripts/train_step_ddp.py [imgs_per_gpu] [bf16] [fuse]                           # 1 GPU
+    python scripts/train_step_ddp.py [imgs_per_gpu] [bf16] [fuse] [channels_last]           # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \\
         --master-port 29511 scripts/train_step_ddp.py [imgs_per_gpu] [bf16]                 # N GPUs
 
@@ -55,9 +55,13 @@ def main():
     student = Student().to(dev).train()
     model = nn.parallel.DistributedDataParallel(student, device_ids=[local], bucket_cap_mb=25) if world > 1 else student
     det = GFLIncrementERD(student.head, 40, ori_model=Teacher().to(dev).eval(), extract_feat=None)
+    cl = 'channels_last' in args   # run the frozen teacher NHWC end to end: its tower outputs are then what the fused head streams
+    if cl:
+        det.ori_model.to(memory_format=torch.channels_last)
     params = [p for p in student.parameters() if p.requires_grad]
     opt = torch.optim.SGD(params, lr=1e-4, momentum=0.9, weight_decay=1e-4)
     x = torch.randn(n, 3, 800, 1344, device=dev)
+    x_t = x.contiguous(memory_format=torch.channels_last) if cl else x   # the teacher's view of the batch
     rng = np.random.RandomState(rank)
 
     class DS:
@@ -75,14 +79,14 @@ def main():
         if fuse:
             with torch.no_grad():
                 with torch.autocast('cuda', torch.bfloat16, enabled=amp):
-                    feats = det.ori_model.body(x)
+                    feats = det.ori_model.body(x_t)
                 ori_outs, (cls_sel, box_sel), _ = fused_teacher_head(student.head.path, det.ori_model.head, feats, 80, 16)
             ev[1].record()
             sel = (cls_sel, None, box_sel, None)
         else:
             with torch.no_grad(), torch.autocast('cuda', torch.bfloat16, enabled=amp):
-                ori_outs = det.ori_model(x)
-            ori_outs = ([t.float() for t in ori_outs[0]], [t.float() for t in ori_outs[1]])
+                ori_outs = det.ori_model(x_t)
+            ori_outs = ([t.float().contiguous() for t in ori_outs[0]], [t.float().contiguous() for t in ori_outs[1]])
             ev[1].record()
             sel = det.sel_pos(*ori_outs)                                    # gfl_increment_erd.py:207-209
         with torch.autocast('cuda', torch.bfloat16, enabled=amp):
@@ -108,7 +112,7 @@ def main():
         print(json.dumps({
             'metric': 'images_per_sec_train_step', 'value': world * n / (step_ms * 1e-3), 'n_gpus': world,
             'images_per_gpu': n, 'ms_per_step': round(step_ms, 3),
-            'conv_precision': 'bf16 autocast' if amp else 'fp32 (TF32 convs)', 'teacher_head_fused': fuse,
+            'conv_precision': 'bf16 autocast' if amp else 'fp32 (TF32 convs)', 'teacher_head_fused': fuse, 'teacher_channels_last': cl,
             'ms': {'teacher_forward': round(float(t[0]), 3), 'sel_pos_plus_student_forward': round(float(t[1]), 3),
                    'erd_loss_path_fwd_bwd': round(float(t[2]), 3), 'conv_backward_plus_grad_allreduce': round(float(t[3]), 3),
                    'sgd_step': round(float(t[4]), 3)},
