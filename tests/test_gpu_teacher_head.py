@@ -188,3 +188,47 @@ def test_detector_loss_with_fused_teacher_head():
         # (the head-output gradients are the same bits; cuDNN's TF32 backward of the student convs in between is
         # not run-to-run exact)
         assert float((a - c).abs().max()) <= 1e-3 * max(float(c.abs().max()), 1e-12)
+
+
+@pytest.mark.parametrize('seed', [0, 1])
+def test_fused_teacher_head_random_geometries(seed):
+    """Ragged geometries (widths and heights that are no multiples of the 16-pixel patch or of 8, single-row levels,
+    one image): the emitted logits against cuDNN's convolution of the same features (both TF32: loose tolerance), and
+    the epilogue's cache + thresholds + selections bit-identical to the teacher pass on the emitted logits."""
+    import random
+    rng = random.Random(1000 + seed)
+    dev = 'cuda'
+    for _ in range(4):
+        n = rng.choice([1, 2, 5])
+        ori = rng.choice([40, 70, 24])
+        img_hw = (rng.randrange(64, 420), rng.randrange(64, 520))
+        batch = make_batch(n, img_hw, ori=ori, num_classes=max(80, ori + 10), seed=rng.randrange(1 << 20), num_gt=2)
+        shapes = batch.shapes
+        cls_f, reg_f = _towers(n, shapes, seed=rng.randrange(1 << 20))
+        w_cls, b_cls, w_reg, b_reg, scales = _head_params(ori, seed=rng.randrange(1 << 20))
+        head = TeacherHead(w_cls.to(dev), b_cls.to(dev), w_reg.to(dev), b_reg.to(dev), scales)
+        cls_d = [x.to(dev).contiguous(memory_format=torch.channels_last) for x in cls_f]
+        reg_d = [x.to(dev).contiguous(memory_format=torch.channels_last) for x in reg_f]
+        b = batch.to(dev)
+        fused, plain = ErdPath(), ErdPath()
+        pf = fused.plan(b.s_cls, batch.num_classes, ori, batch.reg_max)
+        pp = plain.plan(b.s_cls, batch.num_classes, ori, batch.reg_max)
+        t_cls = [torch.full((n, ori, h, w), float('nan'), device=dev) for h, w in shapes]
+        t_box = [torch.full((n, 68, h, w), float('nan'), device=dev) for h, w in shapes]
+        fused.teacher_head_fused(pf, head, cls_d, reg_d, t_cls, t_box)
+        fused.ers_select_cached(pf)
+        plain.ers_select(pp, t_cls, t_box)
+        torch.cuda.synchronize()
+        for l in range(5):
+            ref_c = F.conv2d(cls_d[l], w_cls.to(dev), b_cls.to(dev), padding=1)
+            ref_r = F.conv2d(reg_d[l], w_reg.to(dev), b_reg.to(dev), padding=1) * scales[l]
+            assert torch.isfinite(t_cls[l]).all() and torch.isfinite(t_box[l]).all(), (img_hw, l)
+            assert (t_cls[l] - ref_c).abs().max() <= 3e-2 and (t_box[l] - ref_r).abs().max() <= 3e-2, (img_hw, ori, l)
+        for name in ('t_m', 't_u', 't_arg', 't_dist'):
+            assert torch.equal(pf.workspace_field(name, torch.int32), pp.workspace_field(name, torch.int32)), (img_hw, ori, name)
+        assert torch.equal(pf.thr.view(torch.int32), pp.thr.view(torch.int32)), (img_hw, ori)
+        assert torch.equal(pf.cls_count, pp.cls_count) and torch.equal(pf.box_count, pp.box_count)
+        assert torch.equal(pf.sel_flags, pp.sel_flags)
+        for i in range(n):
+            assert torch.equal(pf.cls_inds[i, :int(pf.cls_count[i])], pp.cls_inds[i, :int(pp.cls_count[i])])
+            assert torch.equal(pf.box_inds[i, :int(pf.box_count[i])], pp.box_inds[i, :int(pp.box_count[i])])
