@@ -25,7 +25,7 @@
 // Warp roles (320 threads, one CTA per SM, persistent over the patches):
 //   warps 0-3  A producers: 16-byte loads -> 16-byte shared stores (zeros = padding) into the stage, two stages;
 //   warp  4    B loader: one elected lane, 1-D bulk copies (cp.async.bulk) of the pre-packed weight tile of
-//              (32-channel slice, tap) -- the packed image IS the shared-memory image -- three stages;
+//              (32-channel slice, tap) -- the packed image IS the shared-memory image -- up to four stages;
 //   warp  5    TMEM allocation + the single MMA-issuing thread (tcgen05.mma kind::tf32, commit -> mbarriers);
 //   warps 6-9  epilogue: tcgen05.ld of the own lane quadrant, one anchor per lane, exactly the arithmetic of
 //              teacher.cu (identical bits for identical logits).  Accumulators are double buffered in TMEM
@@ -380,7 +380,6 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
     const unsigned int pc_bits = __ldg(ws.pthr_state), pb_bits = __ldg(ws.pthr_state + 1);
     const float pthr_c = pc_bits ? from_ordered_bits(~pc_bits) : INFINITY;
     const float pthr_b = pb_bits ? from_ordered_bits(~pb_bits) : INFINITY;
-    const int rows = ori + kBoxCh;
     uint32_t itile = 0;
     for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, ++itile) {
       const HTile b = h_tile(A, t);
@@ -512,7 +511,6 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
         __stcg(ws.ers_part + ((size_t)b.n * A.tiles_per_img * 4 + (size_t)b.sub * 4 + q) * 4 + lane, v);
       }
     }
-    (void)rows;
   }
   // ---------------------------------------------------------------------- teardown
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
