@@ -138,16 +138,19 @@ __global__ void __launch_bounds__(256) assign_prepass_kernel(Geo g, Workspace ws
   __shared__ double s_acc[2 * kLevels + 1];
   if (threadIdx.x < 2 * kLevels + 1) s_acc[threadIdx.x] = 0.0;
   __syncthreads();
-  // one batch of independent loads: the argmax-table entries of this thread's anchors.  A warp's four 32-anchor
-  // chunks are dealt round-robin over the image's CTAs (chunk c -> CTA c mod gridDim.x), not cut from one contiguous
-  // 1024-anchor range: positives cluster (with many GT boxes nearly every anchor of the coarse levels is one), and
-  // the CTA that owned those levels alone took several times as long as the rest of the grid.
+  // one batch of independent loads: the argmax-table entries of this thread's anchors.  With few GT boxes a CTA takes
+  // one contiguous 1024-anchor range.  With many (more than 24 per image on average) a warp's four 32-anchor chunks
+  // are dealt round-robin over the image's CTAs instead (chunk c -> CTA c mod gridDim.x): positives then cluster --
+  // nearly every anchor of the coarse levels is one -- and the CTA that owned those levels alone took several times as
+  // long as the rest of the grid (dense config: 107 -> 41 us); the scattered chunks cost the sparse case 2-3 us.
   const int warp = threadIdx.x >> 5;
+  const bool spread = A.gt_offsets[g.n_img] > 24 * g.n_img;   // grid-uniform
   int anchor[kAssignPer];
   unsigned long long key[kAssignPer];
 #pragma unroll
   for (int i = 0; i < kAssignPer; ++i) {
-    anchor[i] = ((i * 8 + warp) * (int)gridDim.x + (int)blockIdx.x) * 32 + lane;
+    anchor[i] = spread ? ((i * 8 + warp) * (int)gridDim.x + (int)blockIdx.x) * 32 + lane
+                       : (int)blockIdx.x * (256 * kAssignPer) + (int)threadIdx.x + i * 256;
     key[i] = anchor[i] < g.A ? ws.atss_key[(size_t)n * g.A + anchor[i]] : 0ull;
   }
   const int pad_h = pad_hw[n * 2], pad_w = pad_hw[n * 2 + 1], first_gt = A.gt_offsets[n];
