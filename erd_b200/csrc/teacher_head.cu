@@ -28,8 +28,9 @@
 //              (32-channel slice, tap) -- the packed image IS the shared-memory image -- up to four stages;
 //   warp  5    TMEM allocation + the single MMA-issuing thread (tcgen05.mma kind::tf32, commit -> mbarriers);
 //   warps 6-9  epilogue: tcgen05.ld of the own lane quadrant, one anchor per lane, exactly the arithmetic of
-//              teacher.cu (identical bits for identical logits).  Accumulators are double buffered in TMEM
-//              when they fit (ori <= 48), so the epilogue of patch i runs under the MMAs of patch i + 1.
+//              teacher.cu (identical bits for identical logits).  Accumulators live in a ring of per-half
+//              buffers in TMEM (four for ori <= 48, three up to 80), handed back half by half, so the epilogue of
+//              patch i runs under the MMAs of patch i + 1.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -72,7 +73,7 @@ struct HeadArgs {
   int tiles_per_img, total_tiles;
   int stash_pitch;
   int emit;
-  int n_acc, acc_stride;        // accumulator buffers in TMEM and their column stride
+  int n_hbuf, h_stride;         // accumulator buffers in TMEM, one per patch HALF (a ring of 2..4), and their column stride
   int b_stage_bytes, b_stages;
   int exp;                      // developer experiments (-DERD_HEAD_EXP, env ERD_HEAD_EXP): results are garbage when set
 };
@@ -148,7 +149,7 @@ __host__ __device__ constexpr uint32_t h_idesc(int n) {
 
 __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Workspace ws, HeadArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long s_bar[2 * kAStages + 2 * kBStages + 4];
+  __shared__ __align__(8) unsigned long long s_bar[2 * kAStages + 2 * kBStages + 6];
   __shared__ uint32_t s_tmem;
   unsigned char* sA = smem;
   unsigned char* sB = smem + kAStages * kAStageBytes;
@@ -169,7 +170,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
     auto init = [](uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); };
     for (int s = 0; s < kAStages; ++s) { init(full_a(s), 128); init(empty_a(s), 1); }
     for (int s = 0; s < kBStages; ++s) { init(full_b(s), 1); init(empty_b(s), 1); }
-    for (int s = 0; s < 2; ++s) { init(t_full(s), 1); init(t_empty(s), 4); }
+    for (int s = 0; s < 2; ++s) init(t_full(s), 1);
+    for (int s = 0; s < 4; ++s) init(t_empty(s), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < ncp + kRegPad; i += blockDim.x)
@@ -284,12 +286,17 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
     const uint32_t lo_a_lbo = (uint32_t)(kAPlane >> 4) << 16, lo_c_lbo = (lbo_cls >> 4) << 16, lo_r_lbo = (lbo_reg >> 4) << 16;
     uint32_t ia = 0, ib = 0, itile = 0;
     for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, ++itile) {
-      const int acc = itile % A.n_acc;
+      // the patch's two halves accumulate in two consecutive buffers of the half-buffer ring; the epilogue hands each
+      // back as soon as it has read it, so with three buffers (49..80 old classes) the next patch still starts before
+      // the epilogue of this one is through, and with four (up to 48) a whole patch ahead
+      const uint32_t hb0 = (2 * itile) % A.n_hbuf, hb1 = (2 * itile + 1) % A.n_hbuf;
       const HTile b = h_tile(A, t);
       const bool right_half = b.x0 + 8 < g.w[b.l];   // a patch on the map's right edge may hold no pixel in its right half
-      h_wait(t_empty(acc), ((itile / A.n_acc) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
+      h_wait(t_empty(hb0), (((2 * itile) / A.n_hbuf) & 1u) ^ 1u);       // the epilogue has drained these buffers
+      h_wait(t_empty(hb1), (((2 * itile + 1) / A.n_hbuf) & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d0 = tmem + acc * A.acc_stride;
+      const uint32_t dbuf[2] = {tmem + hb0 * A.h_stride, tmem + hb1 * A.h_stride};
+      const int fb = itile & 1;
       for (int kc = 0; kc < kNKC; ++kc, ++ia) {
         const int sa = ia % kAStages;
         h_wait(full_a(sa), (ia / kAStages) & 1u);
@@ -309,43 +316,14 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
           const uint32_t bc = h_smem(sB + (size_t)sb * A.b_stage_bytes);
           const uint32_t bc0 = (bc >> 4) | lo_c_lbo, br0 = ((bc + ncp * 128) >> 4) | lo_r_lbo;
 #ifdef ERD_HEAD_EXP
-          if ((A.exp & 16) && h_elect()) {   // chain-major order: each accumulator's four K steps back to back
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-              for (int tw = 0; tw < 2; ++tw) {
-#pragma unroll
-                for (int s = 0; s < kKC / 8; ++s) {
-                  const uint32_t accum = (kc | tap | s) ? 1u : 0u;
-                  const uint32_t dh = d0 + h * (ncp + kRegPad);
-                  const uint32_t a_lo = a0 + (2 * s * kAPlane + h * 128) / 16;
-                  if (tw == 0) h_mma(dh, h_desc2(a_lo, hi_a), h_desc2(bc0 + 2 * s * (lbo_cls >> 4), hi_b), idesc_cls, accum);
-                  else h_mma(dh + ncp, h_desc2(a_lo + kATower / 16, hi_a), h_desc2(br0 + 2 * s * (lbo_reg >> 4), hi_b), idesc_reg, accum);
-                }
-              }
-            }
-          }
-          if ((A.exp & 32) && h_elect()) {   // K split: odd K steps accumulate into a second set of columns (n_acc forced to 1)
-#pragma unroll
-            for (int s = 0; s < kKC / 8; ++s) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint32_t accum = (kc | tap | (s >> 1)) ? 1u : 0u;
-                const uint32_t dh = d0 + h * (ncp + kRegPad) + (s & 1) * 256;
-                const uint32_t a_lo = a0 + (2 * s * kAPlane + h * 128) / 16;
-                h_mma(dh, h_desc2(a_lo, hi_a), h_desc2(bc0 + 2 * s * (lbo_cls >> 4), hi_b), idesc_cls, accum);
-                h_mma(dh + ncp, h_desc2(a_lo + kATower / 16, hi_a), h_desc2(br0 + 2 * s * (lbo_reg >> 4), hi_b), idesc_reg, accum);
-              }
-            }
-          }
           if ((A.exp & 64) && h_elect()) {   // no MMAs at all: the barrier protocol alone
           }
-          if ((A.exp & (48 | 64)) && h_elect()) {
+          if ((A.exp & 64) && h_elect()) {
             h_commit(empty_b(sb));
             if (tap == 8) h_commit(empty_a(sa));
-            if (tap == 8 && kc == kNKC - 1) h_commit(t_full(acc));
+            if (tap == 8 && kc == kNKC - 1) h_commit(t_full(fb));
           }
-          if (!(A.exp & (48 | 64)))
+          if (!(A.exp & 64))
 #endif
           if (h_elect()) {
 #pragma unroll
@@ -354,7 +332,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
               for (int h = 0; h < 2; ++h) {         // left / right 8-pixel half of the patch: M = 16 rows x 8 pixels
                 if (h == 1 && !right_half) continue;
                 const uint32_t accum = (kc | tap | s) ? 1u : 0u;
-                const uint32_t dh = d0 + h * (ncp + kRegPad);
+                const uint32_t dh = dbuf[h];
                 const uint32_t a_lo = a0 + (2 * s * kAPlane + h * 128) / 16;
 #ifdef ERD_HEAD_EXP
                 if (!(A.exp & 8))
@@ -368,7 +346,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
             }
             h_commit(empty_b(sb));
             if (tap == 8) h_commit(empty_a(sa));
-            if (tap == 8 && kc == kNKC - 1) h_commit(t_full(acc));
+            if (tap == 8 && kc == kNKC - 1) h_commit(t_full(fb));
           }
           __syncwarp();
         }
@@ -385,18 +363,21 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
       const HTile b = h_tile(A, t);
       const int H = g.h[b.l], W = g.w[b.l], HW = H * W;
       const float scale = A.scale[b.l];
-      const int acc = itile % A.n_acc;
-      h_wait(t_full(acc), (itile / A.n_acc) & 1u);
+      h_wait(t_full(itile & 1), (itile >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       double sums[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
-        if (h == 1 && b.x0 + 8 >= W) break;   // no pixel there: no MMA was issued for this half (warp-uniform)
+        const uint32_t hb = (2 * itile + h) % A.n_hbuf;
+        if (h == 1 && b.x0 + 8 >= W) {   // no pixel there: no MMA was issued for this half (warp-uniform)
+          if (lane == 0) h_arrive(t_empty(hb));
+          break;
+        }
         const int mrow = 32 * q + lane;
         const int y = b.y0 + (mrow >> 3), x = b.x0 + 8 * h + (mrow & 7);
         const bool in = y < H && x < W;
         const int hw = y * W + x;
-        const uint32_t taddr = tmem + acc * A.acc_stride + h * (ncp + kRegPad) + ((uint32_t)(32 * q) << 16);
+        const uint32_t taddr = tmem + hb * A.h_stride + ((uint32_t)(32 * q) << 16);
         float* oc = A.emit && in ? A.o_cls.p[b.l] + (size_t)b.n * ori * HW + hw : nullptr;
         float* ob = A.emit && in ? A.o_box.p[b.l] + (size_t)b.n * kBoxCh * HW + hw : nullptr;
         // class logits: first maximum (argmax semantics of torch.max, gfl_head_increment_erd.py:194-195)
@@ -489,6 +470,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
           }
           if (in) ws.t_slot[ga] = myslot;
         }
+        // every lane's TMEM reads of this half are complete (h_ld8 waits): hand its buffer back to the MMA thread now,
+        // the rest of the half (cache, sums) works from registers
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) h_arrive(t_empty(hb));
         if (in) {
           sums[0] += (double)m;
           sums[1] += (double)m * (double)m;
@@ -500,10 +486,6 @@ __global__ void __launch_bounds__(kHeadThreads, 1) teacher_head_kernel(Geo g, Wo
           ws.t_dist[ga] = make_float4(dist[0], dist[1], dist[2], dist[3]);
         }
       }
-      // every lane's TMEM reads of this buffer are complete (h_ld8 waits): hand it back to the MMA thread
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) h_arrive(t_empty(acc));
 #pragma unroll
       for (int i = 0; i < 4; ++i) sums[i] = warp_sum(sums[i]);
       if (lane < 4) {
@@ -587,12 +569,10 @@ cudaError_t launch_teacher_head(const Geo& g, const Workspace& ws, const Ptr5& f
   A.tiles_per_img = tiles;
   A.total_tiles = tiles * g.n_img;
   A.stash_pitch = stash_pitch(g.ori);
-  A.acc_stride = 2 * (A.ncls_pad + kRegPad);
-  if (A.acc_stride > 512) return cudaErrorInvalidValue;
-  A.n_acc = 2 * A.acc_stride <= 512 ? 2 : 1;
-#ifdef ERD_HEAD_EXP
-  if (A.exp & 32) A.n_acc = 1;
-#endif
+  A.h_stride = A.ncls_pad + kRegPad;
+  if (2 * A.h_stride > 512) return cudaErrorInvalidValue;
+  A.n_hbuf = 512 / A.h_stride;   // 4: a whole patch ahead (ori <= 48), 3: half a patch ahead (ori <= 80), 2: none
+  if (A.n_hbuf > 4) A.n_hbuf = 4;
   A.b_stage_bytes = (A.ncls_pad + kRegPad) * 128;
   const size_t fixed = (size_t)kAStages * kAStageBytes + (size_t)(A.ncls_pad + kRegPad) * 4 + (((size_t)g.n_img * 4 + 15) & ~(size_t)15);
   A.b_stages = kBStages;
